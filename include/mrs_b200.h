@@ -1,0 +1,203 @@
+/* mrs_b200.h -- C ABI of the B200-native mrs-gym step path (libmrs_b200.so).
+ *
+ * The reference (Acciorocketships/mrs-gym) has no FFI: its hot path sits behind the Python
+ * class MRS (mrsgym/MRS.py:12) and crosses into C only through ~22+N pybullet calls per
+ * agent per step.  This header is the seam a maintainer would bind instead (ctypes stub in
+ * INTEGRATION.md); each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer is CALLER-OWNED (the library never
+ *     allocates or frees device memory), all work is ordered on the passed CUDA stream
+ *     (a cudaStream_t passed as void*), no hidden synchronisation (except mrs_step_host);
+ *   - int return: 0 = OK, <0 = MrsError (mrs_strerror); no C++ exceptions cross the ABI;
+ *   - thread-safe for distinct buffer sets; one host thread per GPU.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns
+ *     MRS_ERR_CUDA.
+ *
+ * Layout in HBM (S = E*N agent slots, s = e*N + a):
+ *   state  float[13][S]   SoA planes: pos xyz | quat xyzw | vel xyz | angvel xyz (world)
+ *   ctrl   float[18][S]   PID planes: int_ori 0-2 | int_pos 3-5 | int_vel 6-8 |
+ *                         last_vel_e 9-11 | d_vel_e 12-14 | last_target_vel 15-17.
+ *                         last_vel_e.x = NaN marks "controller never called"
+ *                         (QuadControl's hasattr laziness, mrsgym/QuadControl.py:55-61).
+ *   rpm    float[4][S]    last rotor speeds (Quadcopter.speeds), optional (may be NULL)
+ *   X_tape float[L][E][N][D], A_tape float[L][E][N][N]   observation history tapes: the
+ *                         host writes slot p-1 at each step (descending) so that slots
+ *                         [p, p+K] are the reference's newest-first K_HOPS+1 window
+ *                         (mrsgym/MRS.py:87-114) with no per-step copy.
+ *   scratch float[6][S]   only for N > 32 (unconstrained velocities + pre-step positions)
+ */
+#ifndef MRS_B200_H
+#define MRS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRS_ABI_VERSION 1
+#define MRS_STATE_PLANES 13
+#define MRS_CTRL_PLANES 18
+#define MRS_STATS_SLOTS 8
+
+/* ACTION_TYPE strings of the reference are method names dispatched by getattr
+ * (mrsgym/Environment.py:92 -> mrsgym/Quadcopter.py:26-65). */
+typedef enum {
+    MRS_SET_TARGET_VEL = 0,   /* Quadcopter.set_target_vel   Quadcopter.py:53-55  */
+    MRS_SET_TARGET_POS = 1,   /* Quadcopter.set_target_pos   Quadcopter.py:58-60  */
+    MRS_SET_TARGET_ACCEL = 2, /* Quadcopter.set_target_accel Quadcopter.py:48-50  */
+    MRS_SET_FORCE = 3,        /* README "set_force" := set_target_accel(F/Mass)   */
+    MRS_SET_TARGET_ORI = 4,   /* Quadcopter.set_target_ori   Quadcopter.py:63-65  */
+    MRS_SET_CONTROL = 5,      /* Quadcopter.set_control      Quadcopter.py:26-34  */
+    MRS_SET_SPEEDS = 6,       /* Quadcopter.set_speeds       Quadcopter.py:38-45  */
+    MRS_NO_ACTION = 7         /* MRS.step(actions=None): no forces (MRS.py:243)   */
+} MrsActionType;
+
+/* Built-in fused state_fn layouts (user state_fn: MRS.py:16, Environment.py:84-87). */
+typedef enum {
+    MRS_X_NONE = 0,           /* X written by the caller (python state_fn)        */
+    MRS_X_POS_VEL = 1,        /* D=6  cat(get_pos, get_vel)  README.md:28-29      */
+    MRS_X_FULL = 2            /* D=13 pos, quat, vel, angvel                      */
+} MrsStateLayout;
+
+typedef enum {
+    MRS_OK = 0,
+    MRS_ERR_ARG = -1,
+    MRS_ERR_CUDA = -2,
+    MRS_ERR_UNSUPPORTED = -3
+} MrsError;
+
+/* status word bits (device, sticky; the host reads them lazily) */
+#define MRS_STATUS_NAN_ACTION 1u   /* mirrors the NaN guard of mrsgym/MRS.py:247-248 */
+#define MRS_STATUS_NONFINITE 2u    /* a state component left the finite range        */
+
+/* stats slots (unsigned long long, device; summed across GPUs per rollout) */
+#define MRS_STAT_AGENT_CONTACTS 0  /* sphere-sphere contact rows that pushed         */
+#define MRS_STAT_GROUND_CONTACTS 1
+#define MRS_STAT_NONFINITE 2
+#define MRS_STAT_NAN_ACTIONS 3
+
+/* cf2x.urdf properties (mrsgym/models/cf2x.urdf:5,11-12,42-78), the derived ones of
+ * Quadcopter.calculate_parameters (Quadcopter.py:153-168) and the QuadControl gains
+ * (QuadControl.py:14-32). */
+typedef struct {
+    float mass, ixx, iyy, izz;           /* file inertia: set_control scaling only */
+    float kf, km, arm;
+    float gnd_eff_coeff, prop_radius, gnd_hclip;
+    float drag_xy, drag_z;
+    float dw1, dw2, dw3;
+    float prop_x[4], prop_y[4];
+    float pos_p, pos_i, pos_d;
+    float vel_p, vel_i, vel_d;
+    float ori_p[3], ori_i[3], ori_d[3];
+    float min_pwm, max_pwm, pwm2rpm_a, pwm2rpm_b;
+    float ctrl_dt, ctrl_gravity;         /* QuadControl always uses DefaultSim: 0.01 / 9.81 */
+    float mix_ainv[16];                  /* inverse of the 'x' mixer, Quadcopter.py:164-165 */
+    float mix_a[16];
+    float nnls_tab[16 * 16];             /* per active set: least-squares solve matrix */
+} MrsQuadParams;
+
+/* What p.stepSimulation() does to this scene (mrsgym/BulletSim.py:46-47); Bullet3 is not
+ * vendored in the reference: see oracle/bullet_model.py for the restated algorithm. */
+typedef struct {
+    float mass;
+    float inertia[3];                    /* AABB-box inertia Bullet uses without URDF_USE_INERTIA_FROM_FILE */
+    float lin_damping, ang_damping;
+    float max_coord_vel;
+    int gyro;
+    float ang_motion_threshold;
+    float erp2, slop, contact_margin;
+    float mu_ground, ground_z;
+    float col_radius, col_halfheight, col_margin;
+    int ground_contact, agent_contact;
+    float agent_radius;                  /* MRS.AGENT_RADIUS, MRS.py:28 */
+} MrsPhysicsParams;
+
+typedef struct {
+    int E, N, K, L;                      /* envs (this GPU's shard), agents/env, K_HOPS, tape slots */
+    int action_type;                     /* MrsActionType */
+    int state_layout;                    /* MrsStateLayout */
+    float dt, gravity;                   /* BulletSim.DT / GRAVITY, BulletSim.py:13-14 */
+    float comm_range;                    /* MRS.COMM_RANGE (inf => ones - eye), MRS.py:117-124 */
+    MrsQuadParams quad;
+    MrsPhysicsParams phys;
+} MrsConfig;
+
+typedef struct {
+    float* state;                        /* [13][S] */
+    float* ctrl;                         /* [18][S] */
+    float* rpm;                          /* [4][S] or NULL */
+    float* X_tape;                       /* [L][E][N][D] or NULL */
+    float* A_tape;                       /* [L][E][N][N] or NULL */
+    float* scratch;                      /* [6][S], needed iff N > 32 */
+    unsigned int* status;                /* [1] */
+    unsigned long long* stats;           /* [MRS_STATS_SLOTS] */
+} MrsBuffers;
+
+int mrs_abi_version(void);
+const char* mrs_strerror(int err);
+
+/* D of a built-in layout (0 for MRS_X_NONE). */
+int mrs_state_dim(int state_layout);
+/* ACTION_DIM of an action type. */
+int mrs_action_dim(int action_type);
+
+/* sizeof(MrsConfig) / sizeof(MrsBuffers) as compiled: lets a foreign binding check its mirror. */
+size_t mrs_sizeof_config(void);
+size_t mrs_sizeof_buffers(void);
+
+/* Fills quad/phys/dt/gravity with the reference's constants (cf2x.urdf, QuadControl gains,
+ * BulletSim defaults) and the mixer tables.  E,N,K,L,action_type,... are left to the caller.
+ * Replaces Quadcopter.read_attributes/calculate_parameters (Quadcopter.py:119-168). */
+int mrs_default_config(MrsConfig* cfg);
+
+/* One env.step for all E envs: actions -> controller -> rotor wrench + aero (ground
+ * effect, drag, downwash) -> Bullet step (contact) -> newest X slice into X tape slot
+ * `slot_x`, newest A slice into A tape slot `slot_a` (the reference shifts its X and A deques
+ * independently, MRS.py:87-114).  actions: device float[E][N][ACTION_DIM] (ignored for
+ * MRS_NO_ACTION).
+ * Replaces MRS.step's set_actions + step_sim + calc_Xk + calc_Ak (MRS.py:252-257). */
+int mrs_step(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int slot_x, int slot_a,
+             void* stream);
+
+/* T consecutive steps in one call (N <= 32: one launch, state stays in registers); step t
+ * reads actions[t] (device float[T][E][N][ACTION_DIM]) and writes tape slots
+ * slot_x_first - t / slot_a_first - t.  The rollout loop of
+ * examples/simulating_data/helper/DataGenerator.py:8-48 with pre-computed actions. */
+int mrs_step_many(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T,
+                  int slot_x_first, int slot_a_first, void* stream);
+
+/* Observation only: X (state layout) and/or A (adjacency) of the CURRENT state into tape
+ * slot `slot`.  Replaces MRS.calc_Xk / MRS.calc_Ak+calc_A (MRS.py:87-124) outside step. */
+int mrs_observe(const MrsConfig* cfg, const MrsBuffers* bufs, int slot, int write_X, int write_A,
+                void* stream);
+
+/* Adjacency of arbitrary float32 positions: pos device float[E][N][3] -> A float[E][N][N].
+ * MRS.calc_A (MRS.py:117-124): bit-exact with torch CPU on identical positions. */
+int mrs_adjacency(const MrsConfig* cfg, const float* pos, float* A, void* stream);
+
+/* Upload start states: device float[E][N][3] each (ori = euler 'xyz' roll,pitch,yaw), NULL
+ * pointer = keep that component; env_mask device uint8[E] or NULL (= all envs).  PID state
+ * is NOT reset (reference quirk).
+ * Replaces Environment.set_state -> Object.set_state (Environment.py:97-103, Object.py:42-65). */
+int mrs_set_state(const MrsConfig* cfg, const MrsBuffers* bufs, const float* pos, const float* ori_euler,
+                  const float* vel, const float* angvel, const unsigned char* env_mask, void* stream);
+
+/* Tape maintenance.  which: 1 = X, 2 = A.  Copies slot src into `count` slots starting at
+ * dst_first (src < 0: fill with zeros).  Used for the reference's ring padding after
+ * reset (X: copies of X0, A: zeros; MRS.py:92-93,107-108) and for window compaction. */
+int mrs_tape_fill(const MrsConfig* cfg, const MrsBuffers* bufs, int which, int src, int dst_first,
+                  int count, void* stream);
+
+/* End-to-end step over HOST buffers (pinned recommended): H2D actions, mrs_step, D2H of the
+ * newest X slice ([E][N][D]) and A slice ([E][N][N]); X_host / A_host may be NULL.
+ * dev_actions: caller-owned device staging float[E][N][ACTION_DIM].  Synchronises the
+ * stream before returning (the reference's step is synchronous). */
+int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host,
+                  float* dev_actions, float* X_host, float* A_host, int slot_x, int slot_a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRS_B200_H */

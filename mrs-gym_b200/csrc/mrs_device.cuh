@@ -1,0 +1,378 @@
+// Per-agent device math of the mrs-gym step path (sm_100a).  fp32 throughout, no fast-math:
+// the adjacency must be bit-exact and the dynamics must hold 1e-4 relative on one-step deltas.
+//
+// Reference being reproduced (files under /root/reference/mrsgym):
+//   QuadControl.py:35-127   cascaded PID (pos -> vel -> accel -> attitude -> pwm -> rpm)
+//   Quadcopter.py:26-65     action modes, Quadcopter.py:172-208 nnlsRPM mixer
+//   Quadcopter.py:38-45     rotor thrust / yaw torque, Quadcopter.py:69-115 aero "dynamics"
+//   BulletSim.py:46-47      p.stepSimulation (Bullet3 semantics: oracle/bullet_model.py)
+// The controller works on rotation matrices straight from the quaternion (the reference's
+// matrix->euler->matrix round trips are identity maps on SO(3)).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "mrs_b200.h"
+
+namespace mrs {
+
+struct Agent {
+    float px, py, pz;
+    float qx, qy, qz, qw;
+    float vx, vy, vz;
+    float wx, wy, wz;
+};
+
+// PID planes touched per mode (the rest of the 18 ctrl planes stay untouched in HBM)
+struct Ctrl {
+    float io[3];   // integral_ori_e
+    float ip[3];   // integral_pos_e
+    float iv[3];   // integral_vel_e
+    float lve[3];  // last_vel_e (x = NaN: never called)
+    float dve[3];  // d_vel_e
+    float ltv[3];  // last_target_vel
+};
+
+template <int MODE> struct ModeTraits;
+template <> struct ModeTraits<MRS_SET_TARGET_VEL>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = true;  };
+template <> struct ModeTraits<MRS_SET_TARGET_POS>   { static constexpr int A = 3; static constexpr bool io = true,  ip = true,  vel = false; };
+template <> struct ModeTraits<MRS_SET_TARGET_ACCEL> { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false; };
+template <> struct ModeTraits<MRS_SET_FORCE>        { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false; };
+template <> struct ModeTraits<MRS_SET_TARGET_ORI>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false; };
+template <> struct ModeTraits<MRS_SET_CONTROL>      { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false; };
+template <> struct ModeTraits<MRS_SET_SPEEDS>       { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false; };
+template <> struct ModeTraits<MRS_NO_ACTION>        { static constexpr int A = 0; static constexpr bool io = false, ip = false, vel = false; };
+
+__host__ __device__ __forceinline__ int state_dim(int layout) {
+    return layout == MRS_X_POS_VEL ? 6 : (layout == MRS_X_FULL ? 13 : 0);
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// body->world rotation, row-major R[3*i+j], from an xyzw unit quaternion
+__device__ __forceinline__ void quat_to_mat(const Agent& s, float* R) {
+    const float x = s.qx, y = s.qy, z = s.qz, w = s.qw;
+    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - z * w);       R[2] = 2.f * (x * z + y * w);
+    R[3] = 2.f * (x * y + z * w);       R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - x * w);
+    R[6] = 2.f * (x * z - y * w);       R[7] = 2.f * (y * z + x * w);       R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+// ------------------------------------------------------------------------------------------
+// QuadControl.attitude_control (QuadControl.py:93-127) on matrices.  Rt = target rotation
+// (columns t0 t1 t2, row-major like R), ta = target acceleration incl. gravity.
+__device__ __forceinline__ void attitude_control(const MrsQuadParams& q, const float* R, const float* Rt,
+                                                 const float* ta, const Agent& s, float* io, float* rpm) {
+    // rot_matrix_e = Rt^T R - R^T Rt ; rot_e = [e21, e02, e10]
+    float re[3];
+    re[0] = (Rt[2] * R[1] + Rt[5] * R[4] + Rt[8] * R[7]) - (R[2] * Rt[1] + R[5] * Rt[4] + R[8] * Rt[7]);
+    re[1] = (Rt[0] * R[2] + Rt[3] * R[5] + Rt[6] * R[8]) - (R[0] * Rt[2] + R[3] * Rt[5] + R[6] * Rt[8]);
+    re[2] = (Rt[1] * R[0] + Rt[4] * R[3] + Rt[7] * R[6]) - (R[1] * Rt[0] + R[4] * Rt[3] + R[7] * Rt[6]);
+    const float we[3] = {-s.wx, -s.wy, -s.wz};   // target_angvel(0) - world angvel
+    float tt[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = clampf(io[k] - re[k] * q.ctrl_dt, -1500.f, 1500.f);
+        if (k < 2) v = clampf(v, -1.f, 1.f);
+        io[k] = v;
+        tt[k] = clampf(-q.ori_p[k] * re[k] + q.ori_i[k] * v + q.ori_d[k] * we[k], -3200.f, 3200.f);
+    }
+    const float nrm = sqrtf(ta[0] * ta[0] + ta[1] * ta[1] + ta[2] * ta[2]);
+    float scalar_thrust = 0.f;
+    if (nrm != 0.f) {
+        const float cosang = (ta[0] * R[2] + ta[1] * R[5] + ta[2] * R[8]) / nrm;
+        scalar_thrust = nrm * q.mass / fmaxf(cosang, 0.2f);
+    }
+    const float thrust = (sqrtf(scalar_thrust / (4.f * q.kf)) - q.pwm2rpm_b) / q.pwm2rpm_a;
+    // MixerMatrix rows (QuadControl.py:26): [.5,-.5,-1] [.5,.5,1] [-.5,.5,-1] [-.5,-.5,1]
+    const float m0 = 0.5f * tt[0], m1 = 0.5f * tt[1], m2 = tt[2];
+    float pwm[4] = {thrust + m0 - m1 - m2, thrust + m0 + m1 + m2, thrust - m0 + m1 - m2, thrust - m0 - m1 + m2};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rpm[i] = q.pwm2rpm_a * clampf(pwm[i], q.min_pwm, q.max_pwm) + q.pwm2rpm_b;
+}
+
+// QuadControl.accel_control (QuadControl.py:73-90): target frame z = a/|a|,
+// x = R[:,1] x z, y = z x x, columns normalised (= scipy from_matrix on orthogonal columns).
+__device__ __forceinline__ void accel_control(const MrsQuadParams& q, const float* R, const float* a_in,
+                                              const Agent& s, float* io, float* rpm) {
+    const float ta[3] = {a_in[0], a_in[1], a_in[2] + q.ctrl_gravity};
+    const float n2 = ta[0] * ta[0] + ta[1] * ta[1] + ta[2] * ta[2];
+    float z[3] = {0.f, 0.f, 1.f};
+    if (n2 > 0.f) {   // |a| == 0 -> NaN -> [0,0,1] in the reference
+        const float inv = 1.f / sqrtf(n2);
+        z[0] = ta[0] * inv; z[1] = ta[1] * inv; z[2] = ta[2] * inv;
+    }
+    // x = R[:,1] x z
+    float x[3] = {R[4] * z[2] - R[7] * z[1], R[7] * z[0] - R[1] * z[2], R[1] * z[1] - R[4] * z[0]};
+    const float xi = 1.f / sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    x[0] *= xi; x[1] *= xi; x[2] *= xi;
+    const float y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+    const float Rt[9] = {x[0], y[0], z[0], x[1], y[1], z[1], x[2], y[2], z[2]};
+    attitude_control(q, R, Rt, ta, s, io, rpm);
+}
+
+// rotation matrix of scipy euler 'xyz' (extrinsic) = Rz(yaw) Ry(pitch) Rx(roll)
+__device__ __forceinline__ void euler_to_mat(float roll, float pitch, float yaw, float* M) {
+    float sr, cr, sp, cp, sy, cy;
+    sincosf(roll, &sr, &cr); sincosf(pitch, &sp, &cp); sincosf(yaw, &sy, &cy);
+    M[0] = cy * cp; M[1] = cy * sp * sr - sy * cr; M[2] = cy * sp * cr + sy * sr;
+    M[3] = sy * cp; M[4] = sy * sp * sr + cy * cr; M[5] = sy * sp * cr - cy * sr;
+    M[6] = -sp;     M[7] = cp * sr;                M[8] = cp * cr;
+}
+
+// nnlsRPM (Quadcopter.py:172-208).  The 4x4 NNLS is solved by enumerating the 16 active
+// sets: the optimum is the primal-feasible subset solution of least residual.
+__device__ __noinline__ void nnls_enumerate(const MrsQuadParams& q, const float* B, float* sq) {
+    float best = INFINITY;
+    for (int m = 0; m < 16; ++m) {
+        float x[4];
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float* t = q.nnls_tab + m * 16 + i * 4;
+            x[i] = t[0] * B[0] + t[1] * B[1] + t[2] * B[2] + t[3] * B[3];
+            ok = ok && (x[i] >= 0.f);
+        }
+        if (!ok) continue;
+        float res = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float* a = q.mix_a + r * 4;
+            const float d = a[0] * x[0] + a[1] * x[1] + a[2] * x[2] + a[3] * x[3] - B[r];
+            res += d * d;
+        }
+        if (res < best) {
+            best = res;
+            sq[0] = x[0]; sq[1] = x[1]; sq[2] = x[2]; sq[3] = x[3];
+        }
+    }
+}
+
+__device__ __forceinline__ void set_control(const MrsQuadParams& q, const float* act, float* rpm) {
+    const float inv_kfl = 1.f / (q.kf * q.arm);
+    const float B[4] = {act[0] * q.mass / q.kf, act[1] * q.ixx * inv_kfl, act[2] * q.iyy * inv_kfl,
+                        act[3] * q.izz / q.km};
+    float sq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float* a = q.mix_ainv + i * 4;
+        sq[i] = a[0] * B[0] + a[1] * B[1] + a[2] * B[2] + a[3] * B[3];
+    }
+    if (fminf(fminf(sq[0], sq[1]), fminf(sq[2], sq[3])) < 0.f) nnls_enumerate(q, B, sq);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rpm[i] = sqrtf(sq[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// action -> rpm for one agent (Quadcopter.set_* -> QuadControl.*).
+template <int MODE>
+__device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Agent& s, const float* R, const float* act,
+                                              Ctrl& k, float* rpm) {
+    const MrsQuadParams& q = c.quad;
+    if constexpr (MODE == MRS_SET_SPEEDS) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rpm[i] = act[i];
+    } else if constexpr (MODE == MRS_SET_CONTROL) {
+        set_control(q, act, rpm);
+    } else if constexpr (MODE == MRS_SET_TARGET_ORI) {
+        float Rt[9];
+        euler_to_mat(act[0], act[1], act[2], Rt);
+        const float ta[3] = {0.f, 0.f, 9.81f};   // literal in Quadcopter.py:64
+        attitude_control(q, R, Rt, ta, s, k.io, rpm);
+    } else if constexpr (MODE == MRS_SET_TARGET_ACCEL) {
+        accel_control(q, R, act, s, k.io, rpm);
+    } else if constexpr (MODE == MRS_SET_FORCE) {
+        const float a[3] = {act[0] / q.mass, act[1] / q.mass, act[2] / q.mass};
+        accel_control(q, R, a, s, k.io, rpm);
+    } else if constexpr (MODE == MRS_SET_TARGET_POS) {
+        // QuadControl.pos_control (QuadControl.py:35-48)
+        const float p[3] = {s.px, s.py, s.pz}, v[3] = {s.vx, s.vy, s.vz};
+        float a[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float e = act[i] - p[i];
+            k.ip[i] = k.ip[i] + e * q.ctrl_dt;
+            a[i] = q.pos_p * e + q.pos_i * k.ip[i] + q.pos_d * (0.f - v[i]);
+        }
+        accel_control(q, R, a, s, k.io, rpm);
+    } else if constexpr (MODE == MRS_SET_TARGET_VEL) {
+        // QuadControl.vel_control (QuadControl.py:51-70)
+        const float v[3] = {s.vx, s.vy, s.vz};
+        const bool first = isnan(k.lve[0]);
+        float a[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float e = act[i] - v[i];
+            const float le = first ? e : k.lve[i];
+            const float lt = first ? act[i] : k.ltv[i];
+            const float d0 = first ? 0.f : k.dve[i];
+            const float d = (((e - le) - (act[i] - lt)) / q.ctrl_dt) * 0.5f + d0 * 0.5f;
+            k.dve[i] = d;
+            k.lve[i] = e;
+            k.ltv[i] = act[i];
+            k.iv[i] = k.iv[i] + e * q.ctrl_dt;
+            a[i] = q.vel_p * e + q.vel_i * k.iv[i] + q.vel_d * d;
+        }
+        accel_control(q, R, a, s, k.io, rpm);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rpm[i] = 0.f;
+    }
+}
+
+// One pair of the downwash loop (Quadcopter.py:99-115), float32 like the reference:
+// returns the body-z force on agent i caused by agent j (rel = p_j - p_i).
+// Early-out: when 0.5*(dxy/beta)^2 > 104 the reference's float32 exp() underflows to 0
+// (denormal at worst, |force| < 1e-40 N), so the divisions and the exp are skipped.
+__device__ __forceinline__ float downwash_pair(const MrsQuadParams& q, float rx, float ry, float rz) {
+    const float dxy2 = rx * rx + ry * ry;
+    if (!(rz > 0.f && dxy2 < 100.f)) return 0.f;
+    const float beta = q.dw2 * rz + q.dw3;
+    if (dxy2 > 208.f * beta * beta) return 0.f;
+    const float dxy = sqrtf(dxy2);
+    const float r = (1.f / (4.f * rz)) * q.prop_radius;
+    const float alpha = q.dw1 * (r * r);
+    const float qq = (1.f / beta) * dxy;
+    return -alpha * expf(-0.5f * (qq * qq));
+}
+
+// rotor thrust + yaw torque (Quadcopter.py:38-45), ground effect / drag (Quadcopter.py:69-98),
+// downwash sum `dw` -> Bullet unconstrained velocity update (bullet_model.unconstrained_velocities).
+// Overwrites s.v / s.w with the unconstrained velocities v*, w*.
+template <bool FORCES>
+__device__ __forceinline__ void apply_wrench(const MrsConfig& c, Agent& s, const float* R, const float* rpm, float dw) {
+    const MrsQuadParams& q = c.quad;
+    const MrsPhysicsParams& ph = c.phys;
+    float Fb[3] = {0.f, 0.f, 0.f}, Tb[3] = {0.f, 0.f, 0.f};
+    if constexpr (FORCES) {
+        float w2[4], fz = 0.f;
+        const bool gnd_ok = (R[8] > 0.f) || (R[7] < 0.f);   // roll < pi/2 (pitch < pi/2 always)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            w2[i] = rpm[i] * rpm[i];
+            float f = w2[i] * q.kf;
+            if (gnd_ok) {
+                const float h = fmaxf(s.pz + R[6] * q.prop_x[i] + R[7] * q.prop_y[i], q.gnd_hclip);
+                const float rr = q.prop_radius / (4.f * h);
+                f += w2[i] * q.kf * q.gnd_eff_coeff * (rr * rr);
+            }
+            fz += f;
+            Tb[0] += q.prop_y[i] * f;
+            Tb[1] -= q.prop_x[i] * f;
+        }
+        Tb[2] = q.km * (-w2[0] + w2[1] - w2[2] + w2[3]);
+        // drag = R (c * v) applied again in the link frame
+        const float ssum = (2.f * 3.14159265358979323846f / 60.f) * (rpm[0] + rpm[1] + rpm[2] + rpm[3]);
+        const float cx = -q.drag_xy * ssum * s.vx, cy = -q.drag_xy * ssum * s.vy, cz = -q.drag_z * ssum * s.vz;
+        Fb[0] = R[0] * cx + R[1] * cy + R[2] * cz;
+        Fb[1] = R[3] * cx + R[4] * cy + R[5] * cz;
+        Fb[2] = R[6] * cx + R[7] * cy + R[8] * cz + fz + dw;
+    }
+    // linear: a = R Fb / m - g z - v (k + k|v|)
+    const float im = 1.f / ph.mass;
+    const float vn = sqrtf(s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);
+    const float kl = ph.lin_damping + ph.lin_damping * vn;
+    const float ax = (R[0] * Fb[0] + R[1] * Fb[1] + R[2] * Fb[2]) * im - s.vx * kl;
+    const float ay = (R[3] * Fb[0] + R[4] * Fb[1] + R[5] * Fb[2]) * im - s.vy * kl;
+    const float az = (R[6] * Fb[0] + R[7] * Fb[1] + R[8] * Fb[2]) * im - c.gravity - s.vz * kl;
+    // angular in the body frame: I wdot = tau - w x Iw - Iw (k + k|w|)
+    const float wb[3] = {R[0] * s.wx + R[3] * s.wy + R[6] * s.wz, R[1] * s.wx + R[4] * s.wy + R[7] * s.wz,
+                         R[2] * s.wx + R[5] * s.wy + R[8] * s.wz};
+    const float Iw[3] = {ph.inertia[0] * wb[0], ph.inertia[1] * wb[1], ph.inertia[2] * wb[2]};
+    const float wn = sqrtf(wb[0] * wb[0] + wb[1] * wb[1] + wb[2] * wb[2]);
+    const float ka = ph.ang_damping + ph.ang_damping * wn;
+    float rhs[3] = {Tb[0] - Iw[0] * ka, Tb[1] - Iw[1] * ka, Tb[2] - Iw[2] * ka};
+    if (ph.gyro) {
+        rhs[0] -= wb[1] * Iw[2] - wb[2] * Iw[1];
+        rhs[1] -= wb[2] * Iw[0] - wb[0] * Iw[2];
+        rhs[2] -= wb[0] * Iw[1] - wb[1] * Iw[0];
+    }
+    const float wd[3] = {rhs[0] / ph.inertia[0], rhs[1] / ph.inertia[1], rhs[2] / ph.inertia[2]};
+    const float mv = ph.max_coord_vel;
+    s.vx = clampf(s.vx + c.dt * ax, -mv, mv);
+    s.vy = clampf(s.vy + c.dt * ay, -mv, mv);
+    s.vz = clampf(s.vz + c.dt * az, -mv, mv);
+    s.wx = clampf(s.wx + c.dt * (R[0] * wd[0] + R[1] * wd[1] + R[2] * wd[2]), -mv, mv);
+    s.wy = clampf(s.wy + c.dt * (R[3] * wd[0] + R[4] * wd[1] + R[5] * wd[2]), -mv, mv);
+    s.wz = clampf(s.wz + c.dt * (R[6] * wd[0] + R[7] * wd[1] + R[8] * wd[2]), -mv, mv);
+}
+
+// contact row right-hand side (bullet_model._contact_rhs)
+__device__ __forceinline__ float contact_rhs(const MrsPhysicsParams& ph, float dist, float vn, float dt) {
+    const float pen = dist + ph.slop;
+    const float rhs = (pen > 0.f) ? (-vn - pen / dt) : (-vn - pen * ph.erp2 / dt);
+    return fmaxf(rhs, 0.f);
+}
+
+// sphere-sphere contact of agent i with agent j (bullet_model.agent_contact_dv): d = p_i - p_j,
+// dv = v*_i - v*_j; returns true and adds this row's velocity change to acc when it pushes.
+__device__ __forceinline__ bool agent_contact_pair(const MrsPhysicsParams& ph, float dt, float dx, float dy, float dz,
+                                                   float dvx, float dvy, float dvz, float* acc) {
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    const float lim = 2.f * ph.agent_radius + ph.contact_margin;
+    if (!(d2 < lim * lim) || !(d2 > 0.f)) return false;
+    const float d = sqrtf(d2);
+    const float inv = 1.f / d;
+    const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
+    const float vn = dvx * nx + dvy * ny + dvz * nz;
+    const float rhs = 0.5f * contact_rhs(ph, d - 2.f * ph.agent_radius, vn, dt);
+    acc[0] += rhs * nx; acc[1] += rhs * ny; acc[2] += rhs * nz;
+    return rhs > 0.f;
+}
+
+// ground plane vs the quad's collision cylinder, impulse at the CoM (bullet_model.ground_contact)
+__device__ __forceinline__ bool ground_contact(const MrsPhysicsParams& ph, float dt, Agent& s) {
+    const float R22 = 1.f - 2.f * (s.qx * s.qx + s.qy * s.qy);
+    const float ext = ph.col_radius * sqrtf(fmaxf(1.f - R22 * R22, 0.f)) + ph.col_halfheight * fabsf(R22) + ph.col_margin;
+    const float dist = s.pz - ext - ph.ground_z;
+    if (!(dist < ph.contact_margin)) return false;
+    const float jn = contact_rhs(ph, dist, s.vz, dt);
+    const float vt = sqrtf(s.vx * s.vx + s.vy * s.vy);
+    const float scale = (vt > 0.f) ? fminf(vt, ph.mu_ground * jn) / vt : 0.f;
+    s.vz += jn;
+    s.vx -= s.vx * scale;
+    s.vy -= s.vy * scale;
+    return jn > 0.f;
+}
+
+// btMultiBody::stepPositionsMultiDof (bullet_model.integrate_positions)
+__device__ __forceinline__ void integrate(const MrsConfig& c, Agent& s) {
+    const float dt = c.dt;
+    s.px += dt * s.vx; s.py += dt * s.vy; s.pz += dt * s.vz;
+    float ang = sqrtf(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);
+    if (ang * dt > c.phys.ang_motion_threshold) ang = 0.5f * 1.57079632679489661923f / dt;
+    float k, cw;
+    if (ang < 0.001f) {
+        k = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang;
+        cw = cosf(0.5f * ang * dt);
+    } else {
+        float sn;
+        sincosf(0.5f * ang * dt, &sn, &cw);
+        k = sn / ang;
+    }
+    const float ax = s.wx * k, ay = s.wy * k, az = s.wz * k;
+    // q <- dq (x) q, xyzw
+    const float nx = cw * s.qx + ax * s.qw + ay * s.qz - az * s.qy;
+    const float ny = cw * s.qy - ax * s.qz + ay * s.qw + az * s.qx;
+    const float nz = cw * s.qz + ax * s.qy - ay * s.qx + az * s.qw;
+    const float nw = cw * s.qw - ax * s.qx - ay * s.qy - az * s.qz;
+    const float inv = 1.f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    s.qx = nx * inv; s.qy = ny * inv; s.qz = nz * inv; s.qw = nw * inv;
+}
+
+// MRS.calc_A pair (MRS.py:117-124), bit-exact with torch CPU float32 norm:
+// d = sqrt_rn(fma(dz,dz,fma(dy,dy,dx*dx))), A = d <= COMM_RANGE (NaN -> 0).
+// sqrt_rn is monotone, so d <= range  <=>  s <= s_max with s_max the largest float whose
+// correctly rounded root is <= range (computed on the host, adjacency_threshold()): the
+// comparison is done on the squared distance, bit-identical and without the sqrt.
+__device__ __forceinline__ float adjacency_pair(float xi, float yi, float zi, float xj, float yj, float zj, float s_max) {
+    const float dx = __fsub_rn(xi, xj), dy = __fsub_rn(yi, yj), dz = __fsub_rn(zi, zj);
+    const float s = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return (s <= s_max) ? 1.f : 0.f;
+}
+
+__device__ __forceinline__ bool agent_finite(const Agent& s) {
+    const float t = s.px + s.py + s.pz + s.qx + s.qy + s.qz + s.qw + s.vx + s.vy + s.vz + s.wx + s.wy + s.wz;
+    return isfinite(t);
+}
+
+}  // namespace mrs

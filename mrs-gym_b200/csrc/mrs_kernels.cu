@@ -1,0 +1,916 @@
+// mrs_kernels.cu -- sm_100a kernels + C ABI of the B200-native mrs-gym step path.
+//
+// Two execution shapes, chosen per call from N (agents per env):
+//
+//  * N <= 32  "group" path: one lane per agent, an env is a group of G = pow2ceil(N) lanes of one
+//    warp (N=8: 4 envs per warp).  Everything of MRS.step that touches the simulator is ONE kernel:
+//    action -> cascaded PID / mixer -> rotor wrench + ground effect + drag + downwash ->
+//    Bullet velocity update -> sphere / ground contact -> position + quaternion integration ->
+//    newest X slice + newest A slice.  The three intra-env pair passes (downwash on pre-step
+//    positions, contact on unconstrained velocities, adjacency on post-step positions) go through a
+//    per-warp shared-memory tile read with 128-bit LDS.  With T > 1 (mrs_step_many) the state stays
+//    in registers across steps, only actions stream in and X/A stream out.
+//
+//  * N > 32   "tiled" path: an env spans many CTAs, so the step is three kernels with the pair
+//    passes tiled n-body style through shared memory:  pre (forces -> v*, w*; copies pre-step
+//    positions to scratch), post (contact, integration, X), adjacency (row tile x column tile,
+//    coalesced 128-bit stores; this is a pure streaming store at N=4096).
+//
+// Reference behaviour: /root/reference/mrsgym/MRS.py:240-277 and callees (see mrs_device.cuh);
+// Bullet step restated in oracle/bullet_model.py.  No CPU fallback exists in this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "mrs_b200.h"
+#include "mrs_device.cuh"
+
+namespace mrs {
+
+constexpr int kBlock = 128;
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct StepArgs {
+    const float* actions;  // [T][E][N][A]
+    int T;
+    int slot_x, slot_a;    // step t writes X tape slot slot_x - t and A tape slot slot_a - t
+    int G;                 // group width (power of two >= N), group path only
+    int nchunks;           // warp-sized work items, group path only
+    float s_max;           // adjacency threshold on the squared distance (inf: ones - eye)
+    int comm_inf;
+};
+
+// ------------------------------------------------------------------------------ state planes
+__device__ __forceinline__ void load_agent(const float* __restrict__ st, size_t S, size_t s, Agent& a) {
+    a.px = st[0 * S + s]; a.py = st[1 * S + s]; a.pz = st[2 * S + s];
+    a.qx = st[3 * S + s]; a.qy = st[4 * S + s]; a.qz = st[5 * S + s]; a.qw = st[6 * S + s];
+    a.vx = st[7 * S + s]; a.vy = st[8 * S + s]; a.vz = st[9 * S + s];
+    a.wx = st[10 * S + s]; a.wy = st[11 * S + s]; a.wz = st[12 * S + s];
+}
+
+__device__ __forceinline__ void store_agent(float* __restrict__ st, size_t S, size_t s, const Agent& a) {
+    st[0 * S + s] = a.px; st[1 * S + s] = a.py; st[2 * S + s] = a.pz;
+    st[3 * S + s] = a.qx; st[4 * S + s] = a.qy; st[5 * S + s] = a.qz; st[6 * S + s] = a.qw;
+    st[7 * S + s] = a.vx; st[8 * S + s] = a.vy; st[9 * S + s] = a.vz;
+    st[10 * S + s] = a.wx; st[11 * S + s] = a.wy; st[12 * S + s] = a.wz;
+}
+
+__device__ __forceinline__ void dummy_agent(Agent& a) {
+    a.px = a.py = 0.f; a.pz = 1.0e3f;
+    a.qx = a.qy = a.qz = 0.f; a.qw = 1.f;
+    a.vx = a.vy = a.vz = 0.f;
+    a.wx = a.wy = a.wz = 0.f;
+}
+
+template <int MODE>
+__device__ __forceinline__ void load_ctrl(const float* __restrict__ ct, size_t S, size_t s, Ctrl& k) {
+    using MT = ModeTraits<MODE>;
+    if constexpr (MT::io) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) k.io[i] = ct[(0 + i) * S + s];
+    }
+    if constexpr (MT::ip) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) k.ip[i] = ct[(3 + i) * S + s];
+    }
+    if constexpr (MT::vel) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            k.iv[i] = ct[(6 + i) * S + s];
+            k.lve[i] = ct[(9 + i) * S + s];
+            k.dve[i] = ct[(12 + i) * S + s];
+            k.ltv[i] = ct[(15 + i) * S + s];
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void store_ctrl(float* __restrict__ ct, size_t S, size_t s, const Ctrl& k) {
+    using MT = ModeTraits<MODE>;
+    if constexpr (MT::io) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ct[(0 + i) * S + s] = k.io[i];
+    }
+    if constexpr (MT::ip) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ct[(3 + i) * S + s] = k.ip[i];
+    }
+    if constexpr (MT::vel) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            ct[(6 + i) * S + s] = k.iv[i];
+            ct[(9 + i) * S + s] = k.lve[i];
+            ct[(12 + i) * S + s] = k.dve[i];
+            ct[(15 + i) * S + s] = k.ltv[i];
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ bool load_action(const float* __restrict__ actions, size_t idx, float* act) {
+    constexpr int A = ModeTraits<MODE>::A;
+    if constexpr (A == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(actions) + idx);
+        act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+        return isnan(v.x) || isnan(v.y) || isnan(v.z) || isnan(v.w);
+    } else if constexpr (A == 3) {
+        const float* p = actions + idx * 3;
+        act[0] = __ldg(p); act[1] = __ldg(p + 1); act[2] = __ldg(p + 2); act[3] = 0.f;
+        return isnan(act[0]) || isnan(act[1]) || isnan(act[2]);
+    } else {
+        act[0] = act[1] = act[2] = act[3] = 0.f;
+        return false;
+    }
+}
+
+// newest X slice of one agent (Environment.get_X with the built-in state_fn layouts)
+__device__ __forceinline__ void write_X(float* __restrict__ Xs, int layout, size_t s, const Agent& a) {
+    if (layout == MRS_X_POS_VEL) {
+        float2* p = reinterpret_cast<float2*>(Xs + s * 6);
+        p[0] = make_float2(a.px, a.py);
+        p[1] = make_float2(a.pz, a.vx);
+        p[2] = make_float2(a.vy, a.vz);
+    } else if (layout == MRS_X_FULL) {
+        float* p = Xs + s * 13;
+        p[0] = a.px; p[1] = a.py; p[2] = a.pz;
+        p[3] = a.qx; p[4] = a.qy; p[5] = a.qz; p[6] = a.qw;
+        p[7] = a.vx; p[8] = a.vy; p[9] = a.vz;
+        p[10] = a.wx; p[11] = a.wy; p[12] = a.wz;
+    }
+}
+
+// ------------------------------------------------------------------------------ group path
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+step_group_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const StepArgs a) {
+    __shared__ float4 sh_pos[kBlock];
+    __shared__ float4 sh_vel[kBlock];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float4* wpos = sh_pos + wib * 32;
+    float4* wvel = sh_vel + wib * 32;
+    const int G = a.G, N = c.N, E = c.E;
+    const int gpw = 32 / G;
+    const int ai = lane & (G - 1);
+    const int gb = lane - ai;
+    const size_t S = (size_t)E * N;
+    const int wtotal = gridDim.x * kWarpsPerBlock;
+    const MrsPhysicsParams& ph = c.phys;
+    const float lim = 2.f * ph.agent_radius + ph.contact_margin;
+    const float lim2 = lim * lim;
+    const bool pair_contact = ph.agent_contact && N > 1;
+    const size_t xslot = S * (size_t)state_dim(c.state_layout);
+    const size_t aslot = S * (size_t)N;
+
+    for (int chunk = blockIdx.x * kWarpsPerBlock + wib; chunk < a.nchunks; chunk += wtotal) {
+        const long long e = (long long)chunk * gpw + (lane / G);
+        const bool valid = (e < E) && (ai < N);
+        const size_t s = valid ? (size_t)e * N + ai : 0;
+        Agent st;
+        Ctrl k;
+        if (valid) {
+            load_agent(b.state, S, s, st);
+            load_ctrl<MODE>(b.ctrl, S, s, k);
+        } else {
+            dummy_agent(st);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) k.io[i] = k.ip[i] = k.iv[i] = k.lve[i] = k.dve[i] = k.ltv[i] = 0.f;
+        }
+        unsigned status = 0;
+        unsigned n_agent_rows = 0, n_ground = 0;
+        float rpm[4] = {0.f, 0.f, 0.f, 0.f};
+
+        for (int t = 0; t < a.T; ++t) {
+            float act[4];
+            bool nan_act = false;
+            if (valid) nan_act = load_action<MODE>(a.actions, (size_t)t * S + s, act);
+            else act[0] = act[1] = act[2] = act[3] = 0.f;
+            if (nan_act) status |= MRS_STATUS_NAN_ACTION;
+
+            float R[9];
+            quat_to_mat(st, R);
+            action_to_rpm<MODE>(c, st, R, act, k, rpm);
+
+            // ---- pair pass 1: downwash + contact proximity on the pre-step positions
+            __syncwarp();
+            wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
+            __syncwarp();
+            float dw = 0.f;
+            bool near = false;
+            if (MODE != MRS_NO_ACTION || pair_contact) {
+                for (int r = 1; r < G; ++r) {
+                    const int j = (ai + r) & (G - 1);
+                    if (j < N) {
+                        const float4 pj = wpos[gb + j];
+                        const float rx = pj.x - st.px, ry = pj.y - st.py, rz = pj.z - st.pz;
+                        if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, rx, ry, rz);
+                        near = near || (rx * rx + ry * ry + rz * rz < lim2);
+                    }
+                }
+            }
+            const float p0x = st.px, p0y = st.py, p0z = st.pz;
+            apply_wrench<MODE != MRS_NO_ACTION>(c, st, R, rpm, dw);
+
+            // ---- pair pass 2 (rare): sphere-sphere contact on the unconstrained velocities
+            if (pair_contact && __any_sync(kFull, near && valid)) {
+                wvel[lane] = make_float4(st.vx, st.vy, st.vz, 0.f);
+                __syncwarp();
+                if (near) {
+                    float acc[3] = {0.f, 0.f, 0.f};
+                    for (int r = 1; r < G; ++r) {
+                        const int j = (ai + r) & (G - 1);
+                        if (j < N) {
+                            const float4 pj = wpos[gb + j];
+                            const float4 vj = wvel[gb + j];
+                            if (agent_contact_pair(ph, c.dt, p0x - pj.x, p0y - pj.y, p0z - pj.z, st.vx - vj.x,
+                                                   st.vy - vj.y, st.vz - vj.z, acc))
+                                ++n_agent_rows;
+                        }
+                    }
+                    st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
+                }
+            }
+            if (ph.ground_contact && ground_contact(ph, c.dt, st)) ++n_ground;
+            integrate(c, st);
+            if (!agent_finite(st)) status |= MRS_STATUS_NONFINITE;
+
+            // ---- observation: newest X slice and newest A slice into tape slot slot_first - t
+            if (b.X_tape && c.state_layout != MRS_X_NONE && valid)
+                write_X(b.X_tape + (size_t)(a.slot_x - t) * xslot, c.state_layout, s, st);
+            if (b.A_tape) {
+                float* Arow = b.A_tape + (size_t)(a.slot_a - t) * aslot + s * N;
+                if (a.comm_inf) {
+                    if (valid)
+                        for (int j = 0; j < N; ++j) Arow[j] = (j == ai) ? 0.f : 1.f;
+                } else {
+                    __syncwarp();
+                    wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
+                    __syncwarp();
+                    if (valid) {
+                        if ((N & 3) == 0) {
+                            for (int j = 0; j < N; j += 4) {
+                                float v[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float4 pj = wpos[gb + j + u];
+                                    v[u] = (j + u == ai) ? 0.f
+                                                         : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, a.s_max);
+                                }
+                                *reinterpret_cast<float4*>(Arow + j) = make_float4(v[0], v[1], v[2], v[3]);
+                            }
+                        } else {
+                            for (int j = 0; j < N; ++j) {
+                                const float4 pj = wpos[gb + j];
+                                Arow[j] = (j == ai) ? 0.f : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, a.s_max);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        if (valid) {
+            store_agent(b.state, S, s, st);
+            store_ctrl<MODE>(b.ctrl, S, s, k);
+            if (b.rpm && MODE != MRS_NO_ACTION) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b.rpm[i * S + s] = rpm[i];
+            }
+        } else {
+            status = 0; n_agent_rows = 0; n_ground = 0;
+        }
+        // warp-aggregated status / statistics (atomics only when something happened)
+        const unsigned any_status = __reduce_or_sync(kFull, status);
+        const unsigned sum_rows = __reduce_add_sync(kFull, n_agent_rows);
+        const unsigned sum_gnd = __reduce_add_sync(kFull, n_ground);
+        if (lane == 0) {
+            if (any_status && b.status) atomicOr(b.status, any_status);
+            if (b.stats) {
+                if (sum_rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)sum_rows);
+                if (sum_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)sum_gnd);
+                if (any_status & MRS_STATUS_NONFINITE) atomicAdd(b.stats + MRS_STAT_NONFINITE, 1ull);
+                if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ tiled path (N > 32)
+// grid: (ceil(N / kBlock), E).  scratch planes: 0-2 unconstrained velocity, 3-5 pre-step position.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+step_pre_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const float* __restrict__ actions) {
+    __shared__ float4 tile[kBlock];
+    const int N = c.N;
+    const size_t S = (size_t)c.E * N;
+    const size_t env0 = (size_t)blockIdx.y * N;
+    const int ai = blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = ai < N;
+    const size_t s = env0 + (valid ? ai : 0);
+    Agent st;
+    Ctrl k;
+    load_agent(b.state, S, s, st);
+    load_ctrl<MODE>(b.ctrl, S, s, k);
+    float act[4];
+    unsigned status = 0;
+    if (load_action<MODE>(actions, s, act) && valid) status |= MRS_STATUS_NAN_ACTION;
+    float R[9], rpm[4];
+    quat_to_mat(st, R);
+    action_to_rpm<MODE>(c, st, R, act, k, rpm);
+    float dw = 0.f;
+    if (MODE != MRS_NO_ACTION) {
+        for (int j0 = 0; j0 < N; j0 += kBlock) {
+            const int j = j0 + threadIdx.x;
+            __syncthreads();
+            if (j < N) tile[threadIdx.x] = make_float4(b.state[0 * S + env0 + j], b.state[1 * S + env0 + j],
+                                                       b.state[2 * S + env0 + j], 0.f);
+            __syncthreads();
+            const int cnt = min(kBlock, N - j0);
+            for (int u = 0; u < cnt; ++u) {
+                if (j0 + u == ai) continue;
+                const float4 pj = tile[u];
+                dw += downwash_pair(c.quad, pj.x - st.px, pj.y - st.py, pj.z - st.pz);
+            }
+        }
+    }
+    const float p0x = st.px, p0y = st.py, p0z = st.pz;
+    apply_wrench<MODE != MRS_NO_ACTION>(c, st, R, rpm, dw);
+    if (valid) {
+        float* sc = b.scratch;
+        sc[0 * S + s] = st.vx; sc[1 * S + s] = st.vy; sc[2 * S + s] = st.vz;
+        sc[3 * S + s] = p0x; sc[4 * S + s] = p0y; sc[5 * S + s] = p0z;
+        b.state[10 * S + s] = st.wx; b.state[11 * S + s] = st.wy; b.state[12 * S + s] = st.wz;
+        store_ctrl<MODE>(b.ctrl, S, s, k);
+        if (b.rpm && MODE != MRS_NO_ACTION) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b.rpm[i * S + s] = rpm[i];
+        }
+        if (status && b.status) {
+            atomicOr(b.status, status);
+            if (b.stats) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+step_post_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, int slot) {
+    __shared__ float4 tpos[kBlock];
+    __shared__ float4 tvel[kBlock];
+    const int N = c.N;
+    const size_t S = (size_t)c.E * N;
+    const size_t env0 = (size_t)blockIdx.y * N;
+    const int ai = blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = ai < N;
+    const size_t s = env0 + (valid ? ai : 0);
+    const MrsPhysicsParams& ph = c.phys;
+    const float* sc = b.scratch;
+    Agent st;
+    st.px = sc[3 * S + s]; st.py = sc[4 * S + s]; st.pz = sc[5 * S + s];
+    st.vx = sc[0 * S + s]; st.vy = sc[1 * S + s]; st.vz = sc[2 * S + s];
+    st.qx = b.state[3 * S + s]; st.qy = b.state[4 * S + s]; st.qz = b.state[5 * S + s]; st.qw = b.state[6 * S + s];
+    st.wx = b.state[10 * S + s]; st.wy = b.state[11 * S + s]; st.wz = b.state[12 * S + s];
+    unsigned rows = 0, gnd = 0;
+    if (ph.agent_contact && N > 1) {
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int j0 = 0; j0 < N; j0 += kBlock) {
+            const int j = j0 + threadIdx.x;
+            __syncthreads();
+            if (j < N) {
+                tpos[threadIdx.x] = make_float4(sc[3 * S + env0 + j], sc[4 * S + env0 + j], sc[5 * S + env0 + j], 0.f);
+                tvel[threadIdx.x] = make_float4(sc[0 * S + env0 + j], sc[1 * S + env0 + j], sc[2 * S + env0 + j], 0.f);
+            }
+            __syncthreads();
+            const int cnt = min(kBlock, N - j0);
+            for (int u = 0; u < cnt; ++u) {
+                if (j0 + u == ai) continue;
+                const float4 pj = tpos[u];
+                const float dx = st.px - pj.x, dy = st.py - pj.y, dz = st.pz - pj.z;
+                const float lim = 2.f * ph.agent_radius + ph.contact_margin;
+                if (dx * dx + dy * dy + dz * dz < lim * lim) {
+                    const float4 vj = tvel[u];
+                    if (agent_contact_pair(ph, c.dt, dx, dy, dz, st.vx - vj.x, st.vy - vj.y, st.vz - vj.z, acc)) ++rows;
+                }
+            }
+        }
+        st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
+    }
+    if (ph.ground_contact && ground_contact(ph, c.dt, st)) ++gnd;
+    integrate(c, st);
+    if (valid) {
+        store_agent(b.state, S, s, st);
+        if (b.X_tape && c.state_layout != MRS_X_NONE)
+            write_X(b.X_tape + (size_t)slot * S * state_dim(c.state_layout), c.state_layout, s, st);
+        const bool bad = !agent_finite(st);
+        if (bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
+        if (b.stats) {
+            if (rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)rows);
+            if (gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)gnd);
+            if (bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, 1ull);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ adjacency
+// Flat version, any N and any position layout: one thread per output element.
+// pos component c of agent (e, i) = pos[c * cs + (e * N + i) * as].
+__global__ void __launch_bounds__(256)
+adjacency_flat_kernel(const float* __restrict__ pos, size_t cs, size_t as, float* __restrict__ A, int E, int N,
+                      float s_max, int comm_inf) {
+    const size_t total = (size_t)E * N * N;
+    for (size_t kx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; kx < total; kx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(kx % N);
+        const size_t row = kx / N;
+        const int i = (int)(row % N);
+        const size_t e = row / N;
+        float v;
+        if (i == j) v = 0.f;
+        else if (comm_inf) v = 1.f;
+        else {
+            const size_t si = (e * N + i) * as, sj = (e * N + j) * as;
+            v = adjacency_pair(pos[si], pos[cs + si], pos[2 * cs + si], pos[sj], pos[cs + sj], pos[2 * cs + sj], s_max);
+        }
+        A[kx] = v;
+    }
+}
+
+// Tiled version for N >= 128, N % 4 == 0.  CTA = kRowTile rows x 512 columns of one env; each
+// lane keeps its 4 column positions in registers, row positions are broadcast from shared
+// memory, each warp store is 512 contiguous bytes of one A row.
+constexpr int kRowTile = 32;
+__global__ void __launch_bounds__(kBlock)
+adjacency_tiled_kernel(const float* __restrict__ pos, size_t cs, size_t as, float* __restrict__ A, int E, int N,
+                       float s_max, int comm_inf) {
+    __shared__ float4 rows[kRowTile];
+    const int col_tiles = (N + 4 * kBlock - 1) / (4 * kBlock);
+    const int ct = blockIdx.x % col_tiles;
+    const int rt = blockIdx.x / col_tiles;
+    const size_t e = blockIdx.y;
+    const size_t env0 = e * N;
+    const int i0 = rt * kRowTile;
+    const int j = ct * 4 * kBlock + threadIdx.x * 4;
+    if (threadIdx.x < kRowTile && i0 + threadIdx.x < N) {
+        const size_t si = (env0 + i0 + threadIdx.x) * as;
+        rows[threadIdx.x] = make_float4(pos[si], pos[cs + si], pos[2 * cs + si], 0.f);
+    }
+    float xj[4], yj[4], zj[4];
+    const bool col_ok = j < N;
+    if (col_ok) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t sj = (env0 + j + u) * as;
+            xj[u] = pos[sj]; yj[u] = pos[cs + sj]; zj[u] = pos[2 * cs + sj];
+        }
+    }
+    __syncthreads();
+    if (!col_ok) return;
+    const int nrows = min(kRowTile, N - i0);
+    float* out = A + (env0 + i0) * (size_t)N + j;
+    for (int r = 0; r < nrows; ++r) {
+        const float4 pi = rows[r];
+        const int i = i0 + r;
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j + u == i) v[u] = 0.f;
+            else if (comm_inf) v[u] = 1.f;
+            else v[u] = adjacency_pair(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], s_max);
+        }
+        __stcs(reinterpret_cast<float4*>(out + (size_t)r * N), make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
+// X of the current state (MRS.calc_Xk outside step)
+__global__ void __launch_bounds__(256)
+observe_x_kernel(const MrsBuffers b, size_t S, int layout, int slot) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    Agent st;
+    load_agent(b.state, S, s, st);
+    write_X(b.X_tape + (size_t)slot * S * state_dim(layout), layout, s, st);
+}
+
+// ------------------------------------------------------------------------------ set_state
+// Object.set_state (Object.py:42-65): euler 'xyz' (extrinsic) -> quaternion xyzw =
+// qz(yaw) * qy(pitch) * qx(roll); NULL component = keep; masked per env.
+__global__ void __launch_bounds__(256)
+set_state_kernel(float* __restrict__ st, size_t S, int N, const float* __restrict__ pos, const float* __restrict__ ori,
+                 const float* __restrict__ vel, const float* __restrict__ angvel, const unsigned char* __restrict__ mask) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    if (mask && !mask[s / N]) return;
+    if (pos) {
+        st[0 * S + s] = pos[3 * s]; st[1 * S + s] = pos[3 * s + 1]; st[2 * S + s] = pos[3 * s + 2];
+    }
+    if (ori) {
+        float sr, cr, sp, cp, sy, cy;
+        sincosf(0.5f * ori[3 * s], &sr, &cr);
+        sincosf(0.5f * ori[3 * s + 1], &sp, &cp);
+        sincosf(0.5f * ori[3 * s + 2], &sy, &cy);
+        st[3 * S + s] = sr * cp * cy - cr * sp * sy;
+        st[4 * S + s] = cr * sp * cy + sr * cp * sy;
+        st[5 * S + s] = cr * cp * sy - sr * sp * cy;
+        st[6 * S + s] = cr * cp * cy + sr * sp * sy;
+    }
+    if (vel) {
+        st[7 * S + s] = vel[3 * s]; st[8 * S + s] = vel[3 * s + 1]; st[9 * S + s] = vel[3 * s + 2];
+    }
+    if (angvel) {
+        st[10 * S + s] = angvel[3 * s]; st[11 * S + s] = angvel[3 * s + 1]; st[12 * S + s] = angvel[3 * s + 2];
+    }
+}
+
+// tape maintenance: 128-bit grid-stride copy / zero fill (slot sizes are multiples of 4 floats
+// whenever E*N is; scalar tail otherwise)
+__global__ void __launch_bounds__(256)
+tape_fill_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t slot_elems, int count) {
+    const size_t total = slot_elems * (size_t)count;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if ((slot_elems & 3) == 0) {
+        const size_t n4 = total >> 2, s4 = slot_elems >> 2;
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        const float4* r4 = reinterpret_cast<const float4*>(src);
+        for (size_t i = tid; i < n4; i += stride) d4[i] = src ? r4[i % s4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        for (size_t i = tid; i < total; i += stride) dst[i] = src ? src[i % slot_elems] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+static int g_sm_count = 0;
+
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        g_sm_count = n;
+    }
+    return g_sm_count;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// largest float s with sqrt_rn(s) <= r  (see adjacency_pair)
+static float adjacency_threshold(float r) {
+    if (!(r >= 0.f)) return -1.f;          // negative or NaN range: nothing is adjacent
+    if (isinf(r)) return INFINITY;
+    float s = r * r;
+    if (isinf(s)) return 3.402823466e+38f;  // every finite squared distance qualifies
+    while (sqrtf(s) > r) s = nextafterf(s, -INFINITY);
+    for (;;) {
+        const float up = nextafterf(s, INFINITY);
+        if (isinf(up) || sqrtf(up) > r) break;
+        s = up;
+    }
+    return s;
+}
+
+static int check_cfg(const MrsConfig* cfg) {
+    if (!cfg) return MRS_ERR_ARG;
+    if (cfg->E <= 0 || cfg->N <= 0 || cfg->K < 0) return MRS_ERR_ARG;
+    if (cfg->action_type < 0 || cfg->action_type > MRS_NO_ACTION) return MRS_ERR_ARG;
+    if (cfg->state_layout < 0 || cfg->state_layout > MRS_X_FULL) return MRS_ERR_ARG;
+    return MRS_OK;
+}
+
+static int last_error() { return cudaGetLastError() == cudaSuccess ? MRS_OK : MRS_ERR_CUDA; }
+
+template <int MODE>
+static int launch_group(const MrsConfig& c, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
+    static int resident = 0;
+    if (resident == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, step_group_kernel<MODE>, kBlock, 0) != cudaSuccess ||
+            resident <= 0)
+            return MRS_ERR_CUDA;
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return MRS_ERR_CUDA;
+    const int bps = env_int("MRS_B200_BLOCKS_PER_SM", resident);
+    const long long need = ((long long)a.nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long cap = (long long)sms * (bps > 0 ? bps : resident);
+    long long blocks = need;
+    if (need > cap) {  // several chunks per warp: split evenly so every warp does the same count
+        const long long iters = (need + cap - 1) / cap;
+        blocks = (need + iters - 1) / iters;
+    }
+    step_group_kernel<MODE><<<(unsigned)blocks, kBlock, 0, st>>>(c, b, a);
+    return last_error();
+}
+
+template <int MODE>
+static int launch_tiled(const MrsConfig& c, const MrsBuffers& b, const StepArgs& a, cudaStream_t st);
+
+static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, int N, float s_max, int comm_inf,
+                            cudaStream_t st) {
+    if (N >= 128 && (N & 3) == 0) {
+        const int col_tiles = (N + 4 * kBlock - 1) / (4 * kBlock);
+        const int row_tiles = (N + kRowTile - 1) / kRowTile;
+        dim3 grid((unsigned)(col_tiles * row_tiles), (unsigned)E);
+        adjacency_tiled_kernel<<<grid, kBlock, 0, st>>>(pos, cs, as, A, E, N, s_max, comm_inf);
+    } else {
+        const size_t total = (size_t)E * N * N;
+        const size_t blocks = (total + 255) / 256;
+        const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 32;
+        adjacency_flat_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(pos, cs, as, A, E, N, s_max,
+                                                                                        comm_inf);
+    }
+    return last_error();
+}
+
+template <int MODE>
+static int launch_tiled(const MrsConfig& c, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
+    if (!b.scratch) return MRS_ERR_ARG;
+    const size_t S = (size_t)c.E * c.N;
+    constexpr int A = ModeTraits<MODE>::A;
+    dim3 grid((unsigned)((c.N + kBlock - 1) / kBlock), (unsigned)c.E);
+    for (int t = 0; t < a.T; ++t) {
+        step_pre_kernel<MODE><<<grid, kBlock, 0, st>>>(c, b, a.actions ? a.actions + (size_t)t * S * A : nullptr);
+        step_post_kernel<<<grid, kBlock, 0, st>>>(c, b, a.slot_x - t);
+        if (b.A_tape) {
+            const int rc = launch_adjacency(b.state, S, 1, b.A_tape + (size_t)(a.slot_a - t) * S * c.N, c.E, c.N, a.s_max,
+                                            a.comm_inf, st);
+            if (rc) return rc;
+        }
+    }
+    return last_error();
+}
+
+static int pow2ceil(int n) {
+    int g = 1;
+    while (g < n) g <<= 1;
+    return g;
+}
+
+template <int MODE>
+static int dispatch_step(const MrsConfig& c, const MrsBuffers& b, StepArgs a, cudaStream_t st) {
+    if (c.N <= 32) {
+        a.G = pow2ceil(c.N);
+        const int gpw = 32 / a.G;
+        a.nchunks = (c.E + gpw - 1) / gpw;
+        return launch_group<MODE>(c, b, a, st);
+    }
+    return launch_tiled<MODE>(c, b, a, st);
+}
+
+static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T, int slot_x, int slot_a,
+                     void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs || !bufs->state || !bufs->ctrl) return MRS_ERR_ARG;
+    if (T <= 0) return MRS_ERR_ARG;
+    if (cfg->action_type != MRS_NO_ACTION && !actions) return MRS_ERR_ARG;
+    if (bufs->X_tape && cfg->state_layout != MRS_X_NONE && (slot_x >= cfg->L || slot_x - (T - 1) < 0)) return MRS_ERR_ARG;
+    if (bufs->A_tape && (slot_a >= cfg->L || slot_a - (T - 1) < 0)) return MRS_ERR_ARG;
+    StepArgs a;
+    a.actions = actions;
+    a.T = T;
+    a.slot_x = slot_x;
+    a.slot_a = slot_a;
+    a.G = 0;
+    a.nchunks = 0;
+    a.comm_inf = isinf(cfg->comm_range) && cfg->comm_range > 0.f;
+    a.s_max = adjacency_threshold(cfg->comm_range);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cfg->action_type) {
+        case MRS_SET_TARGET_VEL:   return dispatch_step<MRS_SET_TARGET_VEL>(*cfg, *bufs, a, st);
+        case MRS_SET_TARGET_POS:   return dispatch_step<MRS_SET_TARGET_POS>(*cfg, *bufs, a, st);
+        case MRS_SET_TARGET_ACCEL: return dispatch_step<MRS_SET_TARGET_ACCEL>(*cfg, *bufs, a, st);
+        case MRS_SET_FORCE:        return dispatch_step<MRS_SET_FORCE>(*cfg, *bufs, a, st);
+        case MRS_SET_TARGET_ORI:   return dispatch_step<MRS_SET_TARGET_ORI>(*cfg, *bufs, a, st);
+        case MRS_SET_CONTROL:      return dispatch_step<MRS_SET_CONTROL>(*cfg, *bufs, a, st);
+        case MRS_SET_SPEEDS:       return dispatch_step<MRS_SET_SPEEDS>(*cfg, *bufs, a, st);
+        case MRS_NO_ACTION:        return dispatch_step<MRS_NO_ACTION>(*cfg, *bufs, a, st);
+    }
+    return MRS_ERR_ARG;
+}
+
+}  // namespace mrs
+
+// ================================================================================ C ABI
+using namespace mrs;
+
+extern "C" {
+
+int mrs_abi_version(void) { return MRS_ABI_VERSION; }
+
+const char* mrs_strerror(int err) {
+    switch (err) {
+        case MRS_OK: return "ok";
+        case MRS_ERR_ARG: return "invalid argument";
+        case MRS_ERR_CUDA: return "CUDA error (no device, bad launch or asynchronous fault)";
+        case MRS_ERR_UNSUPPORTED: return "unsupported configuration";
+    }
+    return "unknown error";
+}
+
+int mrs_action_dim(int action_type) {
+    switch (action_type) {
+        case MRS_SET_TARGET_VEL: case MRS_SET_TARGET_POS: case MRS_SET_TARGET_ACCEL: case MRS_SET_FORCE:
+        case MRS_SET_TARGET_ORI: return 3;
+        case MRS_SET_CONTROL: case MRS_SET_SPEEDS: return 4;
+    }
+    return 0;
+}
+
+int mrs_state_dim(int state_layout) { return state_dim(state_layout); }
+
+size_t mrs_sizeof_config(void) { return sizeof(MrsConfig); }
+size_t mrs_sizeof_buffers(void) { return sizeof(MrsBuffers); }
+
+int mrs_default_config(MrsConfig* cfg) {
+    if (!cfg) return MRS_ERR_ARG;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->E = 1; cfg->N = 1; cfg->K = 0; cfg->L = 1;
+    cfg->action_type = MRS_SET_TARGET_VEL;
+    cfg->state_layout = MRS_X_POS_VEL;
+    cfg->dt = 0.01f;
+    cfg->gravity = 9.81f;
+    cfg->comm_range = INFINITY;
+    MrsQuadParams& q = cfg->quad;
+    // cf2x.urdf:5,11-12 and prop link CoM offsets :42,54,66,78
+    q.mass = 0.027f; q.ixx = 1.4e-5f; q.iyy = 1.4e-5f; q.izz = 2.17e-5f;
+    q.kf = 3.16e-10f; q.km = 7.94e-12f; q.arm = 0.0397f;
+    q.gnd_eff_coeff = 11.36859f; q.prop_radius = 2.31348e-2f;
+    q.drag_xy = 9.1785e-7f; q.drag_z = 10.311e-7f;
+    q.dw1 = 2267.18f; q.dw2 = 0.16f; q.dw3 = -0.11f;
+    const float px[4] = {0.028f, -0.028f, -0.028f, 0.028f}, py[4] = {0.028f, 0.028f, -0.028f, -0.028f};
+    for (int i = 0; i < 4; ++i) { q.prop_x[i] = px[i]; q.prop_y[i] = py[i]; }
+    // Quadcopter.calculate_parameters (Quadcopter.py:153-168), in double then rounded
+    {
+        const double g = 9.81 * 0.027, kf = 3.16e-10, t2w = 2.25, coeff = 11.36859, pr = 2.31348e-2;
+        const double max_rpm = sqrt(t2w * g / (4 * kf));
+        const double max_thrust = 4.0 * kf * max_rpm * max_rpm;
+        q.gnd_hclip = (float)(0.25 * pr * sqrt((15.0 * max_rpm * max_rpm * kf * coeff) / max_thrust));
+    }
+    // QuadControl gains (QuadControl.py:14-32)
+    q.pos_p = 1.5f; q.pos_i = 0.001f; q.pos_d = 1.0f;
+    q.vel_p = 3.0f; q.vel_i = 0.1f; q.vel_d = 1.0f;
+    const float op[3] = {70000.f, 70000.f, 60000.f}, oi[3] = {0.f, 0.f, 500.f}, od[3] = {20000.f, 20000.f, 12000.f};
+    for (int i = 0; i < 3; ++i) { q.ori_p[i] = op[i]; q.ori_i[i] = oi[i]; q.ori_d[i] = od[i]; }
+    q.min_pwm = 20000.f; q.max_pwm = 65535.f; q.pwm2rpm_a = 0.2685f; q.pwm2rpm_b = 4070.3f;
+    q.ctrl_dt = 0.01f; q.ctrl_gravity = 9.81f;
+    // 'x' mixer (Quadcopter.py:164) and its inverse; orthogonal rows => Ainv = A^T D^-1
+    const double r2 = 1.0 / sqrt(2.0);
+    const double A[4][4] = {{1, 1, 1, 1}, {r2, r2, -r2, -r2}, {-r2, r2, r2, -r2}, {-1, 1, -1, 1}};
+    const double rown[4] = {4.0, 2.0, 2.0, 4.0};
+    for (int r = 0; r < 4; ++r)
+        for (int cidx = 0; cidx < 4; ++cidx) {
+            q.mix_a[r * 4 + cidx] = (float)A[r][cidx];
+            q.mix_ainv[cidx * 4 + r] = (float)(A[r][cidx] / rown[r]);
+        }
+    // least-squares solve matrices of the 16 active sets: P_S = (A_S^T A_S)^-1 A_S^T (4x4, zero rows off S)
+    for (int m = 0; m < 16; ++m) {
+        int cols[4], nc = 0;
+        for (int cidx = 0; cidx < 4; ++cidx) if ((m >> cidx) & 1) cols[nc++] = cidx;
+        double Gm[4][8];
+        for (int i = 0; i < nc; ++i) {
+            for (int j = 0; j < nc; ++j) {
+                double acc = 0;
+                for (int r = 0; r < 4; ++r) acc += A[r][cols[i]] * A[r][cols[j]];
+                Gm[i][j] = acc;
+            }
+            for (int j = 0; j < nc; ++j) Gm[i][nc + j] = (i == j) ? 1.0 : 0.0;
+        }
+        for (int p = 0; p < nc; ++p) {   // Gauss-Jordan, SPD Gram matrix
+            int best = p;
+            for (int r = p + 1; r < nc; ++r) if (fabs(Gm[r][p]) > fabs(Gm[best][p])) best = r;
+            if (best != p) for (int j = 0; j < 2 * nc; ++j) { double tmp = Gm[p][j]; Gm[p][j] = Gm[best][j]; Gm[best][j] = tmp; }
+            const double piv = Gm[p][p];
+            for (int j = 0; j < 2 * nc; ++j) Gm[p][j] /= piv;
+            for (int r = 0; r < nc; ++r) if (r != p) {
+                const double f = Gm[r][p];
+                for (int j = 0; j < 2 * nc; ++j) Gm[r][j] -= f * Gm[p][j];
+            }
+        }
+        for (int i = 0; i < nc; ++i)
+            for (int r = 0; r < 4; ++r) {
+                double acc = 0;
+                for (int j = 0; j < nc; ++j) acc += Gm[i][nc + j] * A[r][cols[j]];
+                q.nnls_tab[m * 16 + cols[i] * 4 + r] = (float)acc;
+            }
+    }
+    MrsPhysicsParams& p = cfg->phys;   // oracle/bullet_model.py PhysicsParams
+    p.mass = 0.027f;
+    {
+        const double hx = 0.06 + 3 * 0.001, hz = 0.0125 + 3 * 0.001, lx = 2 * hx, lz = 2 * hz, m = 0.027;
+        p.inertia[0] = p.inertia[1] = (float)(m / 12.0 * (lx * lx + lz * lz));
+        p.inertia[2] = (float)(m / 12.0 * (lx * lx + lx * lx));
+    }
+    p.lin_damping = 0.04f; p.ang_damping = 0.04f; p.max_coord_vel = 100.f; p.gyro = 1;
+    p.ang_motion_threshold = 0.78539816339744830962f;
+    p.erp2 = 0.08f; p.slop = 1e-5f; p.contact_margin = 0.02f;
+    p.mu_ground = 0.75f; p.ground_z = 0.5f;
+    p.col_radius = 0.06f; p.col_halfheight = 0.0125f; p.col_margin = 0.001f;
+    p.ground_contact = 1; p.agent_contact = 1;
+    p.agent_radius = 0.3f;
+    return MRS_OK;
+}
+
+int mrs_step(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int slot_x, int slot_a, void* stream) {
+    return step_impl(cfg, bufs, actions, 1, slot_x, slot_a, stream);
+}
+
+int mrs_step_many(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T, int slot_x_first,
+                  int slot_a_first, void* stream) {
+    return step_impl(cfg, bufs, actions, T, slot_x_first, slot_a_first, stream);
+}
+
+int mrs_observe(const MrsConfig* cfg, const MrsBuffers* bufs, int slot, int write_X, int write_A, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs || !bufs->state) return MRS_ERR_ARG;
+    if (slot < 0 || slot >= cfg->L) return MRS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t S = (size_t)cfg->E * cfg->N;
+    if (write_X && cfg->state_layout != MRS_X_NONE) {
+        if (!bufs->X_tape) return MRS_ERR_ARG;
+        observe_x_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(*bufs, S, cfg->state_layout, slot);
+        if ((rc = last_error())) return rc;
+    }
+    if (write_A) {
+        if (!bufs->A_tape) return MRS_ERR_ARG;
+        const int comm_inf = isinf(cfg->comm_range) && cfg->comm_range > 0.f;
+        rc = launch_adjacency(bufs->state, S, 1, bufs->A_tape + (size_t)slot * S * cfg->N, cfg->E, cfg->N,
+                              adjacency_threshold(cfg->comm_range), comm_inf, st);
+    }
+    return rc;
+}
+
+int mrs_adjacency(const MrsConfig* cfg, const float* pos, float* A, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!pos || !A) return MRS_ERR_ARG;
+    const int comm_inf = isinf(cfg->comm_range) && cfg->comm_range > 0.f;
+    return launch_adjacency(pos, 1, 3, A, cfg->E, cfg->N, adjacency_threshold(cfg->comm_range), comm_inf,
+                            (cudaStream_t)stream);
+}
+
+int mrs_set_state(const MrsConfig* cfg, const MrsBuffers* bufs, const float* pos, const float* ori_euler,
+                  const float* vel, const float* angvel, const unsigned char* env_mask, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs || !bufs->state) return MRS_ERR_ARG;
+    const size_t S = (size_t)cfg->E * cfg->N;
+    set_state_kernel<<<(unsigned)((S + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bufs->state, S, cfg->N, pos,
+                                                                                   ori_euler, vel, angvel, env_mask);
+    return last_error();
+}
+
+int mrs_tape_fill(const MrsConfig* cfg, const MrsBuffers* bufs, int which, int src, int dst_first, int count,
+                  void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs || (which != 1 && which != 2)) return MRS_ERR_ARG;
+    if (count <= 0) return count == 0 ? MRS_OK : MRS_ERR_ARG;
+    if (dst_first < 0 || dst_first + count > cfg->L || src >= cfg->L) return MRS_ERR_ARG;
+    if (src >= 0 && src >= dst_first && src < dst_first + count) return MRS_ERR_ARG;
+    const size_t S = (size_t)cfg->E * cfg->N;
+    float* tape = (which == 1) ? bufs->X_tape : bufs->A_tape;
+    if (!tape) return MRS_ERR_ARG;
+    const size_t slot_elems = (which == 1) ? S * (size_t)state_dim(cfg->state_layout) : S * (size_t)cfg->N;
+    if (slot_elems == 0) return MRS_ERR_ARG;
+    const size_t work = (slot_elems * count + 3) / 4;
+    size_t blocks = (work + 255) / 256;
+    const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 16;
+    if (blocks > cap) blocks = cap;
+    tape_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        tape + (size_t)dst_first * slot_elems, src >= 0 ? tape + (size_t)src * slot_elems : nullptr, slot_elems, count);
+    return last_error();
+}
+
+int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host, float* dev_actions,
+                  float* X_host, float* A_host, int slot_x, int slot_a, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs) return MRS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t S = (size_t)cfg->E * cfg->N;
+    const int adim = mrs_action_dim(cfg->action_type);
+    if (adim > 0) {
+        if (!actions_host || !dev_actions) return MRS_ERR_ARG;
+        if (cudaMemcpyAsync(dev_actions, actions_host, S * adim * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return MRS_ERR_CUDA;
+    }
+    rc = step_impl(cfg, bufs, dev_actions, 1, slot_x, slot_a, stream);
+    if (rc) return rc;
+    const int D = state_dim(cfg->state_layout);
+    if (X_host && bufs->X_tape && D > 0) {
+        if (cudaMemcpyAsync(X_host, bufs->X_tape + (size_t)slot_x * S * D, S * D * sizeof(float), cudaMemcpyDeviceToHost,
+                            st) != cudaSuccess)
+            return MRS_ERR_CUDA;
+    }
+    if (A_host && bufs->A_tape) {
+        if (cudaMemcpyAsync(A_host, bufs->A_tape + (size_t)slot_a * S * cfg->N, S * cfg->N * sizeof(float),
+                            cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            return MRS_ERR_CUDA;
+    }
+    return cudaStreamSynchronize(st) == cudaSuccess ? MRS_OK : MRS_ERR_CUDA;
+}
+
+}  // extern "C"

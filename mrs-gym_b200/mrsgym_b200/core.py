@@ -1,0 +1,289 @@
+"""Swarm: the batched [envs x agents] device state store and its C-ABI calls.
+
+Replaces, for the step path only, the reference's BulletSim + Environment + Quadcopter +
+QuadControl object graph (/root/reference/mrsgym/BulletSim.py, Environment.py:84-124,
+Quadcopter.py, QuadControl.py).  PyTorch owns every device buffer (the library never
+allocates); all launches go on torch's current stream.
+
+Observation history ("tapes"): X_tape [L][E][N][D] and A_tape [L][E][N][N].  Time runs towards
+LOWER slot indices: a step writes slot head-1, so slots [head, head+K] are exactly the
+reference's newest-first K_HOPS+1 window (MRS.get_Xk / get_Ak, MRS.py:98-114) as a zero-copy
+view.  When a head reaches 0 the K newest slots are moved to the top of the tape.  X and A keep
+separate heads because the reference shifts its two deques independently (calc_Ak can be called
+without calc_Xk, examples/simulating_data/helper/DataGenerator.py:23).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _abi
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def shard_range(E_total: int, rank: int, world: int):
+    """Contiguous env block owned by `rank`: [lo, hi)."""
+    base, rem = divmod(E_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class Swarm:
+    def __init__(self, E: int, N: int, K: int = 0, action_type='set_target_vel', state_layout=_abi.X_POS_VEL,
+                 comm_range=float('inf'), dt=0.01, gravity=9.81, agent_radius=0.3, device='cuda',
+                 tape_slots=None, want_A=True, custom_D=0, keep_rpm=False):
+        self.lib = _abi.lib()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _abi.MrsError('mrsgym_b200 runs on CUDA devices only (no CPU fallback); got %s' % device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.E, self.N, self.K = int(E), int(N), int(K)
+        self.S = self.E * self.N
+        self.cfg = _abi.default_config()
+        self.cfg.E, self.cfg.N, self.cfg.K = self.E, self.N, self.K
+        self.set_action_type(action_type)
+        self.cfg.state_layout = state_layout
+        self.cfg.comm_range = float(comm_range)
+        self.cfg.dt, self.cfg.gravity = float(dt), float(gravity)
+        self.cfg.phys.agent_radius = float(agent_radius)
+        self.D = _abi.STATE_DIMS[state_layout] if state_layout != _abi.X_NONE else int(custom_D)
+        self.L = int(tape_slots) if tape_slots else max(2 * self.K + 2, 16)
+        if self.L < 2 * self.K + 2:
+            raise ValueError('tape_slots must be >= 2*K_HOPS+2')
+        self.cfg.L = self.L
+        dev = self.device
+        z = dict(device=dev, dtype=torch.float32)
+        self.state = torch.zeros(_abi.STATE_PLANES, self.S, **z)
+        self.state[6].fill_(1.0)                                  # identity quaternion (xyzw)
+        self.ctrl = torch.zeros(_abi.CTRL_PLANES, self.S, **z)
+        self.ctrl[9].fill_(float('nan'))                          # last_vel_e.x = NaN: never called
+        self.rpm = torch.zeros(4, self.S, **z) if keep_rpm else None
+        self.X_tape = torch.zeros(self.L, self.E, self.N, max(self.D, 1), **z) if self.D > 0 else None
+        self.A_tape = torch.zeros(self.L, self.E, self.N, self.N, **z) if want_A else None
+        self.scratch = torch.zeros(_abi.SCRATCH_PLANES, self.S, **z) if self.N > 32 else None
+        self.status = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.stats = torch.zeros(_abi.STATS_SLOTS, device=dev, dtype=torch.int64)
+        self.bufs = _abi.MrsBuffers()
+        self._bind()
+        self.hx = self.L - self.K - 1
+        self.ha = self.L - self.K - 1
+        self.launches = 0          # kernel launches issued through the ABI (bench: gpu_launches)
+
+    # ------------------------------------------------------------------ plumbing
+    def _bind(self):
+        b = self.bufs
+        b.state, b.ctrl = self.state.data_ptr(), self.ctrl.data_ptr()
+        b.rpm = self.rpm.data_ptr() if self.rpm is not None else None
+        b.X_tape = self.X_tape.data_ptr() if (self.X_tape is not None and self.cfg.state_layout != _abi.X_NONE) else None
+        b.A_tape = self.A_tape.data_ptr() if self.A_tape is not None else None
+        b.scratch = self.scratch.data_ptr() if self.scratch is not None else None
+        b.status, b.stats = self.status.data_ptr(), self.stats.data_ptr()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_action_type(self, action_type):
+        if action_type is None:
+            self.cfg.action_type = _abi.NO_ACTION
+        elif isinstance(action_type, str):
+            if action_type not in _abi.ACTION_TYPES:
+                # the reference dispatches with getattr(agent, behaviour) (Environment.py:92)
+                raise AttributeError("'Quadcopter' object has no attribute '%s'" % action_type)
+            self.cfg.action_type = _abi.ACTION_TYPES[action_type]
+        else:
+            self.cfg.action_type = int(action_type)
+        return _abi.ACTION_DIMS[self.cfg.action_type]
+
+    @property
+    def action_dim(self):
+        return _abi.ACTION_DIMS[self.cfg.action_type]
+
+    # ------------------------------------------------------------------ tapes
+    def _make_room(self, which: int, need: int = 1):
+        """Ensure `need` free slots below the head of tape `which` (1 = X, 2 = A)."""
+        head = self.hx if which == 1 else self.ha
+        if head >= need:
+            return head
+        K, L = self.K, self.L
+        tape = self.X_tape if which == 1 else self.A_tape
+        if tape is not None and K > 0 and which == 1 and self.cfg.state_layout == _abi.X_NONE:
+            tape[L - K:L] = tape[head:head + K].clone()      # python-written X (custom state_fn)
+        elif tape is not None and K > 0:
+            for i in range(K - 1, -1, -1):           # move the K newest slots to the top
+                _abi.check(self.lib.mrs_tape_fill(C.byref(self.cfg), C.byref(self.bufs), which, head + i,
+                                                  L - K + i, 1, self._stream()), 'mrs_tape_fill')
+                self.launches += 1
+        head = L - K
+        if which == 1:
+            self.hx = head
+        else:
+            self.ha = head
+        return head
+
+    def max_chunk(self):
+        """Largest T a single mrs_step_many may take with this tape size."""
+        return self.L - self.K
+
+    def reset_windows(self, write_X=True):
+        """Ring state after MRS.reset/set (MRS.py:185-192): X window = K+1 copies of X0, A window
+        empty (reads as zeros, MRS.py:107-108)."""
+        K, L = self.K, self.L
+        self.hx = self.ha = L - K - 1
+        st = self._stream()
+        if self.X_tape is not None:
+            if write_X and self.cfg.state_layout != _abi.X_NONE:
+                _abi.check(self.lib.mrs_observe(C.byref(self.cfg), C.byref(self.bufs), self.hx, 1, 0, st), 'mrs_observe')
+                self.launches += 1
+            if K > 0 and self.cfg.state_layout != _abi.X_NONE:
+                _abi.check(self.lib.mrs_tape_fill(C.byref(self.cfg), C.byref(self.bufs), 1, self.hx, self.hx + 1, K, st),
+                           'mrs_tape_fill')
+                self.launches += 1
+        if self.A_tape is not None:
+            _abi.check(self.lib.mrs_tape_fill(C.byref(self.cfg), C.byref(self.bufs), 2, -1, self.ha, K + 1, st),
+                       'mrs_tape_fill')
+            self.launches += 1
+            self.ha += 1          # empty deque: the first push lands on slot L-K-1
+
+    def fill_X_history(self):
+        """Custom state_fn path: replicate slot hx into the K older slots (python wrote X0 there)."""
+        if self.K > 0:
+            self.X_tape[self.hx + 1:self.hx + 1 + self.K] = self.X_tape[self.hx]
+
+    def X_window(self):
+        return self.X_tape[self.hx:self.hx + self.K + 1]          # [K+1, E, N, D], newest first
+
+    def A_window(self):
+        return self.A_tape[self.ha:self.ha + self.K + 1]          # [K+1, E, N, N]
+
+    # ------------------------------------------------------------------ the step
+    def step(self, actions):
+        """One env.step for all envs.  actions: device float32 [E,N,A] contiguous, or None."""
+        hx = self._make_room(1) - 1 if self.X_tape is not None else 0
+        ha = self._make_room(2) - 1 if self.A_tape is not None else 0
+        _abi.check(self.lib.mrs_step(C.byref(self.cfg), C.byref(self.bufs), _ptr(actions), hx, ha, self._stream()),
+                   'mrs_step')
+        self.launches += 1 if self.N <= 32 else (3 if self.A_tape is not None else 2)
+        if self.X_tape is not None:
+            self.hx = hx
+        if self.A_tape is not None:
+            self.ha = ha
+
+    def step_many(self, actions, T: int):
+        """T steps with pre-computed actions [T,E,N,A]; chunks at tape wrap-arounds."""
+        done = 0
+        while done < T:
+            hx = self._make_room(1) if self.X_tape is not None else T
+            ha = self._make_room(2) if self.A_tape is not None else T
+            n = min(T - done, hx, ha)
+            a = actions[done:done + n] if actions is not None else None
+            _abi.check(self.lib.mrs_step_many(C.byref(self.cfg), C.byref(self.bufs), _ptr(a), n, hx - 1, ha - 1,
+                                              self._stream()), 'mrs_step_many')
+            self.launches += 1 if self.N <= 32 else n * (3 if self.A_tape is not None else 2)
+            if self.X_tape is not None:
+                self.hx = hx - n
+            if self.A_tape is not None:
+                self.ha = ha - n
+            done += n
+
+    def push_A(self):
+        """MRS.calc_Ak outside step: adjacency of the current positions becomes the newest slot."""
+        ha = self._make_room(2) - 1
+        _abi.check(self.lib.mrs_observe(C.byref(self.cfg), C.byref(self.bufs), ha, 0, 1, self._stream()), 'mrs_observe')
+        self.launches += 1
+        self.ha = ha
+
+    def push_X(self):
+        hx = self._make_room(1) - 1
+        if self.cfg.state_layout != _abi.X_NONE:
+            _abi.check(self.lib.mrs_observe(C.byref(self.cfg), C.byref(self.bufs), hx, 1, 0, self._stream()), 'mrs_observe')
+            self.launches += 1
+        self.hx = hx
+        return hx
+
+    def step_host(self, actions_host, dev_actions, X_host, A_host):
+        """mrs_step_host: pinned host actions in, newest X/A slice out, synchronous."""
+        hx = self._make_room(1) - 1 if self.X_tape is not None else 0
+        ha = self._make_room(2) - 1 if self.A_tape is not None else 0
+        _abi.check(self.lib.mrs_step_host(C.byref(self.cfg), C.byref(self.bufs), _ptr(actions_host), _ptr(dev_actions),
+                                          _ptr(X_host), _ptr(A_host), hx, ha, self._stream()), 'mrs_step_host')
+        self.launches += 1 if self.N <= 32 else (3 if self.A_tape is not None else 2)
+        if self.X_tape is not None:
+            self.hx = hx
+        if self.A_tape is not None:
+            self.ha = ha
+
+    # ------------------------------------------------------------------ state access
+    def set_state(self, pos=None, ori=None, vel=None, angvel=None, env_mask=None):
+        """Environment.set_state -> Object.set_state (Environment.py:97-103, Object.py:42-65).
+        Each of pos/ori(euler xyz)/vel/angvel: [E,N,3] (or [N,3], broadcast over envs) or None = keep."""
+        def prep(x):
+            if x is None:
+                return None
+            x = torch.as_tensor(x, dtype=torch.float32).to(self.device)
+            if x.dim() == 2:
+                x = x.unsqueeze(0).expand(self.E, -1, -1)
+            return x.reshape(self.E, self.N, 3).contiguous()
+        pos, ori, vel, angvel = prep(pos), prep(ori), prep(vel), prep(angvel)
+        if env_mask is not None:
+            env_mask = torch.as_tensor(env_mask).to(self.device).to(torch.uint8).reshape(self.E).contiguous()
+        _abi.check(self.lib.mrs_set_state(C.byref(self.cfg), C.byref(self.bufs), _ptr(pos), _ptr(ori), _ptr(vel),
+                                          _ptr(angvel), _ptr(env_mask), self._stream()), 'mrs_set_state')
+        self.launches += 1
+
+    def set_quat(self, quat):
+        """Exact quaternion upload (xyzw), bypassing the euler conversion (tests / checkpoints)."""
+        q = torch.as_tensor(quat, dtype=torch.float32).to(self.device).reshape(self.S, 4)
+        self.state[3:7] = q.t()
+
+    def _planes(self, lo, hi):
+        return self.state[lo:hi].t().reshape(self.E, self.N, hi - lo)
+
+    def get_pos(self):
+        return self._planes(0, 3)
+
+    def get_quat(self):
+        return self._planes(3, 7)
+
+    def get_vel(self):
+        return self._planes(7, 10)
+
+    def get_angvel(self):
+        return self._planes(10, 13)
+
+    def get_ori(self):
+        """euler 'xyz' [roll, pitch, yaw] as scipy's as_euler('xyz') (Object.get_ori, Object.py:90-97)."""
+        x, y, z, w = (self.state[i] for i in range(3, 7))
+        roll = torch.atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
+        pitch = torch.asin(torch.clamp(2 * (w * y - z * x), -1.0, 1.0))
+        yaw = torch.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+        return torch.stack([roll, pitch, yaw], dim=-1).reshape(self.E, self.N, 3)
+
+    def adjacency(self, pos):
+        """MRS.calc_A on arbitrary float32 positions [E,N,3] -> [E,N,N] (bit-exact with torch CPU)."""
+        pos = torch.as_tensor(pos, dtype=torch.float32).to(self.device).reshape(self.E, self.N, 3).contiguous()
+        A = torch.empty(self.E, self.N, self.N, device=self.device, dtype=torch.float32)
+        _abi.check(self.lib.mrs_adjacency(C.byref(self.cfg), _ptr(pos), _ptr(A), self._stream()), 'mrs_adjacency')
+        self.launches += 1
+        return A
+
+    def read_status(self, clear=True):
+        v = int(self.status.item())
+        if clear and v:
+            self.status.zero_()
+        return v
+
+    def read_stats(self):
+        v = self.stats.tolist()
+        return {n: v[i] for i, n in enumerate(_abi.STAT_NAMES)}
+
+    def allreduce_stats(self, group=None):
+        """Per-rollout statistics reduction across env shards: the ONLY collective of the path
+        (NCCL over NVLink when the process group is nccl)."""
+        from .dist import allreduce_stats
+        return allreduce_stats(self.stats, group)

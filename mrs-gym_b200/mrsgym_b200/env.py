@@ -1,0 +1,410 @@
+"""MRS: the reference's Gym environment class, batched over N_ENVS and running on the B200.
+
+Mirrors /root/reference/mrsgym/MRS.py:12-293 for the step path: same constructor kwargs
+(N_AGENTS, K_HOPS, COMM_RANGE, ACTION_TYPE, AGENT_RADIUS, MAX_TIMESTEPS, START_POS, START_ORI,
+DT, GRAVITY, ...), same `step(actions, ACTION_TYPE=None) -> (X, reward, done, info)` with
+info["A"], same callback order (update -> reward -> last_obs := X -> info -> done ->
+steps_since_reset += 1, MRS.py:260-274), same ring semantics (X padded with copies, A with
+zeros).  New kwargs: N_ENVS (batch of independent worlds; default 1 = reference shapes),
+DEVICE, TAPE_SLOTS, CHECK_NAN, COPY_OBS.
+
+Shapes: N_ENVS == 1 -> X (K+1, N, D), A (K+1, N, N) exactly like the reference;
+        N_ENVS  > 1 -> X [E, K+1, N, D], A [E, K+1, N, N] (zero-copy views of the device tapes
+        unless COPY_OBS; a view stays valid for at least TAPE_SLOTS - 2*K_HOPS - 2 further steps).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _abi
+from .core import Swarm
+from . import spawn as _spawn
+
+_LAYOUTS = {'pos_vel': _abi.X_POS_VEL, 'full': _abi.X_FULL}
+
+
+class AgentBatch:
+    """What a reference-style ``state_fn(quad)`` receives: the getters of Object
+    (/root/reference/mrsgym/Object.py:78-97) for ALL agents at once, component-major
+    ([3, E*N]) so that 1-D code such as ``torch.cat([quad.get_pos(), quad.get_vel()])``
+    (README.md:28-29) works unchanged and yields [D, E*N]."""
+
+    def __init__(self, swarm: Swarm):
+        self._s = swarm
+
+    def get_pos(self):
+        return self._s.state[0:3]
+
+    def get_vel(self):
+        return self._s.state[7:10]
+
+    def get_angvel(self):
+        return self._s.state[10:13]
+
+    def get_quat(self):
+        return self._s.state[3:7]
+
+    def get_ori(self, mat=False):
+        if mat:
+            raise NotImplementedError('get_ori(mat=True) is not provided for batched state_fn; use get_quat()')
+        return self._s.get_ori().reshape(self._s.S, 3).t()
+
+
+class Environment:
+    """Batched stand-in for the reference's Environment on the step path
+    (/root/reference/mrsgym/Environment.py:84-124): getters return [E, N, 3] device tensors
+    ([N, 3] when N_ENVS == 1, like the reference)."""
+
+    def __init__(self, swarm: Swarm, squeeze: bool):
+        self.swarm = swarm
+        self._squeeze = squeeze
+        self.data = {}
+        self.agents = AgentBatch(swarm)
+        self.objects = []
+        self.controlled = []
+        self.object_dict = {}
+
+    def _out(self, x):
+        return x[0] if self._squeeze else x
+
+    def get_pos(self):
+        return self._out(self.swarm.get_pos())
+
+    def get_vel(self):
+        return self._out(self.swarm.get_vel())
+
+    def get_angvel(self):
+        return self._out(self.swarm.get_angvel())
+
+    def get_ori(self):
+        return self._out(self.swarm.get_ori())
+
+    def get_quat(self):
+        return self._out(self.swarm.get_quat())
+
+    def set_state(self, pos=None, ori=None, vel=None, angvel=None, env_mask=None):
+        self.swarm.set_state(pos=pos, ori=ori, vel=vel, angvel=angvel, env_mask=env_mask)
+
+    def set_data(self, name, val):
+        self.data[name] = val
+
+    def get_data(self, name):
+        return self.data.get(name, None)
+
+    # GUI / debug helpers of the reference (Environment.py:127-306) are no-ops headless
+    def draw_links(self, A):
+        pass
+
+    def get_keyboard_events(self):
+        return {}
+
+    def get_mouse_events(self):
+        return {}
+
+
+class _Sim:
+    """BulletSim constants holder (/root/reference/mrsgym/BulletSim.py:8-24)."""
+
+    def __init__(self, **kwargs):
+        self.REAL_TIME = False
+        self.HEADLESS = True
+        self.GRAVITY = 9.81
+        self.DT = 0.01
+        for name, val in kwargs.items():
+            if name in self.__dict__:
+                self.__dict__[name] = val
+
+    def stop(self):
+        pass
+
+
+class MRS:
+    metadata = {'render.modes': ['headless', 'bullet']}
+
+    def __init__(self, state_fn=None, reward_fn=None, done_fn=None, info_fn=None, update_fn=None, start_fn=None,
+                 env='simple', **kwargs):
+        # Constants (MRS.py:24-35) + the batching ones
+        self.N_AGENTS = 1
+        self.K_HOPS = 0
+        self.STATE_SIZE = 0
+        self.ACTION_DIM = 0
+        self.AGENT_RADIUS = 0.3
+        self.COMM_RANGE = float('inf')
+        self.RETURN_A = False
+        self.RETURN_EVENTS = False
+        self.ACTION_TYPE = 'set_target_vel'
+        self.HEADLESS = True
+        self.MAX_TIMESTEPS = float('inf')
+        self.N_ENVS = 1
+        self.DEVICE = 'cuda'
+        self.TAPE_SLOTS = None
+        self.CHECK_NAN = 'auto'
+        self.COPY_OBS = None
+        self.BATCHED = None          # None: batched shapes iff N_ENVS > 1
+        self.set_constants(kwargs)
+        if env != 'simple':
+            raise NotImplementedError("only the 'simple' world (N x cf2x + ground plane, EnvCreator.py:7-13) is in scope")
+        self.state_fn = state_fn
+        self.reward_fn = reward_fn if (reward_fn is not None) else (lambda **kwargs: 0.0)
+        self.done_fn = done_fn if (done_fn is not None) else (
+            lambda **kwargs: kwargs['steps_since_reset'] >= self.MAX_TIMESTEPS)
+        self.info_fn = info_fn if (info_fn is not None) else (lambda **kwargs: {})
+        self.update_fn = update_fn
+        self.start_fn = start_fn
+        self.sim = _Sim(**kwargs)
+        self.START_POS = _spawn.DefaultSpawn(self.N_AGENTS)
+        self.START_ORI = torch.tensor([0, 0, -np.pi / 2, 0, 0, np.pi / 2]).expand(self.N_AGENTS, -1)
+        self.set_constants(kwargs)
+        if isinstance(self.START_ORI, torch.Tensor) and self.START_ORI.dim() == 1:
+            self.START_ORI = self.START_ORI.expand(self.N_AGENTS, -1)
+        self._batched = (self.N_ENVS > 1) if self.BATCHED is None else bool(self.BATCHED)
+        self._copy = (not self._batched) if self.COPY_OBS is None else bool(self.COPY_OBS)
+        # state_fn: None / 'pos_vel' / 'full' -> fused in the step kernel; callable -> python
+        if state_fn is None:
+            state_fn = 'pos_vel'
+        if isinstance(state_fn, str):
+            layout, custom_D = _LAYOUTS[state_fn], 0
+        else:
+            layout = _abi.X_NONE
+            custom_D = self.STATE_SIZE
+        self._layout = layout
+        self.swarm = None
+        self._build(layout, custom_D)
+        self.steps_since_reset = 0
+        self.last_action = None
+        self.last_obs = None
+        self.last_loop_time = time.monotonic()
+        self.is_initialised = False
+        self.reset()
+
+    # ------------------------------------------------------------------ construction
+    def set_constants(self, kwargs):
+        for name, val in kwargs.items():
+            if name in self.__dict__:
+                self.__dict__[name] = val
+
+    def _build(self, layout, custom_D):
+        if layout == _abi.X_NONE and custom_D <= 0:
+            # probe the user's state_fn once on a throw-away one-env swarm to learn D
+            probe = Swarm(1, self.N_AGENTS, 0, self.ACTION_TYPE, _abi.X_POS_VEL, device=self.DEVICE, want_A=False)
+            custom_D = int(self._call_state_fn(probe).shape[-1])
+        self.swarm = Swarm(self.N_ENVS, self.N_AGENTS, self.K_HOPS, self.ACTION_TYPE, layout, self.COMM_RANGE,
+                           dt=self.sim.DT, gravity=self.sim.GRAVITY, agent_radius=self.AGENT_RADIUS,
+                           device=self.DEVICE, tape_slots=self.TAPE_SLOTS, want_A=True, custom_D=custom_D)
+        self.STATE_SIZE = self.swarm.D
+        self.ACTION_DIM = self.swarm.action_dim
+        self.env = Environment(self.swarm, squeeze=not self._batched)
+        self._built_K = self.K_HOPS
+
+    def _call_state_fn(self, swarm):
+        """User state_fn on the whole batch -> [E, N, D] float32."""
+        out = self.state_fn(AgentBatch(swarm))
+        out = torch.as_tensor(out, dtype=torch.float32, device=swarm.device)
+        if out.dim() == 2 and out.shape[1] == swarm.S:        # [D, E*N] (reference-style 1-D code)
+            out = out.t()
+        return out.reshape(swarm.E, swarm.N, -1)
+
+    def _sync_cfg(self):
+        """Attributes are mutable after construction in the reference (e.g. analytics.py:40)."""
+        if self.K_HOPS != self._built_K:
+            raise RuntimeError('K_HOPS cannot change after construction (tape geometry); build a new MRS')
+        c = self.swarm.cfg
+        c.comm_range = float(self.COMM_RANGE)
+        c.phys.agent_radius = float(self.AGENT_RADIUS)
+        c.dt, c.gravity = float(self.sim.DT), float(self.sim.GRAVITY)
+
+    # ------------------------------------------------------------------ observation windows
+    def _shape(self, w):
+        # w: [K+1, E, N, *] tape view, newest first
+        if self._batched:
+            w = w.permute(1, 0, 2, 3)
+        else:
+            w = w[:, 0]
+        return w.clone() if self._copy else w
+
+    def get_Xk(self):
+        return self._shape(self.swarm.X_window())
+
+    def get_Ak(self):
+        return self._shape(self.swarm.A_window())
+
+    def calc_Xk(self):
+        """MRS.calc_Xk (MRS.py:87-95): push X of the current state."""
+        hx = self.swarm.push_X()
+        if self._layout == _abi.X_NONE:
+            self.swarm.X_tape[hx] = self._call_state_fn(self.swarm)
+        return self.get_Xk()
+
+    def calc_Ak(self):
+        """MRS.calc_Ak (MRS.py:102-110): push A of the current positions."""
+        self._sync_cfg()
+        self.swarm.push_A()
+        return self.get_Ak()
+
+    def calc_A(self):
+        self._sync_cfg()
+        A = self.swarm.adjacency(self.swarm.get_pos())
+        return A if self._batched else A[0]
+
+    def get_relative_position(self, pos):
+        N = pos.shape[-2]
+        return pos.unsqueeze(-2).expand(*pos.shape[:-2], N, N, 3) - pos.unsqueeze(-3).expand(*pos.shape[:-2], N, N, 3)
+
+    # ------------------------------------------------------------------ reset / set
+    def generate_start_pos(self):
+        """MRS.generate_start_pos (MRS.py:127-154), batched: tensor START_POS is used as is;
+        a distribution is sampled per env with the same 2*AGENT_RADIUS rejection rule."""
+        if isinstance(self.START_POS, torch.Tensor):
+            return self.START_POS
+        return _spawn.sample_start_pos(self.START_POS, self.N_ENVS, self.N_AGENTS, self.AGENT_RADIUS)
+
+    def generate_start_ori(self):
+        ori = torch.as_tensor(self.START_ORI, dtype=torch.float32)
+        if ori.shape[-1] == 3:
+            return ori
+        lo, hi = ori[..., :3], ori[..., 3:]
+        shape = (self.N_ENVS,) + tuple(lo.shape) if lo.dim() == 2 else tuple(lo.shape)
+        return lo + (hi - lo) * torch.rand(shape)
+
+    def _after_state_change(self):
+        """Tail of MRS.reset / MRS.set (MRS.py:185-192): clear rings, steps := 0, start_fn, X0."""
+        self.steps_since_reset = 0
+        if self.start_fn is not None:
+            self.start_fn(self)
+        self.swarm.reset_windows()
+        if self._layout == _abi.X_NONE:
+            self.swarm.X_tape[self.swarm.hx] = self._call_state_fn(self.swarm)
+            self.swarm.fill_X_history()
+        Xk = self.get_Xk()
+        self.last_obs = Xk
+        return Xk
+
+    def reset(self, pos=None, ori=None, vel=None, angvel=None, env_mask=None):
+        """MRS.reset (MRS.py:174-192).  PID integrators are NOT reset (reference behaviour)."""
+        self.is_initialised = True
+        if pos is None:
+            pos = self.generate_start_pos()
+        if ori is None:
+            ori = self.generate_start_ori()
+        if vel is None:
+            vel = torch.zeros(self.N_AGENTS, 3)
+        if angvel is None:
+            angvel = torch.zeros(self.N_AGENTS, 3)
+        self.swarm.set_state(pos=pos, ori=ori, vel=vel, angvel=angvel, env_mask=env_mask)
+        return self._after_state_change()
+
+    def set(self, pos=None, ori=None, vel=None, angvel=None, env_mask=None):
+        """MRS.set (MRS.py:196-205): like reset, but None keeps the current value."""
+        self.swarm.set_state(pos=pos, ori=ori, vel=vel, angvel=angvel, env_mask=env_mask)
+        return self._after_state_change()
+
+    # ------------------------------------------------------------------ step
+    def _prep_actions(self, actions):
+        adim = self.swarm.action_dim
+        host = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
+        actions = torch.as_tensor(actions).detach()
+        if actions.dtype != torch.float32:
+            actions = actions.to(torch.float32)
+        check = self.CHECK_NAN
+        if (check == 'auto' and host) or check is True:
+            if bool(torch.isnan(actions).any()):
+                raise Exception('The given action contains NaN:\n %s' % str(actions))      # MRS.py:247-248
+        actions = actions.to(self.swarm.device).reshape(self.N_ENVS, self.N_AGENTS, adim).contiguous()
+        return actions
+
+    def step(self, actions, ACTION_TYPE=None):
+        """MRS.step (MRS.py:240-277)."""
+        self._sync_cfg()
+        if actions is not None:
+            if ACTION_TYPE is None:
+                ACTION_TYPE = self.ACTION_TYPE
+            self.ACTION_DIM = self.swarm.set_action_type(ACTION_TYPE)
+            actions = self._prep_actions(actions)
+            self.last_action = actions if self._batched else actions[0]
+        else:
+            self.swarm.set_action_type(None)
+        self.swarm.step(actions)
+        if self._layout == _abi.X_NONE:
+            self.swarm.X_tape[self.swarm.hx] = self._call_state_fn(self.swarm)
+        Xk = self.get_Xk()
+        Ak = self.get_Ak()
+        kw = dict(env=self.env, A=Ak, action=self.last_action, steps_since_reset=self.steps_since_reset)
+        if self.update_fn is not None:
+            self.update_fn(X=Xk, Xlast=self.last_obs, **kw)
+        reward = self.reward_fn(X=Xk, Xlast=self.last_obs, **kw)
+        self.last_obs = Xk
+        info = self.info_fn(X=Xk, Xlast=self.last_obs, **kw)
+        info['A'] = Ak
+        if self.RETURN_EVENTS:
+            info['keyboard_events'] = self.env.get_keyboard_events()
+            info['mouse_events'] = self.env.get_mouse_events()
+        done = self.done_fn(X=Xk, Xlast=self.last_obs, **kw)
+        self.last_loop_time = time.monotonic()
+        self.steps_since_reset += 1
+        return Xk, reward, done, info
+
+    def step_many(self, actions, ACTION_TYPE=None):
+        """T steps with pre-computed actions [T, E, N, A] in one launch (state stays on chip);
+        the rollout loop of examples/simulating_data/helper/DataGenerator.py:8-48 without the
+        per-step host round trip.  Returns the final (X, A) windows; callbacks are not called."""
+        self._sync_cfg()
+        if self._layout == _abi.X_NONE:
+            raise RuntimeError('step_many needs a fused state layout (state_fn "pos_vel" or "full")')
+        if ACTION_TYPE is None:
+            ACTION_TYPE = self.ACTION_TYPE
+        adim = self.swarm.set_action_type(ACTION_TYPE)
+        actions = torch.as_tensor(actions, dtype=torch.float32).to(self.swarm.device)
+        T = actions.shape[0]
+        actions = actions.reshape(T, self.N_ENVS, self.N_AGENTS, adim).contiguous()
+        self.swarm.step_many(actions, T)
+        self.steps_since_reset += T
+        Xk = self.get_Xk()
+        self.last_obs = Xk
+        return Xk, self.get_Ak()
+
+    def check_status(self):
+        """Lazy NaN / non-finite guard for device-resident actions (synchronises)."""
+        v = self.swarm.read_status()
+        if v & _abi.STATUS_NAN_ACTION:
+            raise Exception('The given action contains NaN')
+        if v & _abi.STATUS_NONFINITE:
+            raise FloatingPointError('simulation state left the finite range')
+
+    # ------------------------------------------------------------------ misc API parity
+    def set_data(self, name, val):
+        self.env.set_data(name, val)
+
+    def get_data(self, name):
+        return self.env.get_data(name)
+
+    def close(self):
+        pass
+
+    def render(self, mode='bullet', close=False):
+        if close:
+            self.close()
+
+    def wait(self, dt=None):
+        if dt is None:
+            dt = self.sim.DT
+        diff = time.monotonic() - self.last_loop_time
+        time.sleep(max(dt - diff, 0))
+
+    def get_env(self):
+        return self.env
+
+    def get_objects(self):
+        return self.env.objects
+
+    def get_agents(self):
+        return self.env.agents
+
+    def get_controlled(self):
+        return self.env.controlled
+
+    def get_object_dict(self):
+        return self.env.object_dict

@@ -1,0 +1,118 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol
+include/mrs_b200.h declares, the ctypes mirror matches the compiled structs, compute calls
+fail loudly without a GPU (no fallback), env sharding and the statistics reduction (gloo,
+world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import _REPO
+
+HEADER = os.path.join(_REPO, 'include', 'mrs_b200.h')
+
+
+def _lib():
+    from mrsgym_b200 import _abi
+    if not os.path.isfile(_abi.LIB_PATH):
+        sys.path.insert(0, _REPO)
+        import __graft_entry__
+        __graft_entry__.build()
+    return _abi
+
+
+def test_header_symbols_are_exported():
+    _abi = _lib()
+    text = open(HEADER).read()
+    names = set(re.findall(r'^\s*(?:int|size_t|const char\*)\s+(mrs_\w+)\s*\(', text, flags=re.M))
+    assert len(names) >= 13
+    handle = ctypes.CDLL(_abi.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), n
+    assert names == set(_abi.EXPORTS)
+
+
+def test_struct_mirror_and_defaults():
+    _abi = _lib()
+    lib = _abi.lib()
+    assert lib.mrs_abi_version() == _abi.ABI_VERSION
+    assert lib.mrs_sizeof_config() == ctypes.sizeof(_abi.MrsConfig)
+    assert lib.mrs_sizeof_buffers() == ctypes.sizeof(_abi.MrsBuffers)
+    cfg = _abi.default_config()
+    from oracle import bullet_model as bm, spec
+    Q, P = bm.QuadParams(), bm.PhysicsParams()
+    assert cfg.quad.mass == np.float32(Q.mass) and cfg.quad.kf == np.float32(Q.kf)
+    assert abs(cfg.quad.gnd_hclip - Q.derived()['GroundEffectHClip']) < 1e-8
+    np.testing.assert_allclose(list(cfg.phys.inertia), P.inertia_diag(), rtol=1e-6)
+    np.testing.assert_allclose(np.array(list(cfg.quad.nnls_tab)).reshape(16, 4, 4), spec.nnls_subset_tables(), atol=1e-7)
+    np.testing.assert_allclose(np.array(list(cfg.quad.mix_ainv)).reshape(4, 4), spec.MIX_AINV, atol=1e-7)
+    for mode, code in _abi.ACTION_TYPES.items():
+        assert lib.mrs_action_dim(code) == spec.ACTION_DIMS[mode]
+    assert lib.mrs_state_dim(_abi.X_POS_VEL) == 6 and lib.mrs_state_dim(_abi.X_FULL) == 13
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
+def test_no_cpu_fallback():
+    import mrsgym_b200 as M
+    with pytest.raises(Exception):
+        M.Swarm(1, 3)
+    with pytest.raises(M.MrsError):
+        M.Swarm(1, 3, device='cpu')
+    # argument errors are reported, not crashed on
+    _abi = M._abi
+    assert _abi.lib().mrs_step(None, None, None, 0, 0, None) == -1
+    assert b'argument' in _abi.lib().mrs_strerror(-1)
+
+
+def test_shard_range_partitions_envs():
+    from mrsgym_b200 import shard_range
+    for E in (1, 7, 64, 65536, 65537):
+        for W in (1, 2, 3, 8):
+            spans = [shard_range(E, r, W) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == E
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_spawn_rejection_sampler():
+    from mrsgym_b200 import DefaultSpawn, sample_start_pos
+    torch.manual_seed(0)
+    d = DefaultSpawn(6)
+    s = d.sample()
+    assert s.shape == (6, 3)
+    assert float(s[:, :2].norm(dim=-1).max()) <= 1.0 + 1e-6 and 1.0 <= float(s[:, 2].min()) and float(s[:, 2].max()) <= 3.0
+    pos = sample_start_pos(d, 32, 6, 0.3)
+    dist = (pos.unsqueeze(2) - pos.unsqueeze(1)).norm(dim=-1) + 10 * torch.eye(6)
+    assert float(dist.min()) >= 0.6
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(%(repo)r, 'mrs-gym_b200'))
+from mrsgym_b200.core import shard_range
+from mrsgym_b200.dist import allreduce_stats, init_from_env
+rank, world = init_from_env(backend='gloo')
+lo, hi = shard_range(10, rank, world)
+stats = torch.tensor([hi - lo, rank + 1, 0, 0, 0, 0, 0, 0], dtype=torch.int64)
+out = allreduce_stats(stats)
+assert out.tolist()[:2] == [10, 3], out
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+def test_stats_allreduce_gloo_world2(tmp_path):
+    script = tmp_path / 'w.py'
+    script.write_text(_WORKER % dict(repo=_REPO))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29591', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all('ok' in o for o in outs)

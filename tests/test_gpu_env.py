@@ -1,0 +1,123 @@
+"""The reference-facing Python surface (mrsgym_b200.make('mrs-v0') / MRS.step) on the GPU:
+shapes, callback order, error behaviour and the README example against the golden the
+reference's own Python produced."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_example_c1_vs_golden():
+    """BASELINE configs[0]: 'simple' env, N_AGENTS=3, set_target_vel, K_HOPS=0 (README.md:21-40)."""
+    import mrsgym_b200 as mrsgym
+    g = np.load(os.path.join(GOLDEN, 'ref_c1_vel.npz'))
+    env = mrsgym.make('mrs-v0', state_fn=lambda quad: torch.cat([quad.get_pos(), quad.get_vel()]),
+                      N_AGENTS=3, K_HOPS=0, ACTION_TYPE='set_target_vel', HEADLESS=True,
+                      START_POS=torch.tensor(g['start_pos'], dtype=torch.float32), START_ORI=torch.zeros(3, 3))
+    assert env.STATE_SIZE == 6
+    X0 = env.reset()
+    assert tuple(X0.shape) == (1, 3, 6)
+    np.testing.assert_allclose(X0.cpu().numpy(), g['X0'], atol=1e-6)
+    for t in range(int(g['T'])):
+        X, reward, done, info = env.step(torch.tensor(g['actions'][t]))
+        assert tuple(X.shape) == (1, 3, 6) and tuple(info['A'].shape) == (1, 3, 3)
+        assert reward == 0.0 and done is False
+    np.testing.assert_allclose(X.cpu().numpy(), g['X'][-1], atol=1e-3)
+    np.testing.assert_array_equal(info['A'].cpu().numpy(), g['A'][-1])
+
+
+def test_callbacks_order_and_arguments():
+    import mrsgym_b200 as mrsgym
+    log = []
+
+    def update_fn(**kw):
+        log.append(('update', kw['steps_since_reset'], kw['Xlast'] is kw['X']))
+
+    def reward_fn(**kw):
+        log.append(('reward', kw['steps_since_reset'], kw['Xlast'] is kw['X']))
+        return 1.5
+
+    def info_fn(**kw):
+        log.append(('info', kw['steps_since_reset'], kw['Xlast'] is kw['X']))
+        return {'n': kw['env'].get_pos().shape[0]}
+
+    def done_fn(**kw):
+        log.append(('done', kw['steps_since_reset'], kw['Xlast'] is kw['X']))
+        return kw['steps_since_reset'] >= 1
+
+    env = mrsgym.MRS(state_fn='pos_vel', reward_fn=reward_fn, info_fn=info_fn, update_fn=update_fn, done_fn=done_fn,
+                     N_AGENTS=4, K_HOPS=2, COMM_RANGE=5.0, START_POS=torch.tensor(H.grid_positions(1, 4)[0]),
+                     START_ORI=torch.zeros(4, 3))
+    X, r, d, info = env.step(torch.zeros(4, 3))
+    # reference order: update, reward, (last_obs := X), info, done; callbacks see the pre-increment
+    # counter; info_fn / done_fn see Xlast is X (MRS.py:260-274)
+    assert [l[0] for l in log] == ['update', 'reward', 'info', 'done']
+    assert [l[1] for l in log] == [0, 0, 0, 0]
+    assert [l[2] for l in log] == [False, False, True, True]
+    assert r == 1.5 and d is False and info['n'] == 4 and 'A' in info
+    assert env.steps_since_reset == 1
+    X, r, d, info = env.step(torch.zeros(12))          # flat actions are reshaped (MRS.py:245-246)
+    assert d is True
+    assert tuple(X.shape) == (3, 4, 6) and tuple(info['A'].shape) == (3, 4, 4)
+
+
+def test_error_behaviour():
+    import mrsgym_b200 as mrsgym
+    env = mrsgym.MRS(N_AGENTS=2, START_POS=torch.tensor([[0., 0, 1], [1, 0, 1]]), START_ORI=torch.zeros(2, 3))
+    with pytest.raises(Exception, match='NaN'):
+        env.step(torch.tensor([[float('nan'), 0, 0], [0, 0, 0]]))
+    with pytest.raises(AttributeError):
+        env.step(torch.zeros(2, 3), ACTION_TYPE='set_nothing')
+    # device-resident NaN actions: flagged by the kernel, raised lazily
+    env.step(torch.full((2, 3), float('nan'), device='cuda'))
+    with pytest.raises(Exception, match='NaN'):
+        env.check_status()
+    with pytest.raises(mrsgym.MrsError):
+        mrsgym.Swarm(1, 2, device='cpu')
+
+
+def test_batched_env_shapes_and_modes():
+    import mrsgym_b200 as mrsgym
+    E, N, K = 16, 8, 3
+    pos = torch.tensor(H.grid_positions(E, N, z0=3.0), dtype=torch.float32)
+    env = mrsgym.make('mrs-v0', N_ENVS=E, N_AGENTS=N, K_HOPS=K, COMM_RANGE=2.0, ACTION_TYPE='set_target_pos',
+                      START_POS=pos, state_fn='full')
+    X, r, d, info = env.step(pos.cuda() + 0.1)
+    assert tuple(X.shape) == (E, K + 1, N, 13) and tuple(info['A'].shape) == (E, K + 1, N, N)
+    for mode, adim in [('set_speeds', 4), ('set_control', 4), ('set_force', 3), ('set_target_ori', 3),
+                       ('set_target_accel', 3), ('set_target_vel', 3)]:
+        a = torch.zeros(E, N, adim)
+        if mode == 'set_speeds':
+            a += H.HOVER
+        if mode == 'set_control':
+            a[..., 0] = 9.81
+        X, r, d, info = env.step(a, ACTION_TYPE=mode)
+        assert env.ACTION_DIM == adim
+    assert torch.isfinite(X).all()
+    env.check_status()
+    # no action at all (MRS.step(None)): free fall, still returns observations
+    z0 = env.env.get_pos()[..., 2].clone()
+    env.step(None)
+    assert bool((env.env.get_pos()[..., 2] < z0).all())
+    # calc_Ak outside step shifts only the A ring (DataGenerator.py:23)
+    Xk = env.get_Xk().clone()
+    Ak = env.calc_Ak()
+    assert torch.equal(env.get_Xk(), Xk) and torch.equal(Ak[:, 0], Ak[:, 1])
+
+
+def test_default_reset_spawns_collision_free():
+    import mrsgym_b200 as mrsgym
+    env = mrsgym.MRS(N_ENVS=8, N_AGENTS=6)
+    p = env.env.get_pos()
+    d = (p.unsqueeze(2) - p.unsqueeze(1)).norm(dim=-1) + 10 * torch.eye(6, device=p.device)
+    assert float(d.min()) >= 2 * env.AGENT_RADIUS
+    yaw = env.env.get_ori()[..., 2]
+    assert float(yaw.abs().max()) <= np.pi / 2 + 1e-5
+    X = env.reset()
+    assert tuple(X.shape) == (8, 1, 6, 6)

@@ -1,0 +1,354 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via mrsgym_b200.Swarm / MRS)
+against the CPU oracle on identical seeded inputs and against the committed golden vectors that
+the reference's own Python produced (tests/golden/ref_*.npz).
+
+Tolerances (BASELINE.json north_star):
+  * adjacency A: bit-exact given identical positions;
+  * one-step state deltas: |d_gpu - d_ref| <= 1e-4 * |d_ref| + floor, the floor being the float32
+    resolution of the stored quantity (the GPU state is float32, Bullet's is float64):
+    pos 5e-7 m (1 ulp at 4-8 m), vel 5e-7 m/s, angvel 1e-5 rad/s, quaternion 3e-7;
+  * 100-step free-flight trajectories: position <= 1e-3 m, attitude <= 1e-3 rad;
+    contact trajectories (approximate by design): position <= 5e-2 m.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from conftest import GOLDEN
+from oracle import spec
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+FLOOR = dict(pos=5e-7, vel=5e-7, angvel=1e-5, quat=3e-7)
+
+
+def _swarm(E, N, mode, K=0, comm_range=float('inf'), layout=None, **kw):
+    import mrsgym_b200 as M
+    layout = M._abi.X_POS_VEL if layout is None else layout
+    return M.Swarm(E, N, K, mode, layout, comm_range, **kw)
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _check_delta(tag, s0, g1, r1):
+    """one-step deltas, GPU vs oracle, both measured from the common start state s0"""
+    worst = {}
+    for k in ('pos', 'vel', 'angvel', 'quat'):
+        base = s0[k].astype(np.float64)
+        dg, dr = g1[k] - base, r1[k] - base
+        if k == 'quat':       # q and -q are the same rotation
+            flip = np.sum(g1[k] * r1[k], axis=-1, keepdims=True) < 0
+            dg = np.where(flip, -g1[k], g1[k]) - base
+        err = np.abs(dg - dr)
+        tol = REL * np.abs(dr) + FLOOR[k]
+        worst[k] = float(np.max(err / tol))
+        assert np.all(err <= tol), '%s: %s delta off by %.3g x tolerance (max err %.3g)' % (
+            tag, k, worst[k], err.max())
+    return worst
+
+
+# ------------------------------------------------------------------------------ adjacency
+@pytest.mark.parametrize('E,N,R', [(1, 3, 1.5), (64, 8, 2.0), (16, 32, 2.0), (7, 5, 0.9), (3, 33, 1.7),
+                                   (2, 128, 2.0), (1, 500, 3.0), (1, 4096, 2.0), (4, 16, float('inf')),
+                                   (1, 256, float('inf'))])
+def test_adjacency_bit_exact_vs_torch_cpu(E, N, R):
+    rng = np.random.default_rng(1000 + N)
+    # lattice points (distances hit COMM_RANGE exactly) + jitter on half of the envs
+    pos = H.grid_positions(E, N, spacing=0.5, z0=1.0, jitter=0.0)
+    pos[E // 2:] += rng.uniform(-0.3, 0.3, pos[E // 2:].shape)
+    pos32 = pos.astype(np.float32)
+    sw = _swarm(E, N, 'set_speeds', 0, R)
+    A = sw.adjacency(_dev(pos32)).cpu()
+    ref = H.torch_cpu_adjacency(pos32, R)
+    assert A.shape == ref.shape
+    assert int((A != ref).sum()) == 0
+    np.testing.assert_array_equal(A.numpy(), spec.adjacency(pos32, R))
+    assert torch.equal(A, A.transpose(-1, -2)) and float(torch.diagonal(A, dim1=-2, dim2=-1).abs().sum()) == 0.0
+
+
+def test_adjacency_threshold_edges():
+    """distances one float32 ulp either side of COMM_RANGE, NaN positions, zero range"""
+    R = 2.0
+    base = np.zeros((1, 8, 3), np.float32)
+    d = np.float32(R)
+    offs = [np.nextafter(d, np.float32(0)), d, np.nextafter(d, np.float32(10)), np.float32(1.9999), np.float32(2.0001)]
+    for i, o in enumerate(offs):
+        base[0, i + 1, 0] = o
+    base[0, 7] = np.nan
+    sw = _swarm(1, 8, 'set_speeds', 0, R)
+    A = sw.adjacency(_dev(base)).cpu()
+    assert int((A != H.torch_cpu_adjacency(base, R)).sum()) == 0
+    assert float(A[0, 7].sum()) == 0.0
+    for Rz in (0.0, 1e-30, 1e30):
+        sw = _swarm(1, 8, 'set_speeds', 0, Rz)
+        A = sw.adjacency(_dev(base)).cpu()
+        assert int((A != H.torch_cpu_adjacency(base, Rz)).sum()) == 0
+
+
+# ------------------------------------------------------------------------------ one step
+@pytest.mark.parametrize('mode', H.MODES)
+@pytest.mark.parametrize('E,N', [(64, 8), (5, 3), (8, 32), (3, 40)])
+def test_one_step_delta_vs_oracle(mode, E, N):
+    rng = np.random.default_rng(sum(map(ord, mode)) * 1000 + E * 37 + N)
+    st = H.random_state(rng, E, N, spacing=0.9)
+    act = H.random_actions(rng, mode, 1, E, N, start_pos=st['pos'])
+    sw = _swarm(E, N, mode, 1, 1.5)
+    H.upload_state(sw, st)
+    sw.step(_dev(act[0]))
+    torch.cuda.synchronize()
+    g1 = H.read_state(sw)
+    ref = H.make_spec(E, N, mode, 1, 1.5, st)
+    Xr, Ar = ref.step(act[0])
+    _check_delta('%s E%d N%d' % (mode, E, N), st, g1, H.spec_state(ref))
+    # observation written by the same launch: X = float32 state, A = adjacency of ITS positions
+    X = sw.X_window()[0].cpu().numpy()
+    np.testing.assert_array_equal(X[..., :3], g1['pos'].astype(np.float32))
+    np.testing.assert_array_equal(X[..., 3:], g1['vel'].astype(np.float32))
+    A = sw.A_window()[0].cpu().numpy()
+    np.testing.assert_array_equal(A, spec.adjacency(X[..., :3], 1.5))
+    assert sw.read_status() == 0
+
+
+@pytest.mark.parametrize('mode', ['set_target_vel', 'set_target_pos'])
+def test_controller_state_carries_over_steps(mode):
+    """second and third controller calls use the stored PID planes (integrators, d_vel_e, last_*)"""
+    E, N, T = 16, 8, 3
+    rng = np.random.default_rng(77)
+    st = H.random_state(rng, E, N)
+    act = H.random_actions(rng, mode, T, E, N, start_pos=st['pos'])
+    sw = _swarm(E, N, mode, 0)
+    H.upload_state(sw, st)
+    ref = H.make_spec(E, N, mode, 0, float('inf'), st)
+    for t in range(T):
+        s0 = H.read_state(sw)
+        # restart the oracle from the GPU's float32 state so that each step is a one-step test
+        ref.set_state(pos=s0['pos'], quat=s0['quat'], vel=s0['vel'], angvel=s0['angvel'])
+        sw.step(_dev(act[t]))
+        ref.step(act[t])
+        _check_delta('%s step %d' % (mode, t), {k: v.astype(np.float32) for k, v in s0.items()}, H.read_state(sw),
+                     H.spec_state(ref))
+
+
+def test_no_action_step_is_free_fall():
+    E, N = 4, 8
+    rng = np.random.default_rng(5)
+    st = H.random_state(rng, E, N)
+    sw = _swarm(E, N, 'set_speeds')
+    H.upload_state(sw, st)
+    sw.set_action_type(None)
+    sw.step(None)
+    ref = H.make_spec(E, N, 'set_speeds', 0, float('inf'), st)
+    ref.step(None)
+    _check_delta('no action', st, H.read_state(sw), H.spec_state(ref))
+
+
+# ------------------------------------------------------------------------------ contact
+@pytest.mark.parametrize('N', [4, 16, 48])
+def test_contact_one_step(N):
+    """ground landing + AGENT_RADIUS sphere-sphere rows (C3 regime: 0.55 m spacing < 2*0.3)"""
+    E = 32
+    rng = np.random.default_rng(300 + N)
+    st = H.random_state(rng, E, N, spacing=0.55, z0=0.62, jitter=0.03, tilt=0.05, vel=0.5, angvel=0.2)
+    st['vel'][..., 2] -= 1.0
+    act = H.random_actions(rng, 'set_control', 1, E, N)
+    sw = _swarm(E, N, 'set_control', 0)
+    H.upload_state(sw, st)
+    sw.step(_dev(act[0]))
+    ref = H.make_spec(E, N, 'set_control', 0, float('inf'), st)
+    ref.step(act[0])
+    g1, r1 = H.read_state(sw), H.spec_state(ref)
+    # contact rows switch on thresholds (dist < margin, rhs > 0): allow a float32-sized band
+    for k, tol in (('vel', 2e-4), ('pos', 2e-6), ('angvel', 1e-4)):
+        assert np.max(np.abs(g1[k] - r1[k])) <= tol, k
+    stats = sw.read_stats()
+    assert stats['agent_contact_rows'] > 0 and stats['ground_contacts'] > 0
+
+
+# ------------------------------------------------------------------------------ goldens
+TRAJ = sorted(glob.glob(os.path.join(GOLDEN, 'ref_*.npz')))
+
+
+@pytest.mark.parametrize('path', TRAJ, ids=[os.path.basename(f)[4:-4] for f in TRAJ])
+def test_trajectory_vs_reference_golden(path):
+    """GPU rollout from the golden start state with the golden actions vs the trajectory the
+    reference's own Python produced (oracle/make_golden.py)."""
+    g = np.load(path)
+    N, K, T, mode = int(g['N']), int(g['K']), int(g['T']), str(g['mode'])
+    R = float(g['comm_range'])
+    st = dict(pos=g['start_pos'][None], quat=g['start_quat'][None], vel=g['start_vel'][None],
+              angvel=g['start_angvel'][None])
+    st = {k: v.astype(np.float32) for k, v in st.items()}
+    sw = _swarm(1, N, mode, K, R, agent_radius=float(g['agent_radius']), dt=float(g['dt']))
+    H.upload_state(sw, st)
+    contact = 'contact' in path
+    ptol, atol = (5e-2, 5e-2) if contact else (1e-3, 1e-3)
+    worst_p = worst_a = 0.0
+    for t in range(T):
+        sw.step(_dev(g['actions'][t][None]))
+        s = H.read_state(sw)
+        worst_p = max(worst_p, float(np.abs(s['pos'][0] - g['pos'][t]).max()))
+        worst_a = max(worst_a, float(H.quat_angle(s['quat'][0], g['quat'][t]).max()))
+        if t == 0 and not contact:
+            # first step: rpm-level agreement shows up as a tight velocity match
+            assert np.abs(s['vel'][0] - g['vel'][0]).max() < 2e-6
+            assert np.abs(s['angvel'][0] - g['angvel'][0]).max() < 5e-5
+    assert worst_p <= ptol, 'position drift %.3g m' % worst_p
+    assert worst_a <= atol, 'attitude drift %.3g rad' % worst_a
+    # observation windows of the last step: ring order newest-first, K+1 deep
+    X = sw.X_window()[:, 0].cpu().numpy()
+    assert X.shape == g['X'][-1].shape
+    np.testing.assert_allclose(X, g['X'][-1], atol=10 * ptol, rtol=0)
+    A = sw.A_window()[:, 0].cpu().numpy()
+    assert A.shape == g['A'][-1].shape
+    for k in range(K + 1):
+        np.testing.assert_array_equal(A[k], spec.adjacency(X[k][:, :3], R))
+    assert sw.read_status() == 0
+
+
+# ------------------------------------------------------------------------------ rings / many / shards
+def test_ring_semantics_match_reference():
+    """X padded with copies of X0, A padded with zeros, newest first, independent heads
+    (MRS.py:87-114), across several tape wrap-arounds."""
+    E, N, K, T = 3, 8, 3, 40
+    rng = np.random.default_rng(11)
+    st = H.random_state(rng, E, N)
+    act = H.random_actions(rng, 'set_speeds', T, E, N)
+    sw = _swarm(E, N, 'set_speeds', K, 1.2, tape_slots=2 * K + 2)
+    H.upload_state(sw, st)
+    X0 = sw.X_window().clone()
+    assert all(torch.equal(X0[0], X0[k]) for k in range(K + 1))
+    newest_X, newest_A = [X0[0]], []
+    for t in range(T):
+        sw.step(_dev(act[t]))
+        Xw, Aw = sw.X_window().clone(), sw.A_window().clone()
+        newest_X.insert(0, Xw[0])
+        newest_A.insert(0, Aw[0])
+        for k in range(K + 1):
+            want = newest_X[k] if k < len(newest_X) else newest_X[-1]
+            assert torch.equal(Xw[k], want), (t, k)
+            if k < len(newest_A):
+                assert torch.equal(Aw[k], newest_A[k]), (t, k)
+            else:
+                assert float(Aw[k].abs().sum()) == 0.0, (t, k)
+
+
+@pytest.mark.parametrize('N,mode', [(8, 'set_speeds'), (32, 'set_target_pos'), (3, 'set_target_vel'), (40, 'set_control')])
+def test_step_many_equals_repeated_step(N, mode):
+    E, K, T = 33, 2, 23
+    rng = np.random.default_rng(21)
+    st = H.random_state(rng, E, N)
+    act = _dev(H.random_actions(rng, mode, T, E, N, start_pos=st['pos']))
+    a = _swarm(E, N, mode, K, 1.5, tape_slots=12)
+    b = _swarm(E, N, mode, K, 1.5, tape_slots=12)
+    H.upload_state(a, st)
+    H.upload_state(b, st)
+    for t in range(T):
+        a.step(act[t])
+    b.step_many(act, T)
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(a.ctrl.nan_to_num(nan=-7.0), b.ctrl.nan_to_num(nan=-7.0))
+    assert torch.equal(a.X_window(), b.X_window()) and torch.equal(a.A_window(), b.A_window())
+
+
+@pytest.mark.parametrize('N', [8, 40])
+def test_env_shards_are_independent(N):
+    """1-GPU result == concatenation of per-shard results, bit for bit."""
+    import mrsgym_b200 as M
+    E, T = 50, 5
+    rng = np.random.default_rng(31)
+    st = H.random_state(rng, E, N)
+    act = H.random_actions(rng, 'set_target_vel', T, E, N)
+    full = _swarm(E, N, 'set_target_vel', 1, 1.5)
+    H.upload_state(full, st)
+    full.step_many(_dev(act), T)
+    parts = []
+    for r in range(3):
+        lo, hi = M.shard_range(E, r, 3)
+        sh = _swarm(hi - lo, N, 'set_target_vel', 1, 1.5)
+        H.upload_state(sh, {k: v[lo:hi] for k, v in st.items()})
+        sh.step_many(_dev(act[:, lo:hi]), T)
+        parts.append(sh)
+    S = full.S
+    cat = torch.cat([p.state for p in parts], dim=1)
+    assert torch.equal(full.state, cat)
+    assert torch.equal(full.A_window(), torch.cat([p.A_window() for p in parts], dim=1))
+    assert torch.equal(full.X_window(), torch.cat([p.X_window() for p in parts], dim=1))
+
+
+def test_set_state_euler_and_mask():
+    from scipy.spatial.transform import Rotation as R
+    E, N = 6, 5
+    rng = np.random.default_rng(41)
+    sw = _swarm(E, N, 'set_speeds')
+    pos = rng.uniform(-2, 2, (E, N, 3)).astype(np.float32)
+    ori = rng.uniform(-1.4, 1.4, (E, N, 3)).astype(np.float32)
+    vel = rng.uniform(-1, 1, (E, N, 3)).astype(np.float32)
+    sw.set_state(pos=pos, ori=ori, vel=vel, angvel=None)
+    s = H.read_state(sw)
+    np.testing.assert_array_equal(s['pos'].astype(np.float32), pos)
+    q = R.from_euler('xyz', ori.reshape(-1, 3).astype(np.float64)).as_quat().reshape(E, N, 4)
+    assert np.max(H.quat_angle(s['quat'], q)) < 1e-6
+    np.testing.assert_allclose(sw.get_ori().cpu().numpy(), ori, atol=2e-6)
+    # masked update touches only the selected envs; None keeps the component
+    mask = np.array([1, 0, 0, 1, 0, 0], np.uint8)
+    sw.set_state(pos=np.zeros((E, N, 3), np.float32), env_mask=mask)
+    s2 = H.read_state(sw)
+    assert np.all(s2['pos'][mask == 1] == 0) and np.array_equal(s2['pos'][mask == 0], s['pos'][mask == 0])
+    np.testing.assert_array_equal(s2['vel'], s['vel'])
+    np.testing.assert_array_equal(s2['quat'], s['quat'])
+
+
+def test_step_host_roundtrip():
+    E, N, K = 128, 8, 1
+    rng = np.random.default_rng(51)
+    st = H.random_state(rng, E, N)
+    act = H.random_actions(rng, 'set_speeds', 1, E, N)
+    a = _swarm(E, N, 'set_speeds', K, 2.0)
+    b = _swarm(E, N, 'set_speeds', K, 2.0)
+    H.upload_state(a, st)
+    H.upload_state(b, st)
+    a.step(_dev(act[0]))
+    ah = torch.from_numpy(act[0]).pin_memory()
+    Xh = torch.empty(E, N, 6).pin_memory()
+    Ah = torch.empty(E, N, N).pin_memory()
+    b.step_host(ah, torch.empty(E, N, 4, device='cuda'), Xh, Ah)
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(Xh, a.X_window()[0].cpu()) and torch.equal(Ah, a.A_window()[0].cpu())
+
+
+def test_full_size_properties_c5():
+    """BASELINE configs[4] at full size (65536 envs x 8): properties that need no oracle run --
+    A symmetric with zero diagonal and equal to the oracle adjacency of the GPU's own X on a
+    sample of envs; unit quaternions; every env of a replicated batch evolves identically."""
+    E, N, K, T = 65536, 8, 3, 20
+    rng = np.random.default_rng(61)
+    one = H.random_state(rng, 1, N, spacing=1.0, z0=2.5)
+    st = {k: np.repeat(v, E, axis=0) for k, v in one.items()}
+    a1 = H.random_actions(rng, 'set_speeds', T, 1, N)
+    act = _dev(np.repeat(a1, E, axis=1))
+    sw = _swarm(E, N, 'set_speeds', K, 2.0)
+    H.upload_state(sw, st)
+    sw.step_many(act, T)
+    A = sw.A_window()
+    X = sw.X_window()
+    assert torch.equal(A, A.transpose(-1, -2))
+    assert float(torch.diagonal(A, dim1=-2, dim2=-1).abs().sum()) == 0.0
+    assert torch.equal(X, X[:, :1].expand_as(X)) and torch.equal(A, A[:, :1].expand_as(A))
+    q = sw.get_quat()
+    assert float((q.norm(dim=-1) - 1).abs().max()) < 1e-5
+    idx = torch.tensor([0, 1, E // 2, E - 1])
+    Xs = X[:, idx].cpu().numpy()
+    np.testing.assert_array_equal(A[:, idx].cpu().numpy(), spec.adjacency(Xs[..., :3], 2.0))
+    # and the replicated env agrees with the oracle trajectory
+    ref = H.make_spec(1, N, 'set_speeds', K, 2.0, one)
+    for t in range(T):
+        ref.step(a1[t])
+    assert np.abs(sw.get_pos()[0].cpu().numpy() - ref.pos[0]).max() < 1e-4
+    assert sw.read_status() == 0
