@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the mrs-gym step path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c5|c2|c3|c4]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (default c5 = BASELINE.json configs[4], the config the metric is quoted on; it fits one
+GPU): 65536 envs x 8 agents PER GPU (weak scaling), ACTION_TYPE set_speeds, K_HOPS=3, COMM_RANGE 2.0
+(RETURN_A), built-in state_fn cat(pos, vel).  A "step" is one env.step of all envs = ONE launch of
+step_group_kernel that reads and writes the whole state in HBM.
+
+Timed region: `steps` steps issued as CUDA-graph replays of T-step rollouts (Swarm.capture_rollout;
+actions of every step are distinct device buffers), bracketed by barrier + synchronize, CUDA events
+on the launching stream, max over ranks.  L2: no flush in the headline loop -- per step the kernel
+streams actions + X + A (38 MB at c5) that are distinct every step, while the 27 MB state is
+re-read from wherever the previous step left it (that is the real access pattern of a rollout);
+`l2_flushed` reports the same step timed one launch at a time with a 512 MB read-flush in between.
+
+e2e: the same steps through mrs_step_host (C ABI, pinned HOST buffers): H2D actions, step, D2H of the
+newest X and A slices, stream sync -- every step.
+
+--impl reference: the CPU arm.  The reference is pure Python over PyBullet (not installable here,
+no network), so the CPU implementation that can run is the oracle port (oracle/spec.py, numpy,
+float64 Bullet restatement) on all host cores, one process per core, on a bounded sample of the
+same workload.  The verbatim reference Python is ~100x slower than this port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+_REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (_REPO, os.path.join(_REPO, 'mrs-gym_b200'), os.path.join(_REPO, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+HOVER = 14475.809
+
+WORKLOADS = {
+    # name: E (per GPU), N, mode, K, comm_range, spacing, z0, algorithmic bytes / agent-step
+    'c5': dict(E=65536, N=8, mode='set_speeds', K=3, R=2.0, spacing=1.0, z0=2.5, B=176,
+               desc='65536 envs x 8 agents per GPU, set_speeds, K_HOPS=3, RETURN_A COMM_RANGE=2.0 (BASELINE configs[4])'),
+    'c2': dict(E=256, N=32, mode='set_target_pos', K=3, R=2.0, spacing=1.0, z0=2.5, B=316,
+               desc='256 envs x 32 agents, set_target_pos, K_HOPS=3, RETURN_A COMM_RANGE=2.0 (BASELINE configs[1])'),
+    'c3': dict(E=4096, N=16, mode='set_control', K=0, R=float('inf'), spacing=0.7, z0=1.0, B=144,
+               desc='4096 envs x 16 agents, set_control, ground + agent contact (BASELINE configs[2])'),
+    'c4': dict(E=1, N=4096, mode='set_force', K=0, R=2.0, spacing=1.0, z0=2.0, B=16548,
+               desc='1 env x 4096 agents, set_force, adjacency dominated (BASELINE configs[3])'),
+}
+
+
+# ------------------------------------------------------------------------------ synthetic inputs
+def make_inputs(w, E, T, seed):
+    import numpy as np
+    import helpers as H
+    rng = np.random.default_rng(seed)
+    N = w['N']
+    st = H.random_state(rng, E, N, spacing=w['spacing'], z0=w['z0'], jitter=0.1, tilt=0.0, vel=0.0, angvel=0.0)
+    mode = w['mode']
+    if mode == 'set_speeds':
+        act = (HOVER * (1 + 0.05 * rng.standard_normal((T, E, N, 4), dtype=np.float32))).astype(np.float32)
+    elif mode == 'set_target_pos':
+        act = np.broadcast_to((st['pos'] + rng.normal(0, 0.5, (E, N, 3)).astype(np.float32))[None], (T, E, N, 3)).copy()
+    elif mode == 'set_control':
+        act = np.concatenate([9.81 + rng.uniform(-1, 1, (T, E, N, 1)), rng.uniform(-1, 1, (T, E, N, 3))],
+                             axis=-1).astype(np.float32)
+    elif mode == 'set_force':
+        act = rng.normal(0, 0.02, (T, E, N, 3)).astype(np.float32)
+    else:
+        act = H.random_actions(rng, mode, T, E, N, start_pos=st['pos'])
+    return st, act
+
+
+# ------------------------------------------------------------------------------ CPU arm (oracle port)
+def _cpu_worker(args):
+    wname, E, T, seed = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    import numpy as np
+    import helpers as H
+    w = WORKLOADS[wname]
+    st, act = make_inputs(w, E, T + 1, seed)
+    env = H.make_spec(E, w['N'], w['mode'], w['K'], w['R'], st)
+    env.step(act[0])                       # warm-up (imports, scipy caches)
+    t0 = time.perf_counter()
+    for t in range(T):
+        env.step(act[1 + t])
+    return time.perf_counter() - t0
+
+
+def cpu_port_throughput(wname, procs, E_per_proc, T, seed=4321):
+    """agent-steps/s of the oracle port on `procs` host processes (slowest worker's wall time)."""
+    w = WORKLOADS[wname]
+    ctx = mp.get_context('spawn')
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        walls = pool.map(_cpu_worker, [(wname, E_per_proc, T, seed + i) for i in range(procs)])
+    total = procs * E_per_proc * w['N'] * T
+    return total / max(walls), max(walls), time.perf_counter() - t0
+
+
+def cpu_sample_sizes(wname):
+    w = WORKLOADS[wname]
+    if w['N'] >= 1024:
+        return 1, 2          # one env of 4096 agents: ~N^2 pair arrays in numpy
+    return max(1, 4096 // w['N']), 8
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU through NVML while a region runs."""
+
+    def __init__(self, index, period=0.01):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+                 'hw_power_brake_slowdown': 0x80, 'sync_boost': 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': (s[len(s) // 2] if s else None), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        try:
+            return int(vis.split(',')[local])
+        except Exception:
+            return local
+    return local
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    import mrsgym_b200 as M
+    from mrsgym_b200 import dist as D
+    import helpers as H
+
+    rank, world = D.init_from_env()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    w = WORKLOADS[args.workload]
+    E = w['E'] if args.scaling == 'weak' else max(1, w['E'] // world)
+    N, K = w['N'], w['K']
+    steps, warmup = args.steps, max(args.warmup, 3)
+    T = max(d for d in range(1, min(steps, args.graph_steps) + 1) if steps % d == 0)
+    replays = steps // T
+
+    st, act_np = make_inputs(w, E, T, seed=1234 + 4 + rank)
+    sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T + 2 * K + 2)
+    H.upload_state(sw, st)
+    actions = torch.from_numpy(act_np).to(dev)
+    roll = sw.capture_rollout(actions, T)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- headline: device-resident inputs, graph replays
+    for _ in range(max(1, -(-warmup // T))):
+        roll.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(physical_gpu_index(local))
+    barrier()
+    with sampler:
+        e0.record()
+        for _ in range(replays):
+            roll.replay()
+        if world > 1:
+            stats = sw.allreduce_stats()          # the per-rollout statistics reduction (NCCL)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # keep the same load running long enough for NVML to see the clocks under load
+        t_end = time.time() + args.clock_seconds
+        while time.time() < t_end:
+            for _ in range(max(1, 2000 // T)):
+                roll.replay()
+            torch.cuda.synchronize(dev)
+    gpu_launches = replays * roll.launches_per_replay
+    ms = D.max_over_ranks(ms, dev)
+    agent_steps = float(E) * N * steps * world
+    value = agent_steps / (ms * 1e-3)
+    sw_status = sw.read_status()
+
+    # ---- same step, one launch at a time with an L2 flush in between (per-launch events)
+    flush = torch.zeros(512 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    n_f = min(steps, 20)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_f)]
+    sink = torch.zeros((), device=dev)
+    for i in range(n_f):
+        sink += flush.sum()                 # READ 512 MB: evicts L2 with clean lines (no write-back debt)
+        evs[i][0].record()
+        sw.step(actions[i % T])
+        evs[i][1].record()
+    torch.cuda.synchronize(dev)
+    flushed_ms = sorted(a.elapsed_time(b) for a, b in evs)
+    flushed_med = flushed_ms[len(flushed_ms) // 2]
+    del flush
+
+    # ---- multi-step launch (mrs_step_many: state stays in registers for T steps)
+    many = None
+    if N <= 32:
+        sw.step_many(actions, T)
+        torch.cuda.synchronize(dev)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        sw.step_many(actions, T)
+        m1.record()
+        torch.cuda.synchronize(dev)
+        mm = m0.elapsed_time(m1)
+        many = {'value': float(E) * N * T / (mm * 1e-3), 'unit': 'agent-steps/s (this rank)', 'T': T,
+                'note': 'one launch for T steps, state on chip; streams only actions in and X/A out'}
+
+    # ---- e2e through the C ABI with host buffers
+    adim = M._abi.ACTION_DIMS[sw.cfg.action_type]
+    n_e = min(steps, args.e2e_steps)
+    h2d = E * N * adim * 4
+    d2h = E * N * (6 + N) * 4
+    e2e_value = None
+    if n_e > 0:
+        host_act = [torch.from_numpy(act_np[i % T]).pin_memory() for i in range(min(n_e, T))]
+        dev_act = torch.empty(E, N, max(adim, 1), device=dev)
+        Xh = torch.empty(E, N, 6).pin_memory()
+        Ah = torch.empty(E, N, N).pin_memory()
+        for i in range(3):
+            sw.step_host(host_act[i % len(host_act)], dev_act, Xh, Ah)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(n_e):
+            sw.step_host(host_act[i % len(host_act)], dev_act, Xh, Ah)
+        c1.record()
+        barrier()
+        e2e_ms = D.max_over_ranks(c0.elapsed_time(c1), dev)
+        e2e_value = float(E) * N * n_e * world / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    peaks_path = os.path.join(_REPO, 'MEASURED_PEAKS.json')
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    ms_per_step = ms / steps
+    bytes_per_launch = float(E) * N * w['B']
+    achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(_REPO, 'profiles', 'traffic.json')
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp)).get(args.workload)
+    kernel = 'step_group_kernel<%s>' % w['mode'] if N <= 32 else 'step_pre/step_post/adjacency_tiled'
+    out = {
+        'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling,
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': w['desc'], 'envs_per_gpu': E, 'agents_per_env': N, 'action_type': w['mode'],
+                   'k_hops': K, 'comm_range': w['R'], 'state_fn': 'cat(pos,vel) D=6', 'parallelism': 'env-shard x%d' % world,
+                   'launch': 'CUDA graph of %d single-step launches, %d replays' % (T, replays),
+                   'l2': 'no flush: per-step streamed bytes (actions+X+A) are distinct every step and exceed L2 over the '
+                         'region; state is re-read as the previous step left it; see l2_flushed'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic, 'kernel': kernel, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_agent_step': w['B'], 'agent_steps_per_launch': E * N,
+                     'launch_ms': ms_per_step},
+        'l2_flushed': {'ms_per_step_median': flushed_med, 'ms_min': flushed_ms[0], 'n': n_f,
+                       'value': float(E) * N / (flushed_med * 1e-3),
+                       'achieved_gbs': bytes_per_launch / (flushed_med * 1e-3) / 1e9,
+                       'frac': bytes_per_launch / (flushed_med * 1e-3) / 1e9 / peak},
+        'step_many': many,
+        'e2e': {'value': e2e_value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'steps': n_e, 'api': 'mrs_step_host (C ABI, pinned host buffers, sync every step)'},
+        'gpu_launches': gpu_launches,
+        'clocks': sampler.summary(),
+        'status_word': sw_status,
+    }
+    if world == 1 and not args.no_cpu:
+        procs = os.cpu_count() or 1
+        Ep, Tc = cpu_sample_sizes(args.workload)
+        v, wall, total = cpu_port_throughput(args.workload, procs, Ep, Tc)
+        out['cpu_baseline'] = {'value': v, 'unit': 'agent-steps/s', 'cores': procs, 'kind': 'port',
+                               'sample': '%d processes x %d envs x %d agents x %d steps of the same workload '
+                                         '(oracle/spec.py, numpy float64); %.1f s' % (procs, Ep, w['N'], Tc, total)}
+    print(json.dumps(out))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    procs = os.cpu_count() or 1
+    Ep, _ = cpu_sample_sizes(args.workload)
+    steps, warmup = args.steps, args.warmup
+    # bounded: each "step" here is one env.step of the sample batch (procs x Ep envs)
+    Tc = max(1, min(steps, 16))
+    v, wall, total = cpu_port_throughput(args.workload, procs, Ep, Tc)
+    out = {
+        'impl': 'reference', 'metric': 'agent-steps/sec', 'value': v, 'unit': 'agent-steps/s',
+        'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': Tc, 'warmup': 1,
+        'ms_per_step': wall / Tc * 1e3, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': w['desc'], 'agents_per_env': w['N'], 'action_type': w['mode'], 'k_hops': w['K'],
+                   'comm_range': w['R'], 'state_fn': 'cat(pos,vel) D=6'},
+        'cpu_baseline': {'value': v, 'unit': 'agent-steps/s', 'cores': procs, 'kind': 'port',
+                         'sample': '%d processes x %d envs x %d agents x %d steps (oracle/spec.py numpy port of the '
+                                   'reference step + restated Bullet; PyBullet itself is not installable here)'
+                                   % (procs, Ep, w['N'], Tc)},
+        'e2e': {'value': v, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c5', choices=sorted(WORKLOADS))
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--graph-steps', type=int, default=100, help='steps per captured CUDA graph')
+    ap.add_argument('--e2e-steps', type=int, default=50)
+    ap.add_argument('--clock-seconds', type=float, default=1.0)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

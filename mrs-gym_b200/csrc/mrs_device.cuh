@@ -219,27 +219,48 @@ __device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Agent& s
     }
 }
 
-// One pair of the downwash loop (Quadcopter.py:99-115), float32 like the reference:
-// returns the body-z force on agent i caused by agent j (rel = p_j - p_i).
-// Early-out: when 0.5*(dxy/beta)^2 > 104 the reference's float32 exp() underflows to 0
-// (denormal at worst, |force| < 1e-40 N), so the divisions and the exp are skipped.
-__device__ __forceinline__ float downwash_pair(const MrsQuadParams& q, float rx, float ry, float rz) {
+// ------------------------------------------------------------------------------------------
+// Host-derived constants (reciprocals, products) so that the per-agent code carries no uniform
+// divisions.  Not part of the C ABI: step_impl() fills it from MrsConfig for every call.
+struct Derived {
+    float inv_mass, inv_I[3];
+    float gnd_c;         // kf * gnd_eff_coeff * (prop_radius/4)^2      (ground effect numerator)
+    float dw_c;          // dw1 * (prop_radius/4)^2                      (downwash alpha numerator)
+    float rpm2rad;       // 2*pi/60
+    float q_x2;          // 0.25*dt^2: squared half rotation angle per unit |w|^2
+    float cap_w2;        // (ang_motion_threshold/dt)^2
+    float cap_k, cap_c;  // sin(pi/8) / ((pi/4)/dt), cos(pi/8): Bullet's capped angular step
+    float lim2;          // (2*agent_radius + contact_margin)^2
+    float gnd_skip_z;    // above this height the ground contact row cannot be active
+    float inv_dt, erp_dt;
+    float s_max;         // adjacency threshold on the squared distance
+    int comm_inf;
+};
+
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// One pair of the downwash loop (Quadcopter.py:99-115): body-z force on agent i caused by agent
+// j (rel = p_j - p_i):  -alpha * exp(-0.5 (dxy/beta)^2), alpha = dw1 (prop_radius/(4 dz))^2,
+// beta = dw2 dz + dw3, applied iff dz > 0 and dxy < 10.  Branch-free: only squares of dxy and
+// beta appear, so no sqrt; reciprocals and the exponential go to the SFU (rel. error <= 2e-6 of
+// a term that is itself <= ~0.3 of the weight; the parity floor is 5e-7 m/s per step).
+__device__ __forceinline__ float downwash_pair(const MrsQuadParams& q, const Derived& d, float rx, float ry, float rz) {
     const float dxy2 = rx * rx + ry * ry;
-    if (!(rz > 0.f && dxy2 < 100.f)) return 0.f;
     const float beta = q.dw2 * rz + q.dw3;
-    if (dxy2 > 208.f * beta * beta) return 0.f;
-    const float dxy = sqrtf(dxy2);
-    const float r = (1.f / (4.f * rz)) * q.prop_radius;
-    const float alpha = q.dw1 * (r * r);
-    const float qq = (1.f / beta) * dxy;
-    return -alpha * expf(-0.5f * (qq * qq));
+    const float e = -0.72134752044448170368f * dxy2 * fast_rcp(beta * beta);   // -0.5*log2(e)*(dxy/beta)^2
+    const float f = -d.dw_c * fast_rcp(rz * rz) * fast_ex2(e);
+    return (rz > 0.f && dxy2 < 100.f) ? f : 0.f;
 }
 
 // rotor thrust + yaw torque (Quadcopter.py:38-45), ground effect / drag (Quadcopter.py:69-98),
 // downwash sum `dw` -> Bullet unconstrained velocity update (bullet_model.unconstrained_velocities).
 // Overwrites s.v / s.w with the unconstrained velocities v*, w*.
 template <bool FORCES>
-__device__ __forceinline__ void apply_wrench(const MrsConfig& c, Agent& s, const float* R, const float* rpm, float dw) {
+__device__ __forceinline__ void apply_wrench(const MrsConfig& c, const Derived& d, Agent& s, const float* R,
+                                             const float* rpm, float dw) {
     const MrsQuadParams& q = c.quad;
     const MrsPhysicsParams& ph = c.phys;
     float Fb[3] = {0.f, 0.f, 0.f}, Tb[3] = {0.f, 0.f, 0.f};
@@ -252,8 +273,7 @@ __device__ __forceinline__ void apply_wrench(const MrsConfig& c, Agent& s, const
             float f = w2[i] * q.kf;
             if (gnd_ok) {
                 const float h = fmaxf(s.pz + R[6] * q.prop_x[i] + R[7] * q.prop_y[i], q.gnd_hclip);
-                const float rr = q.prop_radius / (4.f * h);
-                f += w2[i] * q.kf * q.gnd_eff_coeff * (rr * rr);
+                f += w2[i] * d.gnd_c * fast_rcp(h * h);
             }
             fz += f;
             Tb[0] += q.prop_y[i] * f;
@@ -261,15 +281,15 @@ __device__ __forceinline__ void apply_wrench(const MrsConfig& c, Agent& s, const
         }
         Tb[2] = q.km * (-w2[0] + w2[1] - w2[2] + w2[3]);
         // drag = R (c * v) applied again in the link frame
-        const float ssum = (2.f * 3.14159265358979323846f / 60.f) * (rpm[0] + rpm[1] + rpm[2] + rpm[3]);
+        const float ssum = d.rpm2rad * (rpm[0] + rpm[1] + rpm[2] + rpm[3]);
         const float cx = -q.drag_xy * ssum * s.vx, cy = -q.drag_xy * ssum * s.vy, cz = -q.drag_z * ssum * s.vz;
         Fb[0] = R[0] * cx + R[1] * cy + R[2] * cz;
         Fb[1] = R[3] * cx + R[4] * cy + R[5] * cz;
         Fb[2] = R[6] * cx + R[7] * cy + R[8] * cz + fz + dw;
     }
     // linear: a = R Fb / m - g z - v (k + k|v|)
-    const float im = 1.f / ph.mass;
-    const float vn = sqrtf(s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);
+    const float im = d.inv_mass;
+    const float vn = fast_sqrt(s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);
     const float kl = ph.lin_damping + ph.lin_damping * vn;
     const float ax = (R[0] * Fb[0] + R[1] * Fb[1] + R[2] * Fb[2]) * im - s.vx * kl;
     const float ay = (R[3] * Fb[0] + R[4] * Fb[1] + R[5] * Fb[2]) * im - s.vy * kl;
@@ -278,7 +298,7 @@ __device__ __forceinline__ void apply_wrench(const MrsConfig& c, Agent& s, const
     const float wb[3] = {R[0] * s.wx + R[3] * s.wy + R[6] * s.wz, R[1] * s.wx + R[4] * s.wy + R[7] * s.wz,
                          R[2] * s.wx + R[5] * s.wy + R[8] * s.wz};
     const float Iw[3] = {ph.inertia[0] * wb[0], ph.inertia[1] * wb[1], ph.inertia[2] * wb[2]};
-    const float wn = sqrtf(wb[0] * wb[0] + wb[1] * wb[1] + wb[2] * wb[2]);
+    const float wn = fast_sqrt(wb[0] * wb[0] + wb[1] * wb[1] + wb[2] * wb[2]);
     const float ka = ph.ang_damping + ph.ang_damping * wn;
     float rhs[3] = {Tb[0] - Iw[0] * ka, Tb[1] - Iw[1] * ka, Tb[2] - Iw[2] * ka};
     if (ph.gyro) {
@@ -286,7 +306,7 @@ __device__ __forceinline__ void apply_wrench(const MrsConfig& c, Agent& s, const
         rhs[1] -= wb[2] * Iw[0] - wb[0] * Iw[2];
         rhs[2] -= wb[0] * Iw[1] - wb[1] * Iw[0];
     }
-    const float wd[3] = {rhs[0] / ph.inertia[0], rhs[1] / ph.inertia[1], rhs[2] / ph.inertia[2]};
+    const float wd[3] = {rhs[0] * d.inv_I[0], rhs[1] * d.inv_I[1], rhs[2] * d.inv_I[2]};
     const float mv = ph.max_coord_vel;
     s.vx = clampf(s.vx + c.dt * ax, -mv, mv);
     s.vy = clampf(s.vy + c.dt * ay, -mv, mv);
@@ -297,35 +317,37 @@ __device__ __forceinline__ void apply_wrench(const MrsConfig& c, Agent& s, const
 }
 
 // contact row right-hand side (bullet_model._contact_rhs)
-__device__ __forceinline__ float contact_rhs(const MrsPhysicsParams& ph, float dist, float vn, float dt) {
+__device__ __forceinline__ float contact_rhs(const MrsPhysicsParams& ph, const Derived& d, float dist, float vn) {
     const float pen = dist + ph.slop;
-    const float rhs = (pen > 0.f) ? (-vn - pen / dt) : (-vn - pen * ph.erp2 / dt);
+    const float rhs = (pen > 0.f) ? (-vn - pen * d.inv_dt) : (-vn - pen * d.erp_dt);
     return fmaxf(rhs, 0.f);
 }
 
 // sphere-sphere contact of agent i with agent j (bullet_model.agent_contact_dv): d = p_i - p_j,
 // dv = v*_i - v*_j; returns true and adds this row's velocity change to acc when it pushes.
-__device__ __forceinline__ bool agent_contact_pair(const MrsPhysicsParams& ph, float dt, float dx, float dy, float dz,
-                                                   float dvx, float dvy, float dvz, float* acc) {
+// Rare path (only pairs closer than 2*AGENT_RADIUS + margin): IEEE sqrt / division kept.
+__device__ __forceinline__ bool agent_contact_pair(const MrsPhysicsParams& ph, const Derived& dd, float dx, float dy,
+                                                   float dz, float dvx, float dvy, float dvz, float* acc) {
     const float d2 = dx * dx + dy * dy + dz * dz;
-    const float lim = 2.f * ph.agent_radius + ph.contact_margin;
-    if (!(d2 < lim * lim) || !(d2 > 0.f)) return false;
+    if (!(d2 < dd.lim2) || !(d2 > 0.f)) return false;
     const float d = sqrtf(d2);
     const float inv = 1.f / d;
     const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
     const float vn = dvx * nx + dvy * ny + dvz * nz;
-    const float rhs = 0.5f * contact_rhs(ph, d - 2.f * ph.agent_radius, vn, dt);
+    const float rhs = 0.5f * contact_rhs(ph, dd, d - 2.f * ph.agent_radius, vn);
     acc[0] += rhs * nx; acc[1] += rhs * ny; acc[2] += rhs * nz;
     return rhs > 0.f;
 }
 
-// ground plane vs the quad's collision cylinder, impulse at the CoM (bullet_model.ground_contact)
-__device__ __forceinline__ bool ground_contact(const MrsPhysicsParams& ph, float dt, Agent& s) {
+// ground plane vs the quad's collision cylinder, impulse at the CoM (bullet_model.ground_contact).
+// Agents higher than gnd_skip_z cannot have an active row whatever their attitude: early out.
+__device__ __forceinline__ bool ground_contact(const MrsPhysicsParams& ph, const Derived& d, Agent& s) {
+    if (s.pz >= d.gnd_skip_z) return false;
     const float R22 = 1.f - 2.f * (s.qx * s.qx + s.qy * s.qy);
     const float ext = ph.col_radius * sqrtf(fmaxf(1.f - R22 * R22, 0.f)) + ph.col_halfheight * fabsf(R22) + ph.col_margin;
     const float dist = s.pz - ext - ph.ground_z;
     if (!(dist < ph.contact_margin)) return false;
-    const float jn = contact_rhs(ph, dist, s.vz, dt);
+    const float jn = contact_rhs(ph, d, dist, s.vz);
     const float vt = sqrtf(s.vx * s.vx + s.vy * s.vy);
     const float scale = (vt > 0.f) ? fminf(vt, ph.mu_ground * jn) / vt : 0.f;
     s.vz += jn;
@@ -334,20 +356,23 @@ __device__ __forceinline__ bool ground_contact(const MrsPhysicsParams& ph, float
     return jn > 0.f;
 }
 
-// btMultiBody::stepPositionsMultiDof (bullet_model.integrate_positions)
-__device__ __forceinline__ void integrate(const MrsConfig& c, Agent& s) {
+// btMultiBody::stepPositionsMultiDof (bullet_model.integrate_positions): p += dt v; q <- dq (x) q
+// with dq = [w sin(x)/|w|, cos(x)], x = |w| dt / 2 <= pi/8.  sin(x)/x and cos(x) are evaluated as
+// Taylor polynomials in x^2 = dt^2 |w|^2 / 4 (truncation < 2e-9 relative at the cap), so the
+// step needs no sqrt, sincos or division; Bullet's own small-angle Taylor branch is the same
+// series.  |w| dt > pi/4 takes Bullet's capped step (constants in Derived).
+__device__ __forceinline__ void integrate(const MrsConfig& c, const Derived& d, Agent& s) {
     const float dt = c.dt;
     s.px += dt * s.vx; s.py += dt * s.vy; s.pz += dt * s.vz;
-    float ang = sqrtf(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);
-    if (ang * dt > c.phys.ang_motion_threshold) ang = 0.5f * 1.57079632679489661923f / dt;
+    const float w2 = s.wx * s.wx + s.wy * s.wy + s.wz * s.wz;
     float k, cw;
-    if (ang < 0.001f) {
-        k = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang;
-        cw = cosf(0.5f * ang * dt);
+    if (w2 > d.cap_w2) {
+        k = d.cap_k; cw = d.cap_c;
     } else {
-        float sn;
-        sincosf(0.5f * ang * dt, &sn, &cw);
-        k = sn / ang;
+        const float x2 = d.q_x2 * w2;
+        const float sinc = 1.f + x2 * (-1.f / 6.f + x2 * (1.f / 120.f + x2 * (-1.f / 5040.f + x2 * (1.f / 362880.f))));
+        cw = 1.f + x2 * (-0.5f + x2 * (1.f / 24.f + x2 * (-1.f / 720.f + x2 * (1.f / 40320.f + x2 * (-1.f / 3628800.f)))));
+        k = 0.5f * dt * sinc;
     }
     const float ax = s.wx * k, ay = s.wy * k, az = s.wz * k;
     // q <- dq (x) q, xyzw
@@ -355,7 +380,9 @@ __device__ __forceinline__ void integrate(const MrsConfig& c, Agent& s) {
     const float ny = cw * s.qy - ax * s.qz + ay * s.qw + az * s.qx;
     const float nz = cw * s.qz + ax * s.qy - ay * s.qx + az * s.qw;
     const float nw = cw * s.qw - ax * s.qx - ay * s.qy - az * s.qz;
-    const float inv = 1.f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    const float n2 = nx * nx + ny * ny + nz * nz + nw * nw;
+    float inv = fast_rsqrt(n2);
+    inv = inv * (1.5f - 0.5f * n2 * inv * inv);      // one Newton step: full float32 accuracy
     s.qx = nx * inv; s.qy = ny * inv; s.qz = nz * inv; s.qw = nw * inv;
 }
 

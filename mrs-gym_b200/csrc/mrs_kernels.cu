@@ -39,19 +39,17 @@ struct StepArgs {
     int slot_x, slot_a;    // step t writes X tape slot slot_x - t and A tape slot slot_a - t
     int G;                 // group width (power of two >= N), group path only
     int nchunks;           // warp-sized work items, group path only
-    float s_max;           // adjacency threshold on the squared distance (inf: ones - eye)
-    int comm_inf;
 };
 
 // ------------------------------------------------------------------------------ state planes
-__device__ __forceinline__ void load_agent(const float* __restrict__ st, size_t S, size_t s, Agent& a) {
+__device__ __forceinline__ void load_agent(const float* __restrict__ st, unsigned S, unsigned s, Agent& a) {
     a.px = st[0 * S + s]; a.py = st[1 * S + s]; a.pz = st[2 * S + s];
     a.qx = st[3 * S + s]; a.qy = st[4 * S + s]; a.qz = st[5 * S + s]; a.qw = st[6 * S + s];
     a.vx = st[7 * S + s]; a.vy = st[8 * S + s]; a.vz = st[9 * S + s];
     a.wx = st[10 * S + s]; a.wy = st[11 * S + s]; a.wz = st[12 * S + s];
 }
 
-__device__ __forceinline__ void store_agent(float* __restrict__ st, size_t S, size_t s, const Agent& a) {
+__device__ __forceinline__ void store_agent(float* __restrict__ st, unsigned S, unsigned s, const Agent& a) {
     st[0 * S + s] = a.px; st[1 * S + s] = a.py; st[2 * S + s] = a.pz;
     st[3 * S + s] = a.qx; st[4 * S + s] = a.qy; st[5 * S + s] = a.qz; st[6 * S + s] = a.qw;
     st[7 * S + s] = a.vx; st[8 * S + s] = a.vy; st[9 * S + s] = a.vz;
@@ -66,7 +64,7 @@ __device__ __forceinline__ void dummy_agent(Agent& a) {
 }
 
 template <int MODE>
-__device__ __forceinline__ void load_ctrl(const float* __restrict__ ct, size_t S, size_t s, Ctrl& k) {
+__device__ __forceinline__ void load_ctrl(const float* __restrict__ ct, unsigned S, unsigned s, Ctrl& k) {
     using MT = ModeTraits<MODE>;
     if constexpr (MT::io) {
 #pragma unroll
@@ -88,7 +86,7 @@ __device__ __forceinline__ void load_ctrl(const float* __restrict__ ct, size_t S
 }
 
 template <int MODE>
-__device__ __forceinline__ void store_ctrl(float* __restrict__ ct, size_t S, size_t s, const Ctrl& k) {
+__device__ __forceinline__ void store_ctrl(float* __restrict__ ct, unsigned S, unsigned s, const Ctrl& k) {
     using MT = ModeTraits<MODE>;
     if constexpr (MT::io) {
 #pragma unroll
@@ -127,14 +125,14 @@ __device__ __forceinline__ bool load_action(const float* __restrict__ actions, s
 }
 
 // newest X slice of one agent (Environment.get_X with the built-in state_fn layouts)
-__device__ __forceinline__ void write_X(float* __restrict__ Xs, int layout, size_t s, const Agent& a) {
+__device__ __forceinline__ void write_X(float* __restrict__ Xs, int layout, unsigned s, const Agent& a) {
     if (layout == MRS_X_POS_VEL) {
-        float2* p = reinterpret_cast<float2*>(Xs + s * 6);
+        float2* p = reinterpret_cast<float2*>(Xs + (size_t)s * 6);
         p[0] = make_float2(a.px, a.py);
         p[1] = make_float2(a.pz, a.vx);
         p[2] = make_float2(a.vy, a.vz);
     } else if (layout == MRS_X_FULL) {
-        float* p = Xs + s * 13;
+        float* p = Xs + (size_t)s * 13;
         p[0] = a.px; p[1] = a.py; p[2] = a.pz;
         p[3] = a.qx; p[4] = a.qy; p[5] = a.qz; p[6] = a.qw;
         p[7] = a.vx; p[8] = a.vy; p[9] = a.vz;
@@ -143,31 +141,42 @@ __device__ __forceinline__ void write_X(float* __restrict__ Xs, int layout, size
 }
 
 // ------------------------------------------------------------------------------ group path
-template <int MODE>
-__global__ void __launch_bounds__(kBlock)
-step_group_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const StepArgs a) {
+// GT > 0: compile-time group width with N == GT (8, 16, 32: pair loops unrolled, no bounds tests);
+// GT == 0: run-time width a.G >= N (any N <= 32).
+template <int MODE, int GT>
+#ifndef MRS_GROUP_MIN_BLOCKS
+#define MRS_GROUP_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(kBlock, MRS_GROUP_MIN_BLOCKS)
+step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
+                  const StepArgs a) {
     __shared__ float4 sh_pos[kBlock];
     __shared__ float4 sh_vel[kBlock];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float4* wpos = sh_pos + wib * 32;
     float4* wvel = sh_vel + wib * 32;
-    const int G = a.G, N = c.N, E = c.E;
+    const int G = GT ? GT : a.G;
+    const int N = GT ? GT : c.N;
+    const int E = c.E;
     const int gpw = 32 / G;
     const int ai = lane & (G - 1);
     const int gb = lane - ai;
-    const size_t S = (size_t)E * N;
+    const unsigned S = (unsigned)E * (unsigned)N;
     const int wtotal = gridDim.x * kWarpsPerBlock;
     const MrsPhysicsParams& ph = c.phys;
-    const float lim = 2.f * ph.agent_radius + ph.contact_margin;
-    const float lim2 = lim * lim;
     const bool pair_contact = ph.agent_contact && N > 1;
-    const size_t xslot = S * (size_t)state_dim(c.state_layout);
-    const size_t aslot = S * (size_t)N;
+    const size_t xslot = (size_t)S * (size_t)state_dim(c.state_layout);
+    const size_t aslot = (size_t)S * (size_t)N;
 
-    for (int chunk = blockIdx.x * kWarpsPerBlock + wib; chunk < a.nchunks; chunk += wtotal) {
-        const long long e = (long long)chunk * gpw + (lane / G);
-        const bool valid = (e < E) && (ai < N);
-        const size_t s = valid ? (size_t)e * N + ai : 0;
+    // contiguous chunk range per warp, split as evenly as the integers allow over ALL warps of the
+    // grid (grid = SMs x resident CTAs, so every SM carries the same number of chunks +-1)
+    const int gw = blockIdx.x * kWarpsPerBlock + wib;
+    const int chunk_lo = (int)(((long long)gw * a.nchunks) / wtotal);
+    const int chunk_hi = (int)(((long long)(gw + 1) * a.nchunks) / wtotal);
+    for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+        const int e = chunk * gpw + (lane / G);
+        const bool valid = (e < E) && (GT || ai < N);
+        const unsigned s = valid ? (unsigned)e * (unsigned)N + (unsigned)ai : 0u;
         Agent st;
         Ctrl k;
         if (valid) {
@@ -200,18 +209,19 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const
             float dw = 0.f;
             bool near = false;
             if (MODE != MRS_NO_ACTION || pair_contact) {
+#pragma unroll 8
                 for (int r = 1; r < G; ++r) {
-                    const int j = (ai + r) & (G - 1);
-                    if (j < N) {
+                    const int j = ai ^ r;
+                    if (GT || j < N) {
                         const float4 pj = wpos[gb + j];
                         const float rx = pj.x - st.px, ry = pj.y - st.py, rz = pj.z - st.pz;
-                        if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, rx, ry, rz);
-                        near = near || (rx * rx + ry * ry + rz * rz < lim2);
+                        if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, d, rx, ry, rz);
+                        near = near || (rx * rx + ry * ry + rz * rz < d.lim2);
                     }
                 }
             }
             const float p0x = st.px, p0y = st.py, p0z = st.pz;
-            apply_wrench<MODE != MRS_NO_ACTION>(c, st, R, rpm, dw);
+            apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
 
             // ---- pair pass 2 (rare): sphere-sphere contact on the unconstrained velocities
             if (pair_contact && __any_sync(kFull, near && valid)) {
@@ -220,11 +230,11 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const
                 if (near) {
                     float acc[3] = {0.f, 0.f, 0.f};
                     for (int r = 1; r < G; ++r) {
-                        const int j = (ai + r) & (G - 1);
-                        if (j < N) {
+                        const int j = ai ^ r;
+                        if (GT || j < N) {
                             const float4 pj = wpos[gb + j];
                             const float4 vj = wvel[gb + j];
-                            if (agent_contact_pair(ph, c.dt, p0x - pj.x, p0y - pj.y, p0z - pj.z, st.vx - vj.x,
+                            if (agent_contact_pair(ph, d, p0x - pj.x, p0y - pj.y, p0z - pj.z, st.vx - vj.x,
                                                    st.vy - vj.y, st.vz - vj.z, acc))
                                 ++n_agent_rows;
                         }
@@ -232,16 +242,16 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const
                     st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
                 }
             }
-            if (ph.ground_contact && ground_contact(ph, c.dt, st)) ++n_ground;
-            integrate(c, st);
+            if (ph.ground_contact && ground_contact(ph, d, st)) ++n_ground;
+            integrate(c, d, st);
             if (!agent_finite(st)) status |= MRS_STATUS_NONFINITE;
 
-            // ---- observation: newest X slice and newest A slice into tape slot slot_first - t
+            // ---- observation: newest X slice and newest A slice into their tape slots
             if (b.X_tape && c.state_layout != MRS_X_NONE && valid)
                 write_X(b.X_tape + (size_t)(a.slot_x - t) * xslot, c.state_layout, s, st);
             if (b.A_tape) {
-                float* Arow = b.A_tape + (size_t)(a.slot_a - t) * aslot + s * N;
-                if (a.comm_inf) {
+                float* Arow = b.A_tape + (size_t)(a.slot_a - t) * aslot + (size_t)s * N;
+                if (d.comm_inf) {
                     if (valid)
                         for (int j = 0; j < N; ++j) Arow[j] = (j == ai) ? 0.f : 1.f;
                 } else {
@@ -250,20 +260,21 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const
                     __syncwarp();
                     if (valid) {
                         if ((N & 3) == 0) {
+#pragma unroll 2
                             for (int j = 0; j < N; j += 4) {
                                 float v[4];
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
                                     const float4 pj = wpos[gb + j + u];
                                     v[u] = (j + u == ai) ? 0.f
-                                                         : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, a.s_max);
+                                                         : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
                                 }
                                 *reinterpret_cast<float4*>(Arow + j) = make_float4(v[0], v[1], v[2], v[3]);
                             }
                         } else {
                             for (int j = 0; j < N; ++j) {
                                 const float4 pj = wpos[gb + j];
-                                Arow[j] = (j == ai) ? 0.f : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, a.s_max);
+                                Arow[j] = (j == ai) ? 0.f : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
                             }
                         }
                     }
@@ -283,15 +294,18 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const
         }
         // warp-aggregated status / statistics (atomics only when something happened)
         const unsigned any_status = __reduce_or_sync(kFull, status);
-        const unsigned sum_rows = __reduce_add_sync(kFull, n_agent_rows);
-        const unsigned sum_gnd = __reduce_add_sync(kFull, n_ground);
-        if (lane == 0) {
-            if (any_status && b.status) atomicOr(b.status, any_status);
-            if (b.stats) {
-                if (sum_rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)sum_rows);
-                if (sum_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)sum_gnd);
-                if (any_status & MRS_STATUS_NONFINITE) atomicAdd(b.stats + MRS_STAT_NONFINITE, 1ull);
-                if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
+        const unsigned events = __reduce_or_sync(kFull, n_agent_rows | n_ground);
+        if (any_status | events) {
+            const unsigned sum_rows = __reduce_add_sync(kFull, n_agent_rows);
+            const unsigned sum_gnd = __reduce_add_sync(kFull, n_ground);
+            if (lane == 0) {
+                if (any_status && b.status) atomicOr(b.status, any_status);
+                if (b.stats) {
+                    if (sum_rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)sum_rows);
+                    if (sum_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)sum_gnd);
+                    if (any_status & MRS_STATUS_NONFINITE) atomicAdd(b.stats + MRS_STAT_NONFINITE, 1ull);
+                    if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
+                }
             }
         }
     }
@@ -301,14 +315,15 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const
 // grid: (ceil(N / kBlock), E).  scratch planes: 0-2 unconstrained velocity, 3-5 pre-step position.
 template <int MODE>
 __global__ void __launch_bounds__(kBlock)
-step_pre_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const float* __restrict__ actions) {
+step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
+                const float* __restrict__ actions) {
     __shared__ float4 tile[kBlock];
     const int N = c.N;
-    const size_t S = (size_t)c.E * N;
-    const size_t env0 = (size_t)blockIdx.y * N;
+    const unsigned S = (unsigned)c.E * (unsigned)N;
+    const unsigned env0 = blockIdx.y * (unsigned)N;
     const int ai = blockIdx.x * kBlock + threadIdx.x;
     const bool valid = ai < N;
-    const size_t s = env0 + (valid ? ai : 0);
+    const unsigned s = env0 + (valid ? ai : 0);
     Agent st;
     Ctrl k;
     load_agent(b.state, S, s, st);
@@ -331,12 +346,12 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const f
             for (int u = 0; u < cnt; ++u) {
                 if (j0 + u == ai) continue;
                 const float4 pj = tile[u];
-                dw += downwash_pair(c.quad, pj.x - st.px, pj.y - st.py, pj.z - st.pz);
+                dw += downwash_pair(c.quad, d, pj.x - st.px, pj.y - st.py, pj.z - st.pz);
             }
         }
     }
     const float p0x = st.px, p0y = st.py, p0z = st.pz;
-    apply_wrench<MODE != MRS_NO_ACTION>(c, st, R, rpm, dw);
+    apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
     if (valid) {
         float* sc = b.scratch;
         sc[0 * S + s] = st.vx; sc[1 * S + s] = st.vy; sc[2 * S + s] = st.vz;
@@ -355,15 +370,15 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const f
 }
 
 __global__ void __launch_bounds__(kBlock)
-step_post_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, int slot) {
+step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int slot) {
     __shared__ float4 tpos[kBlock];
     __shared__ float4 tvel[kBlock];
     const int N = c.N;
-    const size_t S = (size_t)c.E * N;
-    const size_t env0 = (size_t)blockIdx.y * N;
+    const unsigned S = (unsigned)c.E * (unsigned)N;
+    const unsigned env0 = blockIdx.y * (unsigned)N;
     const int ai = blockIdx.x * kBlock + threadIdx.x;
     const bool valid = ai < N;
-    const size_t s = env0 + (valid ? ai : 0);
+    const unsigned s = env0 + (valid ? ai : 0);
     const MrsPhysicsParams& ph = c.phys;
     const float* sc = b.scratch;
     Agent st;
@@ -387,17 +402,16 @@ step_post_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, int sl
                 if (j0 + u == ai) continue;
                 const float4 pj = tpos[u];
                 const float dx = st.px - pj.x, dy = st.py - pj.y, dz = st.pz - pj.z;
-                const float lim = 2.f * ph.agent_radius + ph.contact_margin;
-                if (dx * dx + dy * dy + dz * dz < lim * lim) {
+                if (dx * dx + dy * dy + dz * dz < d.lim2) {
                     const float4 vj = tvel[u];
-                    if (agent_contact_pair(ph, c.dt, dx, dy, dz, st.vx - vj.x, st.vy - vj.y, st.vz - vj.z, acc)) ++rows;
+                    if (agent_contact_pair(ph, d, dx, dy, dz, st.vx - vj.x, st.vy - vj.y, st.vz - vj.z, acc)) ++rows;
                 }
             }
         }
         st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
     }
-    if (ph.ground_contact && ground_contact(ph, c.dt, st)) ++gnd;
-    integrate(c, st);
+    if (ph.ground_contact && ground_contact(ph, d, st)) ++gnd;
+    integrate(c, d, st);
     if (valid) {
         store_agent(b.state, S, s, st);
         if (b.X_tape && c.state_layout != MRS_X_NONE)
@@ -483,12 +497,12 @@ adjacency_tiled_kernel(const float* __restrict__ pos, size_t cs, size_t as, floa
 
 // X of the current state (MRS.calc_Xk outside step)
 __global__ void __launch_bounds__(256)
-observe_x_kernel(const MrsBuffers b, size_t S, int layout, int slot) {
-    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+observe_x_kernel(const MrsBuffers b, unsigned S, int layout, int slot) {
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     Agent st;
     load_agent(b.state, S, s, st);
-    write_X(b.X_tape + (size_t)slot * S * state_dim(layout), layout, s, st);
+    write_X(b.X_tape + (size_t)slot * S * (size_t)state_dim(layout), layout, s, st);
 }
 
 // ------------------------------------------------------------------------------ set_state
@@ -581,11 +595,36 @@ static int check_cfg(const MrsConfig* cfg) {
 
 static int last_error() { return cudaGetLastError() == cudaSuccess ? MRS_OK : MRS_ERR_CUDA; }
 
-template <int MODE>
-static int launch_group(const MrsConfig& c, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
+static Derived make_derived(const MrsConfig& c) {
+    Derived d;
+    const MrsQuadParams& q = c.quad;
+    const MrsPhysicsParams& p = c.phys;
+    d.inv_mass = (float)(1.0 / (double)p.mass);
+    for (int i = 0; i < 3; ++i) d.inv_I[i] = (float)(1.0 / (double)p.inertia[i]);
+    const double pr4 = (double)q.prop_radius / 4.0;
+    d.gnd_c = (float)((double)q.kf * (double)q.gnd_eff_coeff * pr4 * pr4);
+    d.dw_c = (float)((double)q.dw1 * pr4 * pr4);
+    d.rpm2rad = (float)(2.0 * 3.14159265358979323846 / 60.0);
+    d.q_x2 = (float)(0.25 * (double)c.dt * (double)c.dt);
+    d.cap_w2 = (float)(((double)p.ang_motion_threshold / (double)c.dt) * ((double)p.ang_motion_threshold / (double)c.dt));
+    const double cap_ang = 0.5 * 1.57079632679489661923 / (double)c.dt;      // Bullet: 0.5 * SIMD_HALF_PI / dt
+    d.cap_k = (float)(sin(0.5 * cap_ang * (double)c.dt) / cap_ang);
+    d.cap_c = (float)cos(0.5 * cap_ang * (double)c.dt);
+    const float lim = 2.f * p.agent_radius + p.contact_margin;
+    d.lim2 = lim * lim;
+    d.gnd_skip_z = p.ground_z + p.contact_margin + p.col_radius + p.col_halfheight + p.col_margin + 1e-3f;
+    d.inv_dt = (float)(1.0 / (double)c.dt);
+    d.erp_dt = (float)((double)p.erp2 / (double)c.dt);
+    d.comm_inf = isinf(c.comm_range) && c.comm_range > 0.f;
+    d.s_max = adjacency_threshold(c.comm_range);
+    return d;
+}
+
+template <int MODE, int GT>
+static int launch_group(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     static int resident = 0;
     if (resident == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, step_group_kernel<MODE>, kBlock, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, step_group_kernel<MODE, GT>, kBlock, 0) != cudaSuccess ||
             resident <= 0)
             return MRS_ERR_CUDA;
     }
@@ -594,17 +633,12 @@ static int launch_group(const MrsConfig& c, const MrsBuffers& b, const StepArgs&
     const int bps = env_int("MRS_B200_BLOCKS_PER_SM", resident);
     const long long need = ((long long)a.nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const long long cap = (long long)sms * (bps > 0 ? bps : resident);
-    long long blocks = need;
-    if (need > cap) {  // several chunks per warp: split evenly so every warp does the same count
-        const long long iters = (need + cap - 1) / cap;
-        blocks = (need + iters - 1) / iters;
-    }
-    step_group_kernel<MODE><<<(unsigned)blocks, kBlock, 0, st>>>(c, b, a);
+    // small jobs: one chunk per warp; large jobs: exactly SMs x resident CTAs (one full wave), the
+    // kernel splits the chunks evenly over all warps
+    const long long blocks = need < cap ? need : cap;
+    step_group_kernel<MODE, GT><<<(unsigned)blocks, kBlock, 0, st>>>(c, d, b, a);
     return last_error();
 }
-
-template <int MODE>
-static int launch_tiled(const MrsConfig& c, const MrsBuffers& b, const StepArgs& a, cudaStream_t st);
 
 static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, int N, float s_max, int comm_inf,
                             cudaStream_t st) {
@@ -624,17 +658,17 @@ static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, in
 }
 
 template <int MODE>
-static int launch_tiled(const MrsConfig& c, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
+static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     if (!b.scratch) return MRS_ERR_ARG;
     const size_t S = (size_t)c.E * c.N;
     constexpr int A = ModeTraits<MODE>::A;
     dim3 grid((unsigned)((c.N + kBlock - 1) / kBlock), (unsigned)c.E);
     for (int t = 0; t < a.T; ++t) {
-        step_pre_kernel<MODE><<<grid, kBlock, 0, st>>>(c, b, a.actions ? a.actions + (size_t)t * S * A : nullptr);
-        step_post_kernel<<<grid, kBlock, 0, st>>>(c, b, a.slot_x - t);
+        step_pre_kernel<MODE><<<grid, kBlock, 0, st>>>(c, d, b, a.actions ? a.actions + (size_t)t * S * A : nullptr);
+        step_post_kernel<<<grid, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
         if (b.A_tape) {
-            const int rc = launch_adjacency(b.state, S, 1, b.A_tape + (size_t)(a.slot_a - t) * S * c.N, c.E, c.N, a.s_max,
-                                            a.comm_inf, st);
+            const int rc = launch_adjacency(b.state, S, 1, b.A_tape + (size_t)(a.slot_a - t) * S * c.N, c.E, c.N, d.s_max,
+                                            d.comm_inf, st);
             if (rc) return rc;
         }
     }
@@ -649,13 +683,19 @@ static int pow2ceil(int n) {
 
 template <int MODE>
 static int dispatch_step(const MrsConfig& c, const MrsBuffers& b, StepArgs a, cudaStream_t st) {
+    const Derived d = make_derived(c);
     if (c.N <= 32) {
         a.G = pow2ceil(c.N);
         const int gpw = 32 / a.G;
         a.nchunks = (c.E + gpw - 1) / gpw;
-        return launch_group<MODE>(c, b, a, st);
+        switch (c.N) {   // power-of-two swarms get the unrolled pair loops
+            case 8:  return launch_group<MODE, 8>(c, d, b, a, st);
+            case 16: return launch_group<MODE, 16>(c, d, b, a, st);
+            case 32: return launch_group<MODE, 32>(c, d, b, a, st);
+            default: return launch_group<MODE, 0>(c, d, b, a, st);
+        }
     }
-    return launch_tiled<MODE>(c, b, a, st);
+    return launch_tiled<MODE>(c, d, b, a, st);
 }
 
 static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T, int slot_x, int slot_a,
@@ -674,8 +714,7 @@ static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
     a.slot_a = slot_a;
     a.G = 0;
     a.nchunks = 0;
-    a.comm_inf = isinf(cfg->comm_range) && cfg->comm_range > 0.f;
-    a.s_max = adjacency_threshold(cfg->comm_range);
+    if ((unsigned long long)cfg->E * cfg->N * (cfg->N > 18 ? cfg->N : 18) >= 0xffffffffull) return MRS_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     switch (cfg->action_type) {
         case MRS_SET_TARGET_VEL:   return dispatch_step<MRS_SET_TARGET_VEL>(*cfg, *bufs, a, st);

@@ -191,6 +191,19 @@ class Swarm:
                 self.ha = ha - n
             done += n
 
+    def step_many_single(self, actions, T: int):
+        """T steps as T separate mrs_step launches (each reads and writes the state in HBM)."""
+        for t in range(T):
+            self.step(actions[t] if actions is not None else None)
+
+    def capture_rollout(self, actions, T: int):
+        """CUDA-graph a T-step rollout (launch-bound loops belong in graphs): returns a
+        GraphRollout whose replay() advances all envs by T steps reading actions[t] from the
+        given device buffer (refill it between replays).  Ring semantics are preserved: each
+        replay first moves the K newest slots to the top of the tapes, then writes T slots
+        downwards, ending where it started."""
+        return GraphRollout(self, actions, T)
+
     def push_A(self):
         """MRS.calc_Ak outside step: adjacency of the current positions becomes the newest slot."""
         ha = self._make_room(2) - 1
@@ -287,3 +300,62 @@ class Swarm:
         (NCCL over NVLink when the process group is nccl)."""
         from .dist import allreduce_stats
         return allreduce_stats(self.stats, group)
+
+
+class GraphRollout:
+    def __init__(self, swarm: Swarm, actions, T: int):
+        sw = self.swarm = swarm
+        K, L = sw.K, sw.L
+        if T < 1 or T > L - 2 * K - (1 if K == 0 else 0):
+            raise ValueError('capture_rollout: T=%d needs tape_slots >= T + 2*K_HOPS (+1), have %d' % (T, L))
+        if actions is not None and tuple(actions.shape[:3]) != (T, sw.E, sw.N):
+            raise ValueError('actions must be [T, E, N, A]')
+        self.T, self.actions = T, actions
+        self.h_end = L - K - T
+        self.launches_per_replay = 0
+        # park the current windows at the slots where every replay ends
+        for which, tape, head in ((1, sw.X_tape, sw.hx), (2, sw.A_tape, sw.ha)):
+            if tape is None:
+                continue
+            if which == 1 and sw.cfg.state_layout == _abi.X_NONE:
+                raise RuntimeError('capture_rollout needs a fused state layout')
+            n = min(K + 1, L - head)
+            if head != self.h_end:
+                tape[self.h_end:self.h_end + n] = tape[head:head + n].clone()
+        sw.hx = sw.ha = self.h_end
+        torch.cuda.synchronize(sw.device)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=sw.device)
+        side.wait_stream(torch.cuda.current_stream(sw.device))
+        with torch.cuda.stream(side):
+            before = sw.launches
+            self._body()            # warm-up outside capture (lazy module load, occupancy query)
+            sw.hx = sw.ha = self.h_end
+            torch.cuda.synchronize(sw.device)
+            with torch.cuda.graph(self.graph, stream=side):
+                before = sw.launches
+                self._body()
+                self.launches_per_replay = sw.launches - before
+        torch.cuda.current_stream(sw.device).wait_stream(side)
+        torch.cuda.synchronize(sw.device)
+
+    def _body(self):
+        sw = self.swarm
+        sw.hx = sw.ha = 0 if sw.K > 0 else sw.L - sw.K      # force the move-to-top, then step down
+        if sw.K > 0:
+            # heads sit at h_end; _make_room moves [h_end, h_end+K) to the top when head == 0, so
+            # do the move explicitly from h_end
+            for which, tape in ((1, sw.X_tape), (2, sw.A_tape)):
+                if tape is None:
+                    continue
+                for i in range(sw.K - 1, -1, -1):
+                    _abi.check(sw.lib.mrs_tape_fill(C.byref(sw.cfg), C.byref(sw.bufs), which, self.h_end + i,
+                                                    sw.L - sw.K + i, 1, sw._stream()), 'mrs_tape_fill')
+                    sw.launches += 1
+        sw.hx = sw.ha = sw.L - sw.K
+        sw.step_many_single(self.actions, self.T)
+
+    def replay(self):
+        self.graph.replay()
+        self.swarm.launches += self.launches_per_replay
+        self.swarm.hx = self.swarm.ha = self.h_end

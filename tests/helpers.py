@@ -106,3 +106,38 @@ def torch_cpu_adjacency(pos32, comm_range):
         codist.diagonal().fill_(float('inf'))
         out.append((codist <= comm_range).float())
     return torch.stack(out).reshape(*pos.shape[:-2], N, N)
+
+
+def downwash_sensitivity(pos):
+    """max over agent pairs of |d(downwash force)/d(dz)| [N/m] at positions [N,3]
+    (Quadcopter.py:99-115: F = -dw1 (pr/(4 dz))^2 exp(-0.5 (dxy/(dw2 dz + dw3))^2), dz > 0).  The
+    force is singular at dz -> 0+: a trajectory that passes such a point amplifies float32
+    position rounding (1e-7 m) into a visible velocity kick, in the reference's own dynamics."""
+    p = np.asarray(pos, np.float64)
+    rel = p[None, :, :] - p[:, None, :]
+    dz = rel[..., 2]
+    dxy = np.sqrt(rel[..., 0] ** 2 + rel[..., 1] ** 2)
+    def F(dz):
+        with np.errstate(all='ignore'):
+            a = 2267.18 * (2.31348e-2 / (4 * dz)) ** 2
+            b = 0.16 * dz - 0.11
+            return np.where((dz > 0) & (dxy < 10), a * np.exp(-0.5 * (dxy / b) ** 2), 0.0)
+    h = 1e-6
+    with np.errstate(all='ignore'):
+        S = np.abs(F(dz + h) - F(dz - h)) / (2 * h)
+    S = np.where(np.isfinite(S), S, np.inf)
+    np.fill_diagonal(S, 0.0)
+    return float(S.max())
+
+
+def first_singular_step(g, limit=1.0e3):
+    """first step of a golden trajectory whose PRE-step positions have a downwash sensitivity above
+    `limit` N/m (a 2e-7 m position rounding then changes the force by > 2e-4 N = 0.1 % of the
+    weight); T if none."""
+    T = int(g['T'])
+    prev = g['start_pos']
+    for t in range(T):
+        if downwash_sensitivity(prev) > limit:
+            return t
+        prev = g['pos'][t]
+    return T
