@@ -264,7 +264,7 @@ def run_gpu(args):
     n_e = min(steps, args.e2e_steps)
     h2d = E * N * adim * 4
     d2h = E * N * (6 + N) * 4
-    e2e_value = None
+    e2e_value = e2e_pipe_value = None
     if n_e > 0:
         host_act = [torch.from_numpy(act_np[i % T]).pin_memory() for i in range(min(n_e, T))]
         dev_act = torch.empty(E, N, max(adim, 1), device=dev)
@@ -281,6 +281,22 @@ def run_gpu(args):
         barrier()
         e2e_ms = D.max_over_ranks(c0.elapsed_time(c1), dev)
         e2e_value = float(E) * N * n_e * world / (e2e_ms * 1e-3)
+        # pipelined variant: mrs_rollout_host, copies of neighbouring steps overlap the kernels
+        n_p = min(n_e, T)
+        ah = torch.from_numpy(act_np[:n_p]).pin_memory()
+        Xhh = torch.empty(n_p, E, N, 6).pin_memory()
+        Ahh = torch.empty(n_p, E, N, N).pin_memory()
+        dev2 = torch.empty(2, E, N, max(adim, 1), device=dev)
+        sw.rollout_host(ah, dev2, Xhh, Ahh)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        sw.rollout_host(ah, dev2, Xhh, Ahh)
+        p1.record()
+        barrier()
+        pipe_ms = D.max_over_ranks(p0.elapsed_time(p1), dev)
+        e2e_pipe_value = float(E) * N * n_p * world / (pipe_ms * 1e-3)
+        del ah, Xhh, Ahh
 
     if rank != 0:
         return
@@ -315,8 +331,10 @@ def run_gpu(args):
                        'achieved_gbs': bytes_per_launch / (flushed_med * 1e-3) / 1e9,
                        'frac': bytes_per_launch / (flushed_med * 1e-3) / 1e9 / peak},
         'step_many': many,
-        'e2e': {'value': e2e_value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'steps': n_e, 'api': 'mrs_step_host (C ABI, pinned host buffers, sync every step)'},
+        'e2e': {'value': e2e_pipe_value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'steps': n_e, 'api': 'mrs_rollout_host (C ABI, pinned host buffers; every step: H2D actions, kernel, D2H '
+                                     'newest X and A; copies of neighbouring steps overlap the kernels)',
+                'sync_per_step': {'value': e2e_value, 'api': 'mrs_step_host (same copies, stream sync after every step)'}},
         'gpu_launches': gpu_launches,
         'clocks': sampler.summary(),
         'status_word': sw_status,

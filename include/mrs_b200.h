@@ -25,7 +25,8 @@
  *                         host writes slot p-1 at each step (descending) so that slots
  *                         [p, p+K] are the reference's newest-first K_HOPS+1 window
  *                         (mrsgym/MRS.py:87-114) with no per-step copy.
- *   scratch float[6][S]   only for N > 32 (unconstrained velocities + pre-step positions)
+ *   scratch float[7][S]   only for N > 32 (unconstrained velocities, pre-step positions,
+ *                         contact-proximity flag between the wide-path kernels)
  */
 #ifndef MRS_B200_H
 #define MRS_B200_H
@@ -40,6 +41,7 @@ extern "C" {
 #define MRS_STATE_PLANES 13
 #define MRS_CTRL_PLANES 18
 #define MRS_STATS_SLOTS 8
+#define MRS_SCRATCH_PLANES 7
 
 /* ACTION_TYPE strings of the reference are method names dispatched by getattr
  * (mrsgym/Environment.py:92 -> mrsgym/Quadcopter.py:26-65). */
@@ -130,7 +132,7 @@ typedef struct {
     float* rpm;                          /* [4][S] or NULL */
     float* X_tape;                       /* [L][E][N][D] or NULL */
     float* A_tape;                       /* [L][E][N][N] or NULL */
-    float* scratch;                      /* [6][S], needed iff N > 32 */
+    float* scratch;                      /* [7][S], needed iff N > 32 */
     unsigned int* status;                /* [1] */
     unsigned long long* stats;           /* [MRS_STATS_SLOTS] */
 } MrsBuffers;
@@ -196,6 +198,18 @@ int mrs_tape_fill(const MrsConfig* cfg, const MrsBuffers* bufs, int which, int s
  * stream before returning (the reference's step is synchronous). */
 int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host,
                   float* dev_actions, float* X_host, float* A_host, int slot_x, int slot_a, void* stream);
+
+/* T steps over HOST buffers with the copies pipelined against the kernels (H2D of step t+1 and
+ * D2H of step t-1 overlap the kernel of step t on two internal copy streams).  actions_host
+ * float[T][E][N][ACTION_DIM] (pinned), dev_actions: caller-owned device staging, TWO action
+ * buffers float[2][E][N][ACTION_DIM]; X_host float[T][E][N][D] / A_host float[T][E][N][N] (pinned,
+ * may be NULL) receive the newest slice of every step.  Step t writes tape slots
+ * slot_x_first - t / slot_a_first - t (the caller guarantees they exist).  Synchronises before
+ * returning.  The open-loop rollout of examples/simulating_data/helper/DataGenerator.py:8-48 for a
+ * caller whose actions and trajectory buffers live in host memory. */
+int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host,
+                     float* dev_actions, float* X_host, float* A_host, int T, int slot_x_first,
+                     int slot_a_first, void* stream);
 
 #ifdef __cplusplus
 }

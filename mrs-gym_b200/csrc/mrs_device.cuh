@@ -23,6 +23,7 @@ struct Agent {
     float wx, wy, wz;
 };
 
+// minb: resident CTAs per SM the group kernel is compiled for (register budget per mode)
 // PID planes touched per mode (the rest of the 18 ctrl planes stay untouched in HBM)
 struct Ctrl {
     float io[3];   // integral_ori_e
@@ -34,14 +35,14 @@ struct Ctrl {
 };
 
 template <int MODE> struct ModeTraits;
-template <> struct ModeTraits<MRS_SET_TARGET_VEL>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = true;  };
-template <> struct ModeTraits<MRS_SET_TARGET_POS>   { static constexpr int A = 3; static constexpr bool io = true,  ip = true,  vel = false; };
-template <> struct ModeTraits<MRS_SET_TARGET_ACCEL> { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false; };
-template <> struct ModeTraits<MRS_SET_FORCE>        { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false; };
-template <> struct ModeTraits<MRS_SET_TARGET_ORI>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false; };
-template <> struct ModeTraits<MRS_SET_CONTROL>      { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false; };
-template <> struct ModeTraits<MRS_SET_SPEEDS>       { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false; };
-template <> struct ModeTraits<MRS_NO_ACTION>        { static constexpr int A = 0; static constexpr bool io = false, ip = false, vel = false; };
+template <> struct ModeTraits<MRS_SET_TARGET_VEL>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = true;  static constexpr int minb = 5; };
+template <> struct ModeTraits<MRS_SET_TARGET_POS>   { static constexpr int A = 3; static constexpr bool io = true,  ip = true,  vel = false;  static constexpr int minb = 6; };
+template <> struct ModeTraits<MRS_SET_TARGET_ACCEL> { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = 6; };
+template <> struct ModeTraits<MRS_SET_FORCE>        { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = 6; };
+template <> struct ModeTraits<MRS_SET_TARGET_ORI>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = 6; };
+template <> struct ModeTraits<MRS_SET_CONTROL>      { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
+template <> struct ModeTraits<MRS_SET_SPEEDS>       { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
+template <> struct ModeTraits<MRS_NO_ACTION>        { static constexpr int A = 0; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
 
 __host__ __device__ __forceinline__ int state_dim(int layout) {
     return layout == MRS_X_POS_VEL ? 6 : (layout == MRS_X_FULL ? 13 : 0);
@@ -247,8 +248,7 @@ __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ft
 // beta = dw2 dz + dw3, applied iff dz > 0 and dxy < 10.  Branch-free: only squares of dxy and
 // beta appear, so no sqrt; reciprocals and the exponential go to the SFU (rel. error <= 2e-6 of
 // a term that is itself <= ~0.3 of the weight; the parity floor is 5e-7 m/s per step).
-__device__ __forceinline__ float downwash_pair(const MrsQuadParams& q, const Derived& d, float rx, float ry, float rz) {
-    const float dxy2 = rx * rx + ry * ry;
+__device__ __forceinline__ float downwash_pair(const MrsQuadParams& q, const Derived& d, float dxy2, float rz) {
     const float beta = q.dw2 * rz + q.dw3;
     const float e = -0.72134752044448170368f * dxy2 * fast_rcp(beta * beta);   // -0.5*log2(e)*(dxy/beta)^2
     const float f = -d.dw_c * fast_rcp(rz * rz) * fast_ex2(e);

@@ -140,21 +140,41 @@ __device__ __forceinline__ void write_X(float* __restrict__ Xs, int layout, unsi
     }
 }
 
+// ------------------------------------------------------------------------------ async staging
+// The group kernel walks several warp-chunks per warp.  While chunk c is being computed, the 13
+// state planes (+ the first action) of chunk c+1 are already in flight to a per-warp shared-memory
+// stage through cp.async (LDGSTS): the load latency of a chunk is hidden behind the arithmetic of
+// the previous one without holding a second register copy of the state.  Every lane only ever
+// touches its own stage column, so no warp barrier is needed around the stage.
+#ifndef MRS_PREFETCH
+#define MRS_PREFETCH 1
+#endif
+constexpr int kStageFloats = 13 * 32 + 4 * 32;   // per warp: 13 planes x 32 lanes + 32 float4 actions
+
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------ group path
 // GT > 0: compile-time group width with N == GT (8, 16, 32: pair loops unrolled, no bounds tests);
 // GT == 0: run-time width a.G >= N (any N <= 32).
 template <int MODE, int GT>
-#ifndef MRS_GROUP_MIN_BLOCKS
-#define MRS_GROUP_MIN_BLOCKS 6
-#endif
-__global__ void __launch_bounds__(kBlock, MRS_GROUP_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, ModeTraits<MODE>::minb)
 step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
                   const StepArgs a) {
     __shared__ float4 sh_pos[kBlock];
     __shared__ float4 sh_vel[kBlock];
+    constexpr bool kStage = MRS_PREFETCH && GT != 0 && ModeTraits<MODE>::A == 4 && !ModeTraits<MODE>::io;   // speeds / control
+    __shared__ __align__(16) float sh_stage[kStage ? kWarpsPerBlock * kStageFloats : 4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float4* wpos = sh_pos + wib * 32;
     float4* wvel = sh_vel + wib * 32;
+    float* stage = sh_stage + (kStage ? wib * kStageFloats : 0);
     const int G = GT ? GT : a.G;
     const int N = GT ? GT : c.N;
     const int E = c.E;
@@ -173,13 +193,64 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
     const int gw = blockIdx.x * kWarpsPerBlock + wib;
     const int chunk_lo = (int)(((long long)gw * a.nchunks) / wtotal);
     const int chunk_hi = (int)(((long long)(gw + 1) * a.nchunks) / wtotal);
+    // chunk = 32 consecutive agent slots (GT != 0): a plane's share is 128 contiguous bytes = 8 pieces
+    // of 16 B; 13 planes + 32 actions = 136 pieces, 4-5 cp.async.16 per lane instead of 14 scalar loads.
+    // Piece q = lane + 32 i (plane q >> 3, sub-piece q & 7) lands at stage float offset 4 q, and its
+    // global address is piece0 + i * (4 S floats): one base pointer per chunk, constant strides.
+    const float* piece0 = b.state + (size_t)(lane >> 3) * S + (lane & 7) * 4;
+    const size_t piece_stride = 4 * (size_t)S;
+    auto prefetch = [&](int chunk) {
+        const unsigned s0 = (unsigned)chunk * 32u;
+        const float* g = piece0 + s0;
+        float* sm = stage + 4 * lane;
+        if (s0 + 32u <= S) {
+            cp_async16(sm, g);
+            cp_async16(sm + 128, g + piece_stride);
+            cp_async16(sm + 256, g + 2 * piece_stride);
+            if (lane < 8) cp_async16(sm + 384, g + 3 * piece_stride);
+            cp_async16(sm + 416, a.actions + (size_t)(s0 + lane) * 4);
+        } else {                                   // last, partial chunk (S is a multiple of 4)
+            const bool ok = s0 + (lane & 7) * 4 < S;
+            if (ok) {
+                cp_async16(sm, g);
+                cp_async16(sm + 128, g + piece_stride);
+                cp_async16(sm + 256, g + 2 * piece_stride);
+                if (lane < 8) cp_async16(sm + 384, g + 3 * piece_stride);
+            }
+            if (s0 + lane < S) cp_async16(sm + 416, a.actions + (size_t)(s0 + lane) * 4);
+        }
+        cp_async_commit();
+    };
+    // Programmatic dependent launch: this grid may have been started while the previous kernel of
+    // the stream (normally the previous step) was still draining; everything above is index math.
+    // Let the next step's grid start launching as well, then wait for the previous grid's memory.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (kStage && chunk_lo < chunk_hi) prefetch(chunk_lo);
     for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+        // GT != 0: the chunk is 32 consecutive slots; else lanes >= N of a group idle
         const int e = chunk * gpw + (lane / G);
-        const bool valid = (e < E) && (GT || ai < N);
-        const unsigned s = valid ? (unsigned)e * (unsigned)N + (unsigned)ai : 0u;
+        const bool valid = GT ? ((unsigned)chunk * 32u + (unsigned)lane < S) : ((e < E) && (ai < N));
+        const unsigned s = valid ? (GT ? (unsigned)chunk * 32u + (unsigned)lane : (unsigned)e * (unsigned)N + (unsigned)ai) : 0u;
         Agent st;
         Ctrl k;
-        if (valid) {
+        float4 act0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kStage) {
+            cp_async_wait_all();
+            __syncwarp();           // pieces were fetched by other lanes
+            if (valid) {
+                st.px = stage[0 * 32 + lane]; st.py = stage[1 * 32 + lane]; st.pz = stage[2 * 32 + lane];
+                st.qx = stage[3 * 32 + lane]; st.qy = stage[4 * 32 + lane]; st.qz = stage[5 * 32 + lane];
+                st.qw = stage[6 * 32 + lane];
+                st.vx = stage[7 * 32 + lane]; st.vy = stage[8 * 32 + lane]; st.vz = stage[9 * 32 + lane];
+                st.wx = stage[10 * 32 + lane]; st.wy = stage[11 * 32 + lane]; st.wz = stage[12 * 32 + lane];
+                act0 = *reinterpret_cast<const float4*>(stage + 13 * 32 + 4 * lane);
+            } else {
+                dummy_agent(st);
+            }
+            __syncwarp();           // everyone has read its column before the stage is refilled
+            if (chunk + 1 < chunk_hi) prefetch(chunk + 1);
+        } else if (valid) {
             load_agent(b.state, S, s, st);
             load_ctrl<MODE>(b.ctrl, S, s, k);
         } else {
@@ -194,8 +265,14 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
         for (int t = 0; t < a.T; ++t) {
             float act[4];
             bool nan_act = false;
-            if (valid) nan_act = load_action<MODE>(a.actions, (size_t)t * S + s, act);
-            else act[0] = act[1] = act[2] = act[3] = 0.f;
+            if (kStage && t == 0) {
+                act[0] = act0.x; act[1] = act0.y; act[2] = act0.z; act[3] = act0.w;
+                nan_act = valid && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || isnan(act0.w));
+            } else if (valid) {
+                nan_act = load_action<MODE>(a.actions, (size_t)t * S + s, act);
+            } else {
+                act[0] = act[1] = act[2] = act[3] = 0.f;
+            }
             if (nan_act) status |= MRS_STATUS_NAN_ACTION;
 
             float R[9];
@@ -215,8 +292,9 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
                     if (GT || j < N) {
                         const float4 pj = wpos[gb + j];
                         const float rx = pj.x - st.px, ry = pj.y - st.py, rz = pj.z - st.pz;
-                        if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, d, rx, ry, rz);
-                        near = near || (rx * rx + ry * ry + rz * rz < d.lim2);
+                        const float dxy2 = rx * rx + ry * ry;
+                        if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, d, dxy2, rz);
+                        near = near || (dxy2 + rz * rz < d.lim2);
                     }
                 }
             }
@@ -311,118 +389,146 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
     }
 }
 
-// ------------------------------------------------------------------------------ tiled path (N > 32)
-// grid: (ceil(N / kBlock), E).  scratch planes: 0-2 unconstrained velocity, 3-5 pre-step position.
-template <int MODE>
+// ------------------------------------------------------------------------------ wide path (N > 32)
+// An env no longer fits a warp, so the pair passes are spread over LPA lanes PER AGENT (LPA = 8 for
+// N <= 128, else 32): every lane walks the partners j = l, l + LPA, ... of its agent straight from
+// the L1/L2-resident position planes, the partial sums are combined with a fixed-order xor-shuffle
+// tree (deterministic), and the group's lane 0 runs the per-agent part.  One env of 4096 agents
+// therefore fills the GPU with 4096 warps instead of 32 CTAs.
+// scratch planes: 0-2 unconstrained velocity, 3-5 pre-step position, 6 contact-proximity flag.
+template <int LPA>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPA / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+template <int MODE, int LPA>
 __global__ void __launch_bounds__(kBlock)
 step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
                 const float* __restrict__ actions) {
-    __shared__ float4 tile[kBlock];
     const int N = c.N;
     const unsigned S = (unsigned)c.E * (unsigned)N;
-    const unsigned env0 = blockIdx.y * (unsigned)N;
-    const int ai = blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = ai < N;
-    const unsigned s = env0 + (valid ? ai : 0);
+    const unsigned gid = (blockIdx.x * kBlock + threadIdx.x) / LPA;      // agent slot of this lane group
+    const int l = threadIdx.x & (LPA - 1);
+    const bool valid = gid < S;
+    const unsigned s = valid ? gid : 0u;
+    const unsigned env0 = (s / (unsigned)N) * (unsigned)N;
+    const int ai = (int)(s - env0);
+    const float* __restrict__ px = b.state + 0 * (size_t)S + env0;
+    const float* __restrict__ py = b.state + 1 * (size_t)S + env0;
+    const float* __restrict__ pz = b.state + 2 * (size_t)S + env0;
+    const float pix = px[ai], piy = py[ai], piz = pz[ai];
+    float dw = 0.f;
+    bool near = false;
+    const bool pair_contact = c.phys.agent_contact && N > 1;
+    if (MODE != MRS_NO_ACTION || pair_contact) {
+#pragma unroll 4
+        for (int j = l; j < N; j += LPA) {
+            const float rx = px[j] - pix, ry = py[j] - piy, rz = pz[j] - piz;
+            if (j != ai) {
+                const float dxy2 = rx * rx + ry * ry;
+                if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, d, dxy2, rz);
+                near = near || (dxy2 + rz * rz < d.lim2);
+            }
+        }
+    }
+    dw = group_sum<LPA>(dw);
+    const unsigned gmask = (LPA == 32) ? kFull : (((1u << LPA) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
+    near = (__ballot_sync(kFull, near) & gmask) != 0u;
+    if (l != 0 || !valid) return;
+
     Agent st;
     Ctrl k;
     load_agent(b.state, S, s, st);
     load_ctrl<MODE>(b.ctrl, S, s, k);
     float act[4];
     unsigned status = 0;
-    if (load_action<MODE>(actions, s, act) && valid) status |= MRS_STATUS_NAN_ACTION;
+    if (load_action<MODE>(actions, s, act)) status |= MRS_STATUS_NAN_ACTION;
     float R[9], rpm[4];
     quat_to_mat(st, R);
     action_to_rpm<MODE>(c, st, R, act, k, rpm);
-    float dw = 0.f;
-    if (MODE != MRS_NO_ACTION) {
-        for (int j0 = 0; j0 < N; j0 += kBlock) {
-            const int j = j0 + threadIdx.x;
-            __syncthreads();
-            if (j < N) tile[threadIdx.x] = make_float4(b.state[0 * S + env0 + j], b.state[1 * S + env0 + j],
-                                                       b.state[2 * S + env0 + j], 0.f);
-            __syncthreads();
-            const int cnt = min(kBlock, N - j0);
-            for (int u = 0; u < cnt; ++u) {
-                if (j0 + u == ai) continue;
-                const float4 pj = tile[u];
-                dw += downwash_pair(c.quad, d, pj.x - st.px, pj.y - st.py, pj.z - st.pz);
-            }
-        }
-    }
-    const float p0x = st.px, p0y = st.py, p0z = st.pz;
     apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
-    if (valid) {
-        float* sc = b.scratch;
-        sc[0 * S + s] = st.vx; sc[1 * S + s] = st.vy; sc[2 * S + s] = st.vz;
-        sc[3 * S + s] = p0x; sc[4 * S + s] = p0y; sc[5 * S + s] = p0z;
-        b.state[10 * S + s] = st.wx; b.state[11 * S + s] = st.wy; b.state[12 * S + s] = st.wz;
-        store_ctrl<MODE>(b.ctrl, S, s, k);
-        if (b.rpm && MODE != MRS_NO_ACTION) {
+    float* sc = b.scratch;
+    sc[0 * (size_t)S + s] = st.vx; sc[1 * (size_t)S + s] = st.vy; sc[2 * (size_t)S + s] = st.vz;
+    sc[3 * (size_t)S + s] = pix; sc[4 * (size_t)S + s] = piy; sc[5 * (size_t)S + s] = piz;
+    sc[6 * (size_t)S + s] = (near && pair_contact) ? 1.f : 0.f;
+    b.state[10 * (size_t)S + s] = st.wx; b.state[11 * (size_t)S + s] = st.wy; b.state[12 * (size_t)S + s] = st.wz;
+    store_ctrl<MODE>(b.ctrl, S, s, k);
+    if (b.rpm && MODE != MRS_NO_ACTION) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) b.rpm[i * S + s] = rpm[i];
-        }
-        if (status && b.status) {
-            atomicOr(b.status, status);
-            if (b.stats) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
-        }
+        for (int i = 0; i < 4; ++i) b.rpm[i * (size_t)S + s] = rpm[i];
+    }
+    if (status && b.status) {
+        atomicOr(b.status, status);
+        if (b.stats) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
     }
 }
 
+template <int LPA>
 __global__ void __launch_bounds__(kBlock)
 step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int slot) {
-    __shared__ float4 tpos[kBlock];
-    __shared__ float4 tvel[kBlock];
     const int N = c.N;
     const unsigned S = (unsigned)c.E * (unsigned)N;
-    const unsigned env0 = blockIdx.y * (unsigned)N;
-    const int ai = blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = ai < N;
-    const unsigned s = env0 + (valid ? ai : 0);
+    const unsigned gid = (blockIdx.x * kBlock + threadIdx.x) / LPA;
+    const int l = threadIdx.x & (LPA - 1);
+    const bool valid = gid < S;
+    const unsigned s = valid ? gid : 0u;
+    const unsigned env0 = (s / (unsigned)N) * (unsigned)N;
+    const int ai = (int)(s - env0);
     const MrsPhysicsParams& ph = c.phys;
-    const float* sc = b.scratch;
+    const float* __restrict__ sc = b.scratch;
     Agent st;
-    st.px = sc[3 * S + s]; st.py = sc[4 * S + s]; st.pz = sc[5 * S + s];
-    st.vx = sc[0 * S + s]; st.vy = sc[1 * S + s]; st.vz = sc[2 * S + s];
-    st.qx = b.state[3 * S + s]; st.qy = b.state[4 * S + s]; st.qz = b.state[5 * S + s]; st.qw = b.state[6 * S + s];
-    st.wx = b.state[10 * S + s]; st.wy = b.state[11 * S + s]; st.wz = b.state[12 * S + s];
-    unsigned rows = 0, gnd = 0;
-    if (ph.agent_contact && N > 1) {
-        float acc[3] = {0.f, 0.f, 0.f};
-        for (int j0 = 0; j0 < N; j0 += kBlock) {
-            const int j = j0 + threadIdx.x;
-            __syncthreads();
-            if (j < N) {
-                tpos[threadIdx.x] = make_float4(sc[3 * S + env0 + j], sc[4 * S + env0 + j], sc[5 * S + env0 + j], 0.f);
-                tvel[threadIdx.x] = make_float4(sc[0 * S + env0 + j], sc[1 * S + env0 + j], sc[2 * S + env0 + j], 0.f);
+    st.px = sc[3 * (size_t)S + s]; st.py = sc[4 * (size_t)S + s]; st.pz = sc[5 * (size_t)S + s];
+    st.vx = sc[0 * (size_t)S + s]; st.vy = sc[1 * (size_t)S + s]; st.vz = sc[2 * (size_t)S + s];
+    const bool near = valid && sc[6 * (size_t)S + s] != 0.f;       // uniform over the lane group
+    float acc[3] = {0.f, 0.f, 0.f};
+    unsigned rows = 0;
+    if (near) {
+        const float* __restrict__ qx = sc + 3 * (size_t)S + env0;
+        const float* __restrict__ qy = sc + 4 * (size_t)S + env0;
+        const float* __restrict__ qz = sc + 5 * (size_t)S + env0;
+        for (int j0 = l; j0 < N; j0 += 4 * LPA) {     // 4 independent partner loads in flight per lane
+            float dx[4], dy[4], dz[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * LPA;
+                const bool ok = j < N && j != ai;
+                const int jj = ok ? j : ai;
+                dx[u] = st.px - qx[jj]; dy[u] = st.py - qy[jj]; dz[u] = st.pz - qz[jj];
+                if (!ok) dx[u] = 1.0e18f;
             }
-            __syncthreads();
-            const int cnt = min(kBlock, N - j0);
-            for (int u = 0; u < cnt; ++u) {
-                if (j0 + u == ai) continue;
-                const float4 pj = tpos[u];
-                const float dx = st.px - pj.x, dy = st.py - pj.y, dz = st.pz - pj.z;
-                if (dx * dx + dy * dy + dz * dz < d.lim2) {
-                    const float4 vj = tvel[u];
-                    if (agent_contact_pair(ph, d, dx, dy, dz, st.vx - vj.x, st.vy - vj.y, st.vz - vj.z, acc)) ++rows;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u] < d.lim2) {
+                    const int j = j0 + u * LPA;
+                    const float vjx = sc[0 * (size_t)S + env0 + j], vjy = sc[1 * (size_t)S + env0 + j],
+                                vjz = sc[2 * (size_t)S + env0 + j];
+                    if (agent_contact_pair(ph, d, dx[u], dy[u], dz[u], st.vx - vjx, st.vy - vjy, st.vz - vjz, acc)) ++rows;
                 }
             }
         }
-        st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
     }
+    // every lane of the warp takes part in the shuffles (groups without contact add zeros)
+    acc[0] = group_sum<LPA>(acc[0]); acc[1] = group_sum<LPA>(acc[1]); acc[2] = group_sum<LPA>(acc[2]);
+    rows = (unsigned)group_sum<LPA>((float)rows);
+    if (l != 0 || !valid) return;
+    st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
+    st.qx = b.state[3 * (size_t)S + s]; st.qy = b.state[4 * (size_t)S + s]; st.qz = b.state[5 * (size_t)S + s];
+    st.qw = b.state[6 * (size_t)S + s];
+    st.wx = b.state[10 * (size_t)S + s]; st.wy = b.state[11 * (size_t)S + s]; st.wz = b.state[12 * (size_t)S + s];
+    unsigned gnd = 0;
     if (ph.ground_contact && ground_contact(ph, d, st)) ++gnd;
     integrate(c, d, st);
-    if (valid) {
-        store_agent(b.state, S, s, st);
-        if (b.X_tape && c.state_layout != MRS_X_NONE)
-            write_X(b.X_tape + (size_t)slot * S * state_dim(c.state_layout), c.state_layout, s, st);
-        const bool bad = !agent_finite(st);
-        if (bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
-        if (b.stats) {
-            if (rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)rows);
-            if (gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)gnd);
-            if (bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, 1ull);
-        }
+    store_agent(b.state, S, s, st);
+    if (b.X_tape && c.state_layout != MRS_X_NONE)
+        write_X(b.X_tape + (size_t)slot * S * state_dim(c.state_layout), c.state_layout, s, st);
+    const bool bad = !agent_finite(st);
+    if (bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
+    if (b.stats) {
+        if (rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)rows);
+        if (gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)gnd);
+        if (bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, 1ull);
     }
 }
 
@@ -633,9 +739,33 @@ static int launch_group(const MrsConfig& c, const Derived& d, const MrsBuffers& 
     const int bps = env_int("MRS_B200_BLOCKS_PER_SM", resident);
     const long long need = ((long long)a.nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const long long cap = (long long)sms * (bps > 0 ? bps : resident);
-    // small jobs: one chunk per warp; large jobs: exactly SMs x resident CTAs (one full wave), the
-    // kernel splits the chunks evenly over all warps
-    const long long blocks = need < cap ? need : cap;
+    // one wave; when a warp must take several chunks, shrink the grid so that every warp takes the
+    // same number (the kernel splits the chunks evenly over all warps of the grid)
+    long long blocks = need;
+    if (need > cap) {
+        const long long iters = (need + cap - 1) / cap;
+        blocks = (need + iters - 1) / iters;
+    }
+    // Programmatic dependent launch pays off when the grid is a full wave (measured: -2.3 % at C5);
+    // partial waves are faster with the plain stream order (C3: +11 % with PDL), so keep it to those.
+    static const int use_pdl = env_int("MRS_B200_PDL", 1);
+    if (use_pdl && need >= cap) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)blocks);
+        lc.blockDim = dim3(kBlock);
+        lc.dynamicSmemBytes = 0;
+        lc.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        if (cudaLaunchKernelEx(&lc, step_group_kernel<MODE, GT>, c, d, b, a) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return MRS_ERR_CUDA;
+        }
+        return last_error();
+    }
     step_group_kernel<MODE, GT><<<(unsigned)blocks, kBlock, 0, st>>>(c, d, b, a);
     return last_error();
 }
@@ -657,15 +787,14 @@ static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, in
     return last_error();
 }
 
-template <int MODE>
-static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
-    if (!b.scratch) return MRS_ERR_ARG;
+template <int MODE, int LPA>
+static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     const size_t S = (size_t)c.E * c.N;
     constexpr int A = ModeTraits<MODE>::A;
-    dim3 grid((unsigned)((c.N + kBlock - 1) / kBlock), (unsigned)c.E);
+    const unsigned blocks = (unsigned)((S * LPA + kBlock - 1) / kBlock);
     for (int t = 0; t < a.T; ++t) {
-        step_pre_kernel<MODE><<<grid, kBlock, 0, st>>>(c, d, b, a.actions ? a.actions + (size_t)t * S * A : nullptr);
-        step_post_kernel<<<grid, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
+        step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, a.actions ? a.actions + (size_t)t * S * A : nullptr);
+        step_post_kernel<LPA><<<blocks, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
         if (b.A_tape) {
             const int rc = launch_adjacency(b.state, S, 1, b.A_tape + (size_t)(a.slot_a - t) * S * c.N, c.E, c.N, d.s_max,
                                             d.comm_inf, st);
@@ -673,6 +802,13 @@ static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& 
         }
     }
     return last_error();
+}
+
+template <int MODE>
+static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
+    if (!b.scratch) return MRS_ERR_ARG;
+    if ((unsigned long long)c.E * c.N * 32ull >= 0x7fffffffull * (unsigned long long)kBlock) return MRS_ERR_UNSUPPORTED;
+    return c.N <= 128 ? launch_wide_lpa<MODE, 8>(c, d, b, a, st) : launch_wide_lpa<MODE, 32>(c, d, b, a, st);
 }
 
 static int pow2ceil(int n) {
@@ -949,6 +1085,82 @@ int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* act
                             cudaMemcpyDeviceToHost, st) != cudaSuccess)
             return MRS_ERR_CUDA;
     }
+    return cudaStreamSynchronize(st) == cudaSuccess ? MRS_OK : MRS_ERR_CUDA;
+}
+
+
+// Pipelined host rollout: three streams so that the H2D of step t+1's actions and the D2H of step
+// t-1's X / A slices overlap the kernel of step t (PCIe is full duplex).  The compute stream is the
+// caller's; the two copy streams and four events are created once per device and reused.
+namespace {
+struct CopyLanes {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, tail = nullptr;
+    bool ok = false;
+};
+CopyLanes g_lanes[64];
+CopyLanes* copy_lanes() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    CopyLanes& L = g_lanes[dev];
+    if (!L.ok) {
+        if (cudaStreamCreateWithFlags(&L.h2d, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&L.d2h, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaEventCreateWithFlags(&L.up[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&L.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&L.tail, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        L.ok = true;
+    }
+    return &L;
+}
+}  // namespace
+
+int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host, float* dev_actions,
+                     float* X_host, float* A_host, int T, int slot_x_first, int slot_a_first, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs || T <= 0) return MRS_ERR_ARG;
+    const int adim = mrs_action_dim(cfg->action_type);
+    if (adim <= 0 || !actions_host || !dev_actions) return MRS_ERR_ARG;
+    CopyLanes* L = copy_lanes();
+    if (!L) return MRS_ERR_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t S = (size_t)cfg->E * cfg->N;
+    const size_t abytes = S * adim * sizeof(float);
+    const int D = mrs_state_dim(cfg->state_layout);
+    const size_t xelems = S * (size_t)D, aelems = S * (size_t)cfg->N;
+    // the copy lanes start after whatever the caller already queued on the compute stream
+    if (cudaEventRecord(L->tail, st) != cudaSuccess) return MRS_ERR_CUDA;
+    if (cudaStreamWaitEvent(L->h2d, L->tail, 0) != cudaSuccess) return MRS_ERR_CUDA;
+    if (cudaStreamWaitEvent(L->d2h, L->tail, 0) != cudaSuccess) return MRS_ERR_CUDA;
+    for (int t = 0; t < T; ++t) {
+        const int bsel = t & 1;
+        float* da = dev_actions + (size_t)bsel * S * adim;
+        if (t >= 2 && cudaStreamWaitEvent(L->h2d, L->done[bsel], 0) != cudaSuccess) return MRS_ERR_CUDA;
+        if (cudaMemcpyAsync(da, actions_host + (size_t)t * S * adim, abytes, cudaMemcpyHostToDevice, L->h2d) != cudaSuccess)
+            return MRS_ERR_CUDA;
+        if (cudaEventRecord(L->up[bsel], L->h2d) != cudaSuccess) return MRS_ERR_CUDA;
+        if (cudaStreamWaitEvent(st, L->up[bsel], 0) != cudaSuccess) return MRS_ERR_CUDA;
+        rc = step_impl(cfg, bufs, da, 1, slot_x_first - t, slot_a_first - t, stream);
+        if (rc) return rc;
+        if (cudaEventRecord(L->done[bsel], st) != cudaSuccess) return MRS_ERR_CUDA;
+        if ((X_host && bufs->X_tape && D > 0) || (A_host && bufs->A_tape)) {
+            if (cudaStreamWaitEvent(L->d2h, L->done[bsel], 0) != cudaSuccess) return MRS_ERR_CUDA;
+            if (X_host && bufs->X_tape && D > 0 &&
+                cudaMemcpyAsync(X_host + (size_t)t * xelems, bufs->X_tape + (size_t)(slot_x_first - t) * xelems,
+                                xelems * sizeof(float), cudaMemcpyDeviceToHost, L->d2h) != cudaSuccess)
+                return MRS_ERR_CUDA;
+            if (A_host && bufs->A_tape &&
+                cudaMemcpyAsync(A_host + (size_t)t * aelems, bufs->A_tape + (size_t)(slot_a_first - t) * aelems,
+                                aelems * sizeof(float), cudaMemcpyDeviceToHost, L->d2h) != cudaSuccess)
+                return MRS_ERR_CUDA;
+        }
+    }
+    // join: the caller's stream continues only after the last copies
+    if (cudaEventRecord(L->tail, L->d2h) != cudaSuccess) return MRS_ERR_CUDA;
+    if (cudaStreamWaitEvent(st, L->tail, 0) != cudaSuccess) return MRS_ERR_CUDA;
     return cudaStreamSynchronize(st) == cudaSuccess ? MRS_OK : MRS_ERR_CUDA;
 }
 

@@ -15,7 +15,7 @@ ABI_VERSION = 1
 STATE_PLANES = 13
 CTRL_PLANES = 18
 STATS_SLOTS = 8
-SCRATCH_PLANES = 6
+SCRATCH_PLANES = 7
 
 # MrsActionType: the reference's ACTION_TYPE strings are Quadcopter method names
 # (/root/reference/mrsgym/Environment.py:92)
@@ -96,6 +96,8 @@ _SIGNATURES = {
                                 C.c_void_p]),
     'mrs_step_host': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'mrs_rollout_host': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

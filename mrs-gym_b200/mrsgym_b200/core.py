@@ -231,6 +231,28 @@ class Swarm:
         if self.A_tape is not None:
             self.ha = ha
 
+    def rollout_host(self, actions_host, dev_actions2, X_host=None, A_host=None):
+        """mrs_rollout_host: T steps from pinned host actions [T,E,N,A] with the newest X / A slice of
+        every step copied to pinned host arrays [T,E,N,D] / [T,E,N,N]; copies overlap the kernels.
+        Chunks at tape wrap-arounds."""
+        T = int(actions_host.shape[0])
+        done = 0
+        while done < T:
+            hx = self._make_room(1) if self.X_tape is not None else T
+            ha = self._make_room(2) if self.A_tape is not None else T
+            n = min(T - done, hx, ha)
+            _abi.check(self.lib.mrs_rollout_host(
+                C.byref(self.cfg), C.byref(self.bufs), _ptr(actions_host[done:done + n]), _ptr(dev_actions2),
+                _ptr(X_host[done:done + n]) if X_host is not None else C.c_void_p(0),
+                _ptr(A_host[done:done + n]) if A_host is not None else C.c_void_p(0),
+                n, hx - 1, ha - 1, self._stream()), 'mrs_rollout_host')
+            self.launches += n if self.N <= 32 else n * (3 if self.A_tape is not None else 2)
+            if self.X_tape is not None:
+                self.hx = hx - n
+            if self.A_tape is not None:
+                self.ha = ha - n
+            done += n
+
     # ------------------------------------------------------------------ state access
     def set_state(self, pos=None, ori=None, vel=None, angvel=None, env_mask=None):
         """Environment.set_state -> Object.set_state (Environment.py:97-103, Object.py:42-65).

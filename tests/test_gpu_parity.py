@@ -94,7 +94,7 @@ def test_adjacency_threshold_edges():
 
 # ------------------------------------------------------------------------------ one step
 @pytest.mark.parametrize('mode', H.MODES)
-@pytest.mark.parametrize('E,N', [(64, 8), (5, 3), (8, 32), (3, 40)])
+@pytest.mark.parametrize('E,N', [(64, 8), (5, 3), (8, 32), (3, 40), (2, 100), (1, 300)])
 def test_one_step_delta_vs_oracle(mode, E, N):
     rng = np.random.default_rng(sum(map(ord, mode)) * 1000 + E * 37 + N)
     st = H.random_state(rng, E, N, spacing=0.9)
@@ -150,7 +150,7 @@ def test_no_action_step_is_free_fall():
 
 
 # ------------------------------------------------------------------------------ contact
-@pytest.mark.parametrize('N', [4, 16, 48])
+@pytest.mark.parametrize('N', [4, 16, 48, 200])
 def test_contact_one_step(N):
     """ground landing + AGENT_RADIUS sphere-sphere rows (C3 regime: 0.55 m spacing < 2*0.3)"""
     E = 32
@@ -246,7 +246,8 @@ def test_ring_semantics_match_reference():
                 assert float(Aw[k].abs().sum()) == 0.0, (t, k)
 
 
-@pytest.mark.parametrize('N,mode', [(8, 'set_speeds'), (32, 'set_target_pos'), (3, 'set_target_vel'), (40, 'set_control')])
+@pytest.mark.parametrize('N,mode', [(8, 'set_speeds'), (32, 'set_target_pos'), (3, 'set_target_vel'), (40, 'set_control'),
+                                    (16, 'set_control'), (150, 'set_force')])
 def test_step_many_equals_repeated_step(N, mode):
     E, K, T = 33, 2, 23
     rng = np.random.default_rng(21)
@@ -264,7 +265,7 @@ def test_step_many_equals_repeated_step(N, mode):
     assert torch.equal(a.X_window(), b.X_window()) and torch.equal(a.A_window(), b.A_window())
 
 
-@pytest.mark.parametrize('N', [8, 40])
+@pytest.mark.parametrize('N', [8, 40, 130])
 def test_env_shards_are_independent(N):
     """1-GPU result == concatenation of per-shard results, bit for bit."""
     import mrsgym_b200 as M
@@ -328,6 +329,29 @@ def test_step_host_roundtrip():
     b.step_host(ah, torch.empty(E, N, 4, device='cuda'), Xh, Ah)
     assert torch.equal(a.state, b.state)
     assert torch.equal(Xh, a.X_window()[0].cpu()) and torch.equal(Ah, a.A_window()[0].cpu())
+
+
+def test_rollout_host_pipelined_equals_steps():
+    E, N, K, T = 256, 8, 2, 37
+    rng = np.random.default_rng(52)
+    st = H.random_state(rng, E, N)
+    act = H.random_actions(rng, 'set_speeds', T, E, N)
+    a = _swarm(E, N, 'set_speeds', K, 2.0, tape_slots=16)
+    b = _swarm(E, N, 'set_speeds', K, 2.0, tape_slots=16)
+    H.upload_state(a, st)
+    H.upload_state(b, st)
+    Xs, As = [], []
+    for t in range(T):
+        a.step(_dev(act[t]))
+        Xs.append(a.X_window()[0].cpu())
+        As.append(a.A_window()[0].cpu())
+    ah = torch.from_numpy(act).pin_memory()
+    Xh = torch.empty(T, E, N, 6).pin_memory()
+    Ah = torch.empty(T, E, N, N).pin_memory()
+    b.rollout_host(ah, torch.empty(2, E, N, 4, device='cuda'), Xh, Ah)
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(Xh, torch.stack(Xs)) and torch.equal(Ah, torch.stack(As))
+    assert torch.equal(a.X_window(), b.X_window()) and torch.equal(a.A_window(), b.A_window())
 
 
 def test_full_size_properties_c5():
