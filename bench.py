@@ -298,6 +298,9 @@ def run_gpu(args):
         e2e_pipe_value = float(E) * N * n_p * world / (pipe_ms * 1e-3)
         del ah, Xhh, Ahh
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     peaks_path = os.path.join(_REPO, 'MEASURED_PEAKS.json')

@@ -18,9 +18,12 @@ def init_from_env(backend=None):
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        kw = {}
         if backend == 'nccl':
-            torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            local = int(os.environ.get('LOCAL_RANK', rank))
+            torch.cuda.set_device(local)
+            kw['device_id'] = torch.device('cuda', local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world
 
 
