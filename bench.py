@@ -193,7 +193,8 @@ def run_gpu(args):
     replays = steps // T
 
     st, act_np = make_inputs(w, E, T, seed=1234 + 4 + rank)
-    sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T + 2 * K + 2)
+    sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T + 2 * K + 2,
+                 want_A=not os.environ.get('MRS_EXP_NO_A'))
     H.upload_state(sw, st)
     actions = torch.from_numpy(act_np).to(dev)
     roll = sw.capture_rollout(actions, T)

@@ -30,7 +30,6 @@
 namespace mrs {
 
 constexpr int kBlock = 128;
-constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct StepArgs {
@@ -163,14 +162,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // ------------------------------------------------------------------------------ group path
 // GT > 0: compile-time group width with N == GT (8, 16, 32: pair loops unrolled, no bounds tests);
 // GT == 0: run-time width a.G >= N (any N <= 32).
-template <int MODE, int GT>
-__global__ void __launch_bounds__(kBlock, ModeTraits<MODE>::minb)
+// WPB = warps per CTA.  WPB = 4: many small CTAs, chunks handed out grid-stride (small jobs).
+// WPB = 4 * minb (one CTA owns a whole SM): the CTA takes a contiguous share of the chunks and its
+// warps pull them from a shared-memory counter.  Per-warp timestamps at C5 (tools/trace_c5.py)
+// showed that with a static split the warps of one launch finish between 12 and 21 us after the
+// start -- the hardware warp scheduler is not fair -- and the kernel lasts as long as its slowest
+// warp; the SM-local dynamic hand-out keeps all warps of an SM busy until its share is done
+// (first / last warp end 14.7 / 20.2 us).  A device-wide atomic counter was tried first: 12k
+// same-address L2 atomics per launch serialise and cost +40 %.
+template <int MODE, int GT, int WPB>
+__global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : 1)
 step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
                   const StepArgs a) {
-    __shared__ float4 sh_pos[kBlock];
-    __shared__ float4 sh_vel[kBlock];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool kStage = MRS_PREFETCH && GT != 0 && ModeTraits<MODE>::A == 4 && !ModeTraits<MODE>::io;   // speeds / control
-    __shared__ __align__(16) float sh_stage[kStage ? kWarpsPerBlock * kStageFloats : 4];
+    float4* sh_pos = reinterpret_cast<float4*>(smem_raw);
+    float4* sh_vel = sh_pos + WPB * 32;
+    float* sh_stage = reinterpret_cast<float*>(sh_vel + WPB * 32);
+    __shared__ int sh_counter;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float4* wpos = sh_pos + wib * 32;
     float4* wvel = sh_vel + wib * 32;
@@ -182,17 +191,35 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
     const int ai = lane & (G - 1);
     const int gb = lane - ai;
     const unsigned S = (unsigned)E * (unsigned)N;
-    const int wtotal = gridDim.x * kWarpsPerBlock;
+    const int wtotal = gridDim.x * WPB;
     const MrsPhysicsParams& ph = c.phys;
     const bool pair_contact = ph.agent_contact && N > 1;
     const size_t xslot = (size_t)S * (size_t)state_dim(c.state_layout);
     const size_t aslot = (size_t)S * (size_t)N;
 
-    // contiguous chunk range per warp, split as evenly as the integers allow over ALL warps of the
-    // grid (grid = SMs x resident CTAs, so every SM carries the same number of chunks +-1)
-    const int gw = blockIdx.x * kWarpsPerBlock + wib;
-    const int chunk_lo = (int)(((long long)gw * a.nchunks) / wtotal);
-    const int chunk_hi = (int)(((long long)(gw + 1) * a.nchunks) / wtotal);
+    // Work distribution (see the comment above the kernel): two static rounds, then the CTA-local
+    // counter.  The hand-out for the chunk after next is issued at the top of an iteration
+    // (shared-memory atomic) and consumed at the bottom, so the stage prefetch of the next chunk can
+    // always be issued immediately.
+    constexpr bool kLocal = WPB > 4;
+    const int gw = blockIdx.x * WPB + wib;
+    const int cta_lo = kLocal ? (int)(((long long)blockIdx.x * a.nchunks) / gridDim.x) : 0;
+    const int cta_hi = kLocal ? (int)(((long long)(blockIdx.x + 1) * a.nchunks) / gridDim.x) : a.nchunks;
+    if (kLocal) {
+        if (threadIdx.x == 0) sh_counter = 0;
+        __syncthreads();
+    }
+    auto issue_fetch = [&]() -> int {
+        int v = 0;
+        if (kLocal && lane == 0) v = atomicAdd(&sh_counter, 1);
+        return v;
+    };
+    auto resolve_fetch = [&](int v, int cur_next) -> int {
+        int nx;
+        if (kLocal) nx = cta_lo + 2 * WPB + __shfl_sync(kFull, v, 0);
+        else nx = cur_next + wtotal;
+        return (cur_next >= 0 && nx < cta_hi) ? nx : -1;
+    };
     // chunk = 32 consecutive agent slots (GT != 0): a plane's share is 128 contiguous bytes = 8 pieces
     // of 16 B; 13 planes + 32 actions = 136 pieces, 4-5 cp.async.16 per lane instead of 14 scalar loads.
     // Piece q = lane + 32 i (plane q >> 3, sub-piece q & 7) lands at stage float offset 4 q, and its
@@ -224,10 +251,39 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
     // Programmatic dependent launch: this grid may have been started while the previous kernel of
     // the stream (normally the previous step) was still draining; everything above is index math.
     // Let the next step's grid start launching as well, then wait for the previous grid's memory.
+#ifdef MRS_TRACE
+    // debug build (tools/trace_c5.py): per-warp timeline (globaltimer ns) into bufs.scratch seen as
+    // u64[warps][8], plus per-step aggregates [min start, max wait release, max end, min end]
+    unsigned long long* trace = reinterpret_cast<unsigned long long*>(b.scratch) + (size_t)gw * 8;
+    unsigned long long* agg = reinterpret_cast<unsigned long long*>(b.scratch) + (size_t)8192 * 8 + (size_t)a.slot_x * 4;
+    int trace_i = 0;
+    auto stamp = [&]() {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        if (lane == 0 && trace_i < 8) trace[trace_i] = tns;
+        if (lane == 0 && trace_i == 0) atomicMin(agg + 0, tns);
+        if (lane == 0 && trace_i == 1) atomicMax(agg + 1, tns);
+        ++trace_i;
+    };
+    auto stamp_end = [&]() {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        if (lane == 0) { atomicMax(agg + 2, tns); atomicMin(agg + 3, tns); }
+    };
+    stamp();
+#endif
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (kStage && chunk_lo < chunk_hi) prefetch(chunk_lo);
-    for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+#ifdef MRS_TRACE
+    stamp();
+#endif
+    const int first = kLocal ? cta_lo + wib : gw;
+    const int stride0 = kLocal ? WPB : wtotal;
+    int chunk = first < cta_hi ? first : -1;
+    int chunk_next = (chunk >= 0 && first + stride0 < cta_hi) ? first + stride0 : -1;
+    if (kStage && chunk >= 0) prefetch(chunk);
+    while (chunk >= 0) {
+        const int fetch_ticket = (chunk_next >= 0) ? issue_fetch() : 0;   // warp-uniform condition
         // GT != 0: the chunk is 32 consecutive slots; else lanes >= N of a group idle
         const int e = chunk * gpw + (lane / G);
         const bool valid = GT ? ((unsigned)chunk * 32u + (unsigned)lane < S) : ((e < E) && (ai < N));
@@ -249,7 +305,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
                 dummy_agent(st);
             }
             __syncwarp();           // everyone has read its column before the stage is refilled
-            if (chunk + 1 < chunk_hi) prefetch(chunk + 1);
+            if (chunk_next >= 0) prefetch(chunk_next);
         } else if (valid) {
             load_agent(b.state, S, s, st);
             load_ctrl<MODE>(b.ctrl, S, s, k);
@@ -370,6 +426,9 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
         } else {
             status = 0; n_agent_rows = 0; n_ground = 0;
         }
+#ifdef MRS_TRACE
+        stamp();
+#endif
         // warp-aggregated status / statistics (atomics only when something happened)
         const unsigned any_status = __reduce_or_sync(kFull, status);
         const unsigned events = __reduce_or_sync(kFull, n_agent_rows | n_ground);
@@ -386,7 +445,13 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
                 }
             }
         }
+        const int chunk_next2 = resolve_fetch(fetch_ticket, chunk_next);
+        chunk = chunk_next;
+        chunk_next = chunk_next2;
     }
+#ifdef MRS_TRACE
+    stamp_end();
+#endif
 }
 
 // ------------------------------------------------------------------------------ wide path (N > 32)
@@ -726,48 +791,51 @@ static Derived make_derived(const MrsConfig& c) {
     return d;
 }
 
+template <int MODE, int GT, int WPB>
+static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
+                            bool pdl, cudaStream_t st) {
+    constexpr bool kStage = MRS_PREFETCH && GT != 0 && ModeTraits<MODE>::A == 4 && !ModeTraits<MODE>::io;
+    constexpr size_t smem = (size_t)WPB * 32 * 2 * sizeof(float4) + (kStage ? (size_t)WPB * kStageFloats * sizeof(float) : 16);
+    static bool configured = false;
+    if (!configured) {
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+                cudaSuccess)
+            return MRS_ERR_CUDA;
+        configured = true;
+    }
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)blocks);
+    lc.blockDim = dim3(WPB * 32);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&lc, step_group_kernel<MODE, GT, WPB>, c, d, b, a) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return MRS_ERR_CUDA;
+    }
+    return last_error();
+}
+
 template <int MODE, int GT>
 static int launch_group(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
-    static int resident = 0;
-    if (resident == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, step_group_kernel<MODE, GT>, kBlock, 0) != cudaSuccess ||
-            resident <= 0)
-            return MRS_ERR_CUDA;
-    }
+    constexpr int kBig = 4 * ModeTraits<MODE>::minb;            // warps of a CTA that owns a whole SM
     const int sms = sm_count();
     if (sms <= 0) return MRS_ERR_CUDA;
-    const int bps = env_int("MRS_B200_BLOCKS_PER_SM", resident);
-    const long long need = ((long long)a.nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const long long cap = (long long)sms * (bps > 0 ? bps : resident);
-    // one wave; when a warp must take several chunks, shrink the grid so that every warp takes the
-    // same number (the kernel splits the chunks evenly over all warps of the grid)
-    long long blocks = need;
-    if (need > cap) {
-        const long long iters = (need + cap - 1) / cap;
-        blocks = (need + iters - 1) / iters;
-    }
-    // Programmatic dependent launch pays off when the grid is a full wave (measured: -2.3 % at C5);
-    // partial waves are faster with the plain stream order (C3: +11 % with PDL), so keep it to those.
     static const int use_pdl = env_int("MRS_B200_PDL", 1);
-    if (use_pdl && need >= cap) {
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((unsigned)blocks);
-        lc.blockDim = dim3(kBlock);
-        lc.dynamicSmemBytes = 0;
-        lc.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = attr;
-        lc.numAttrs = 1;
-        if (cudaLaunchKernelEx(&lc, step_group_kernel<MODE, GT>, c, d, b, a) != cudaSuccess) {
-            (void)cudaGetLastError();
-            return MRS_ERR_CUDA;
-        }
-        return last_error();
-    }
-    step_group_kernel<MODE, GT><<<(unsigned)blocks, kBlock, 0, st>>>(c, d, b, a);
-    return last_error();
+    static const int use_big = env_int("MRS_B200_BIGCTA", 1);
+    // large jobs (every warp of the GPU gets more than two chunks): one SM-sized CTA per SM with the
+    // shared-memory hand-out.  Programmatic dependent launch pays off for full waves (measured
+    // -2.3 % at C5); partial waves are faster with plain stream order (C3: +11 % with PDL).
+    if (use_big && a.nchunks > 2 * sms * kBig)
+        return launch_group_wpb<MODE, GT, kBig>(c, d, b, a, sms, use_pdl != 0, st);
+    const long long need = ((long long)a.nchunks + 3) / 4;
+    const long long cap = (long long)sms * ModeTraits<MODE>::minb;
+    return launch_group_wpb<MODE, GT, 4>(c, d, b, a, need < cap ? need : cap, use_pdl && need >= cap, st);
 }
 
 static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, int N, float s_max, int comm_inf,
