@@ -350,7 +350,7 @@ def run_gpu(args):
         out['cpu_baseline'] = {'value': v, 'unit': 'agent-steps/s', 'cores': procs, 'kind': 'port',
                                'sample': '%d processes x %d envs x %d agents x %d steps of the same workload '
                                          '(oracle/spec.py, numpy float64); %.1f s' % (procs, Ep, w['N'], Tc, total)}
-    print(json.dumps(out))
+    emit(out)
 
 
 def run_reference(args):
@@ -378,7 +378,25 @@ def run_reference(args):
         'e2e': {'value': v, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything except the final JSON line goes to stderr (NCCL / torch banners print to fd 1)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + '\n')
+    out.flush()
 
 
 def main():
@@ -394,6 +412,7 @@ def main():
     ap.add_argument('--clock-seconds', type=float, default=1.0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
