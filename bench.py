@@ -49,6 +49,11 @@ WORKLOADS = {
                desc='256 envs x 32 agents, set_target_pos, K_HOPS=3, RETURN_A COMM_RANGE=2.0 (BASELINE configs[1])'),
     'c3': dict(E=4096, N=16, mode='set_control', K=0, R=float('inf'), spacing=0.7, z0=1.0, B=144,
                desc='4096 envs x 16 agents, set_control, ground + agent contact (BASELINE configs[2])'),
+    # not BASELINE configs: the C5 shape with the PID action modes (profiling the controller path)
+    'c5v': dict(E=65536, N=8, mode='set_target_vel', K=3, R=2.0, spacing=1.0, z0=2.5, B=296,
+                desc='65536 envs x 8 agents per GPU, set_target_vel, K_HOPS=3, RETURN_A COMM_RANGE=2.0'),
+    'c5p': dict(E=65536, N=8, mode='set_target_pos', K=3, R=2.0, spacing=1.0, z0=2.5, B=220,
+                desc='65536 envs x 8 agents per GPU, set_target_pos, K_HOPS=3, RETURN_A COMM_RANGE=2.0'),
     'c4': dict(E=1, N=4096, mode='set_force', K=0, R=2.0, spacing=1.0, z0=2.0, B=16548,
                desc='1 env x 4096 agents, set_force, adjacency dominated (BASELINE configs[3])'),
 }
@@ -66,6 +71,8 @@ def make_inputs(w, E, T, seed):
         act = (HOVER * (1 + 0.05 * rng.standard_normal((T, E, N, 4), dtype=np.float32))).astype(np.float32)
     elif mode == 'set_target_pos':
         act = np.broadcast_to((st['pos'] + rng.normal(0, 0.5, (E, N, 3)).astype(np.float32))[None], (T, E, N, 3)).copy()
+    elif mode == 'set_target_vel':
+        act = (rng.standard_normal((1, E, N, 3), dtype=np.float32) * 0.5).repeat(T, 0)
     elif mode == 'set_control':
         act = np.concatenate([9.81 + rng.uniform(-1, 1, (T, E, N, 1)), rng.uniform(-1, 1, (T, E, N, 3))],
                              axis=-1).astype(np.float32)

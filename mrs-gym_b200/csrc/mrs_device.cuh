@@ -44,6 +44,18 @@ template <> struct ModeTraits<MRS_SET_CONTROL>      { static constexpr int A = 4
 template <> struct ModeTraits<MRS_SET_SPEEDS>       { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
 template <> struct ModeTraits<MRS_NO_ACTION>        { static constexpr int A = 0; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
 
+// PID planes a mode carries through the prefetch stage, in stage order: io (planes 0-2), then ip
+// (3-5) or the 12 velocity-controller planes (6-17)
+template <int MODE> __host__ __device__ constexpr int mode_nctrl() {
+    return (ModeTraits<MODE>::io ? 3 : 0) + (ModeTraits<MODE>::ip ? 3 : 0) + (ModeTraits<MODE>::vel ? 12 : 0);
+}
+template <int MODE> __host__ __device__ constexpr int mode_ctrl_plane(int ordinal) {
+    return (ModeTraits<MODE>::vel && ordinal >= 3) ? ordinal + 3 : ordinal;
+}
+template <int MODE> __host__ __device__ constexpr int mode_stage_floats() {
+    return (13 + mode_nctrl<MODE>()) * 32 + ModeTraits<MODE>::A * 32;
+}
+
 __host__ __device__ __forceinline__ int state_dim(int layout) {
     return layout == MRS_X_POS_VEL ? 6 : (layout == MRS_X_FULL ? 13 : 0);
 }
@@ -59,10 +71,44 @@ __device__ __forceinline__ void quat_to_mat(const Agent& s, float* R) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Host-derived constants (reciprocals, products) so that the per-agent code carries no uniform
+// divisions.  Not part of the C ABI: step_impl() fills it from MrsConfig for every call.
+struct Derived {
+    float inv_mass, inv_I[3];
+    float gnd_c;         // kf * gnd_eff_coeff * (prop_radius/4)^2      (ground effect numerator)
+    float dw_c;          // dw1 * (prop_radius/4)^2                      (downwash alpha numerator)
+    float rpm2rad;       // 2*pi/60
+    float q_x2;          // 0.25*dt^2: squared half rotation angle per unit |w|^2
+    float cap_w2;        // (ang_motion_threshold/dt)^2
+    float cap_k, cap_c;  // sin(pi/8) / ((pi/4)/dt), cos(pi/8): Bullet's capped angular step
+    float lim2;          // (2*agent_radius + contact_margin)^2
+    float gnd_skip_z;    // above this height the ground contact row cannot be active
+    float inv_dt, erp_dt;
+    float s_max;         // adjacency threshold on the squared distance
+    int comm_inf;
+    float inv_ctrl_dt;   // 1 / QuadControl DT
+    float inv_4kf;       // 1 / (4 kf)
+    float inv_pwm_a;     // 1 / pwm2rpm_a
+    float inv_qmass;     // 1 / quad mass (set_force := set_target_accel(F / Mass))
+};
+
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 1/sqrt(x) to full float32 accuracy: SFU seed + one Newton step (x > 0)
+__device__ __forceinline__ float rsqrt_nr(float x) {
+    const float y = fast_rsqrt(x);
+    return y * (1.5f - 0.5f * x * y * y);
+}
+
+// ------------------------------------------------------------------------------------------
 // QuadControl.attitude_control (QuadControl.py:93-127) on matrices.  Rt = target rotation
 // (columns t0 t1 t2, row-major like R), ta = target acceleration incl. gravity.
-__device__ __forceinline__ void attitude_control(const MrsQuadParams& q, const float* R, const float* Rt,
-                                                 const float* ta, const Agent& s, float* io, float* rpm) {
+__device__ __forceinline__ void attitude_control(const MrsQuadParams& q, const Derived& d, const float* R, const float* Rt,
+                                                 const float* ta, float nrm, float inv_nrm, const Agent& s, float* io,
+                                                 float* rpm) {
     // rot_matrix_e = Rt^T R - R^T Rt ; rot_e = [e21, e02, e10]
     float re[3];
     re[0] = (Rt[2] * R[1] + Rt[5] * R[4] + Rt[8] * R[7]) - (R[2] * Rt[1] + R[5] * Rt[4] + R[8] * Rt[7]);
@@ -77,13 +123,10 @@ __device__ __forceinline__ void attitude_control(const MrsQuadParams& q, const f
         io[k] = v;
         tt[k] = clampf(-q.ori_p[k] * re[k] + q.ori_i[k] * v + q.ori_d[k] * we[k], -3200.f, 3200.f);
     }
-    const float nrm = sqrtf(ta[0] * ta[0] + ta[1] * ta[1] + ta[2] * ta[2]);
-    float scalar_thrust = 0.f;
-    if (nrm != 0.f) {
-        const float cosang = (ta[0] * R[2] + ta[1] * R[5] + ta[2] * R[8]) / nrm;
-        scalar_thrust = nrm * q.mass / fmaxf(cosang, 0.2f);
-    }
-    const float thrust = (sqrtf(scalar_thrust / (4.f * q.kf)) - q.pwm2rpm_b) / q.pwm2rpm_a;
+    // thrust: |a| m / max(cos(angle(a, body z)), 0.2); nrm = |a|, inv_nrm = 1/|a| (0 if |a| = 0)
+    const float cosang = (ta[0] * R[2] + ta[1] * R[5] + ta[2] * R[8]) * inv_nrm;
+    const float scalar_thrust = (nrm != 0.f) ? nrm * q.mass * fast_rcp(fmaxf(cosang, 0.2f)) : 0.f;
+    const float thrust = (fast_sqrt(scalar_thrust * d.inv_4kf) - q.pwm2rpm_b) * d.inv_pwm_a;
     // MixerMatrix rows (QuadControl.py:26): [.5,-.5,-1] [.5,.5,1] [-.5,.5,-1] [-.5,-.5,1]
     const float m0 = 0.5f * tt[0], m1 = 0.5f * tt[1], m2 = tt[2];
     float pwm[4] = {thrust + m0 - m1 - m2, thrust + m0 + m1 + m2, thrust - m0 + m1 - m2, thrust - m0 - m1 + m2};
@@ -93,22 +136,23 @@ __device__ __forceinline__ void attitude_control(const MrsQuadParams& q, const f
 
 // QuadControl.accel_control (QuadControl.py:73-90): target frame z = a/|a|,
 // x = R[:,1] x z, y = z x x, columns normalised (= scipy from_matrix on orthogonal columns).
-__device__ __forceinline__ void accel_control(const MrsQuadParams& q, const float* R, const float* a_in,
+__device__ __forceinline__ void accel_control(const MrsQuadParams& q, const Derived& d, const float* R, const float* a_in,
                                               const Agent& s, float* io, float* rpm) {
     const float ta[3] = {a_in[0], a_in[1], a_in[2] + q.ctrl_gravity};
     const float n2 = ta[0] * ta[0] + ta[1] * ta[1] + ta[2] * ta[2];
     float z[3] = {0.f, 0.f, 1.f};
+    float inv = 0.f;
     if (n2 > 0.f) {   // |a| == 0 -> NaN -> [0,0,1] in the reference
-        const float inv = 1.f / sqrtf(n2);
+        inv = rsqrt_nr(n2);
         z[0] = ta[0] * inv; z[1] = ta[1] * inv; z[2] = ta[2] * inv;
     }
     // x = R[:,1] x z
     float x[3] = {R[4] * z[2] - R[7] * z[1], R[7] * z[0] - R[1] * z[2], R[1] * z[1] - R[4] * z[0]};
-    const float xi = 1.f / sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const float xi = rsqrt_nr(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
     x[0] *= xi; x[1] *= xi; x[2] *= xi;
     const float y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
     const float Rt[9] = {x[0], y[0], z[0], x[1], y[1], z[1], x[2], y[2], z[2]};
-    attitude_control(q, R, Rt, ta, s, io, rpm);
+    attitude_control(q, d, R, Rt, ta, n2 * inv, inv, s, io, rpm);
 }
 
 // rotation matrix of scipy euler 'xyz' (extrinsic) = Rz(yaw) Ry(pitch) Rx(roll)
@@ -166,8 +210,8 @@ __device__ __forceinline__ void set_control(const MrsQuadParams& q, const float*
 // ------------------------------------------------------------------------------------------
 // action -> rpm for one agent (Quadcopter.set_* -> QuadControl.*).
 template <int MODE>
-__device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Agent& s, const float* R, const float* act,
-                                              Ctrl& k, float* rpm) {
+__device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Derived& d, const Agent& s, const float* R,
+                                              const float* act, Ctrl& k, float* rpm) {
     const MrsQuadParams& q = c.quad;
     if constexpr (MODE == MRS_SET_SPEEDS) {
 #pragma unroll
@@ -178,12 +222,12 @@ __device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Agent& s
         float Rt[9];
         euler_to_mat(act[0], act[1], act[2], Rt);
         const float ta[3] = {0.f, 0.f, 9.81f};   // literal in Quadcopter.py:64
-        attitude_control(q, R, Rt, ta, s, k.io, rpm);
+        attitude_control(q, d, R, Rt, ta, 9.81f, 1.f / 9.81f, s, k.io, rpm);
     } else if constexpr (MODE == MRS_SET_TARGET_ACCEL) {
-        accel_control(q, R, act, s, k.io, rpm);
+        accel_control(q, d, R, act, s, k.io, rpm);
     } else if constexpr (MODE == MRS_SET_FORCE) {
-        const float a[3] = {act[0] / q.mass, act[1] / q.mass, act[2] / q.mass};
-        accel_control(q, R, a, s, k.io, rpm);
+        const float a[3] = {act[0] * d.inv_qmass, act[1] * d.inv_qmass, act[2] * d.inv_qmass};
+        accel_control(q, d, R, a, s, k.io, rpm);
     } else if constexpr (MODE == MRS_SET_TARGET_POS) {
         // QuadControl.pos_control (QuadControl.py:35-48)
         const float p[3] = {s.px, s.py, s.pz}, v[3] = {s.vx, s.vy, s.vz};
@@ -194,7 +238,7 @@ __device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Agent& s
             k.ip[i] = k.ip[i] + e * q.ctrl_dt;
             a[i] = q.pos_p * e + q.pos_i * k.ip[i] + q.pos_d * (0.f - v[i]);
         }
-        accel_control(q, R, a, s, k.io, rpm);
+        accel_control(q, d, R, a, s, k.io, rpm);
     } else if constexpr (MODE == MRS_SET_TARGET_VEL) {
         // QuadControl.vel_control (QuadControl.py:51-70)
         const float v[3] = {s.vx, s.vy, s.vz};
@@ -206,42 +250,19 @@ __device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Agent& s
             const float le = first ? e : k.lve[i];
             const float lt = first ? act[i] : k.ltv[i];
             const float d0 = first ? 0.f : k.dve[i];
-            const float d = (((e - le) - (act[i] - lt)) / q.ctrl_dt) * 0.5f + d0 * 0.5f;
-            k.dve[i] = d;
+            const float dv = (((e - le) - (act[i] - lt)) * d.inv_ctrl_dt) * 0.5f + d0 * 0.5f;
+            k.dve[i] = dv;
             k.lve[i] = e;
             k.ltv[i] = act[i];
             k.iv[i] = k.iv[i] + e * q.ctrl_dt;
-            a[i] = q.vel_p * e + q.vel_i * k.iv[i] + q.vel_d * d;
+            a[i] = q.vel_p * e + q.vel_i * k.iv[i] + q.vel_d * dv;
         }
-        accel_control(q, R, a, s, k.io, rpm);
+        accel_control(q, d, R, a, s, k.io, rpm);
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) rpm[i] = 0.f;
     }
 }
-
-// ------------------------------------------------------------------------------------------
-// Host-derived constants (reciprocals, products) so that the per-agent code carries no uniform
-// divisions.  Not part of the C ABI: step_impl() fills it from MrsConfig for every call.
-struct Derived {
-    float inv_mass, inv_I[3];
-    float gnd_c;         // kf * gnd_eff_coeff * (prop_radius/4)^2      (ground effect numerator)
-    float dw_c;          // dw1 * (prop_radius/4)^2                      (downwash alpha numerator)
-    float rpm2rad;       // 2*pi/60
-    float q_x2;          // 0.25*dt^2: squared half rotation angle per unit |w|^2
-    float cap_w2;        // (ang_motion_threshold/dt)^2
-    float cap_k, cap_c;  // sin(pi/8) / ((pi/4)/dt), cos(pi/8): Bullet's capped angular step
-    float lim2;          // (2*agent_radius + contact_margin)^2
-    float gnd_skip_z;    // above this height the ground contact row cannot be active
-    float inv_dt, erp_dt;
-    float s_max;         // adjacency threshold on the squared distance
-    int comm_inf;
-};
-
-__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // One pair of the downwash loop (Quadcopter.py:99-115): body-z force on agent i caused by agent
 // j (rel = p_j - p_i):  -alpha * exp(-0.5 (dxy/beta)^2), alpha = dw1 (prop_radius/(4 dz))^2,

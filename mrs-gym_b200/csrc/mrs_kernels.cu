@@ -143,12 +143,12 @@ __device__ __forceinline__ void write_X(float* __restrict__ Xs, int layout, unsi
 // The group kernel walks several warp-chunks per warp.  While chunk c is being computed, the 13
 // state planes (+ the first action) of chunk c+1 are already in flight to a per-warp shared-memory
 // stage through cp.async (LDGSTS): the load latency of a chunk is hidden behind the arithmetic of
-// the previous one without holding a second register copy of the state.  Every lane only ever
-// touches its own stage column, so no warp barrier is needed around the stage.
+// the previous one without holding a second register copy of the state.  Stage layout per warp
+// (floats): 13 state planes x 32 | the mode's PID planes x 32 | 32 actions x ACTION_DIM; everything is
+// moved as 16-byte pieces (a plane's share of a chunk is 128 contiguous bytes = 8 pieces).
 #ifndef MRS_PREFETCH
 #define MRS_PREFETCH 1
 #endif
-constexpr int kStageFloats = 13 * 32 + 4 * 32;   // per warp: 13 planes x 32 lanes + 32 float4 actions
 
 __device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : 
 step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
                   const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr bool kStage = MRS_PREFETCH && GT != 0 && ModeTraits<MODE>::A == 4 && !ModeTraits<MODE>::io;   // speeds / control
+    constexpr bool kStage = MRS_PREFETCH && GT != 0;
+    constexpr int kStageFloats = mode_stage_floats<MODE>();
     float4* sh_pos = reinterpret_cast<float4*>(smem_raw);
     float4* sh_vel = sh_pos + WPB * 32;
     float* sh_stage = reinterpret_cast<float*>(sh_vel + WPB * 32);
@@ -220,37 +221,37 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
         else nx = cur_next + wtotal;
         return (cur_next >= 0 && nx < cta_hi) ? nx : -1;
     };
-    // chunk = 32 consecutive agent slots (GT != 0): a plane's share is 128 contiguous bytes = 8 pieces
-    // of 16 B; 13 planes + 32 actions = 136 pieces, 4-5 cp.async.16 per lane instead of 14 scalar loads.
-    // Piece q = lane + 32 i (plane q >> 3, sub-piece q & 7) lands at stage float offset 4 q, and its
-    // global address is piece0 + i * (4 S floats): one base pointer per chunk, constant strides.
-    const float* piece0 = b.state + (size_t)(lane >> 3) * S + (lane & 7) * 4;
-    const size_t piece_stride = 4 * (size_t)S;
+    // chunk = 32 consecutive agent slots (GT != 0).  Piece q (16 B) of the stage lives at float offset
+    // 4 q: q < 104 state (plane q >> 3, sub-piece q & 7), then 8 pieces per PID plane, then the actions
+    // (32 * ACTION_DIM contiguous floats).  Lane l moves pieces l, l + 32, ...
+    constexpr int kNC = mode_nctrl<MODE>();
+    constexpr int kA = ModeTraits<MODE>::A;
+    constexpr int kPieces = 8 * (13 + kNC) + 8 * kA;
     auto prefetch = [&](int chunk) {
         const unsigned s0 = (unsigned)chunk * 32u;
-        const float* g = piece0 + s0;
-        float* sm = stage + 4 * lane;
-        if (s0 + 32u <= S) {
-            cp_async16(sm, g);
-            cp_async16(sm + 128, g + piece_stride);
-            cp_async16(sm + 256, g + 2 * piece_stride);
-            if (lane < 8) cp_async16(sm + 384, g + 3 * piece_stride);
-            cp_async16(sm + 416, a.actions + (size_t)(s0 + lane) * 4);
-        } else {                                   // last, partial chunk (S is a multiple of 4)
-            const bool ok = s0 + (lane & 7) * 4 < S;
-            if (ok) {
-                cp_async16(sm, g);
-                cp_async16(sm + 128, g + piece_stride);
-                cp_async16(sm + 256, g + 2 * piece_stride);
-                if (lane < 8) cp_async16(sm + 384, g + 3 * piece_stride);
+        const unsigned left = min(32u, S - s0);            // agents of this chunk (multiple of N >= 8)
+#pragma unroll
+        for (int i = 0; i < (kPieces + 31) / 32; ++i) {
+            const int q = lane + 32 * i;
+            if (q < kPieces) {
+                const float* g;
+                bool ok;
+                if (q < 104 + 8 * kNC) {
+                    const int pl = q >> 3, sub = q & 7;
+                    const float* base = (pl < 13) ? b.state + (size_t)pl * S
+                                                  : b.ctrl + (size_t)mode_ctrl_plane<MODE>(pl - 13) * S;
+                    g = base + s0 + sub * 4;
+                    ok = (unsigned)(sub * 4) < left;
+                } else {
+                    const int aq = q - (104 + 8 * kNC);
+                    g = a.actions + (size_t)s0 * kA + aq * 4;
+                    ok = (unsigned)(aq * 4) < left * kA;
+                }
+                if (ok) cp_async16(stage + 4 * q, g);
             }
-            if (s0 + lane < S) cp_async16(sm + 416, a.actions + (size_t)(s0 + lane) * 4);
         }
         cp_async_commit();
     };
-    // Programmatic dependent launch: this grid may have been started while the previous kernel of
-    // the stream (normally the previous step) was still draining; everything above is index math.
-    // Let the next step's grid start launching as well, then wait for the previous grid's memory.
 #ifdef MRS_TRACE
     // debug build (tools/trace_c5.py): per-warp timeline (globaltimer ns) into bufs.scratch seen as
     // u64[warps][8], plus per-step aggregates [min start, max wait release, max end, min end]
@@ -300,9 +301,29 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
                 st.qw = stage[6 * 32 + lane];
                 st.vx = stage[7 * 32 + lane]; st.vy = stage[8 * 32 + lane]; st.vz = stage[9 * 32 + lane];
                 st.wx = stage[10 * 32 + lane]; st.wy = stage[11 * 32 + lane]; st.wz = stage[12 * 32 + lane];
-                act0 = *reinterpret_cast<const float4*>(stage + 13 * 32 + 4 * lane);
+                const float* cs = stage + 13 * 32 + lane;
+                if constexpr (ModeTraits<MODE>::io) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) k.io[i] = cs[i * 32];
+                }
+                if constexpr (ModeTraits<MODE>::ip) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) k.ip[i] = cs[(3 + i) * 32];
+                }
+                if constexpr (ModeTraits<MODE>::vel) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        k.iv[i] = cs[(3 + i) * 32]; k.lve[i] = cs[(6 + i) * 32];
+                        k.dve[i] = cs[(9 + i) * 32]; k.ltv[i] = cs[(12 + i) * 32];
+                    }
+                }
+                const float* as = stage + (13 + kNC) * 32 + kA * lane;
+                if constexpr (kA == 4) act0 = *reinterpret_cast<const float4*>(as);
+                if constexpr (kA == 3) act0 = make_float4(as[0], as[1], as[2], 0.f);
             } else {
                 dummy_agent(st);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) k.io[i] = k.ip[i] = k.iv[i] = k.lve[i] = k.dve[i] = k.ltv[i] = 0.f;
             }
             __syncwarp();           // everyone has read its column before the stage is refilled
             if (chunk_next >= 0) prefetch(chunk_next);
@@ -323,7 +344,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
             bool nan_act = false;
             if (kStage && t == 0) {
                 act[0] = act0.x; act[1] = act0.y; act[2] = act0.z; act[3] = act0.w;
-                nan_act = valid && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || isnan(act0.w));
+                nan_act = valid && kA > 0 && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || isnan(act0.w));
             } else if (valid) {
                 nan_act = load_action<MODE>(a.actions, (size_t)t * S + s, act);
             } else {
@@ -333,7 +354,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
 
             float R[9];
             quat_to_mat(st, R);
-            action_to_rpm<MODE>(c, st, R, act, k, rpm);
+            action_to_rpm<MODE>(c, d, st, R, act, k, rpm);
 
             // ---- pair pass 1: downwash + contact proximity on the pre-step positions
             __syncwarp();
@@ -512,7 +533,7 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
     if (load_action<MODE>(actions, s, act)) status |= MRS_STATUS_NAN_ACTION;
     float R[9], rpm[4];
     quat_to_mat(st, R);
-    action_to_rpm<MODE>(c, st, R, act, k, rpm);
+    action_to_rpm<MODE>(c, d, st, R, act, k, rpm);
     apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
     float* sc = b.scratch;
     sc[0 * (size_t)S + s] = st.vx; sc[1 * (size_t)S + s] = st.vy; sc[2 * (size_t)S + s] = st.vz;
@@ -788,14 +809,19 @@ static Derived make_derived(const MrsConfig& c) {
     d.erp_dt = (float)((double)p.erp2 / (double)c.dt);
     d.comm_inf = isinf(c.comm_range) && c.comm_range > 0.f;
     d.s_max = adjacency_threshold(c.comm_range);
+    d.inv_ctrl_dt = (float)(1.0 / (double)q.ctrl_dt);
+    d.inv_4kf = (float)(1.0 / (4.0 * (double)q.kf));
+    d.inv_pwm_a = (float)(1.0 / (double)q.pwm2rpm_a);
+    d.inv_qmass = (float)(1.0 / (double)q.mass);
     return d;
 }
 
 template <int MODE, int GT, int WPB>
 static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
                             bool pdl, cudaStream_t st) {
-    constexpr bool kStage = MRS_PREFETCH && GT != 0 && ModeTraits<MODE>::A == 4 && !ModeTraits<MODE>::io;
-    constexpr size_t smem = (size_t)WPB * 32 * 2 * sizeof(float4) + (kStage ? (size_t)WPB * kStageFloats * sizeof(float) : 16);
+    constexpr bool kStage = MRS_PREFETCH && GT != 0;
+    constexpr size_t smem = (size_t)WPB * 32 * 2 * sizeof(float4) +
+                            (kStage ? (size_t)WPB * mode_stage_floats<MODE>() * sizeof(float) : 16);
     static bool configured = false;
     if (!configured) {
         if (smem > 48 * 1024 &&
