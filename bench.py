@@ -59,6 +59,12 @@ WORKLOADS = {
 }
 
 
+def workload_config(w, E, world):
+    return {'workload': w['desc'], 'envs_per_gpu': E, 'agents_per_env': w['N'], 'action_type': w['mode'],
+            'k_hops': w['K'], 'comm_range': w['R'], 'state_fn': 'cat(pos,vel) D=6',
+            'parallelism': 'env-shard x%d' % world}
+
+
 # ------------------------------------------------------------------------------ synthetic inputs
 def make_inputs(w, E, T, seed):
     import numpy as np
@@ -193,7 +199,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     w = WORKLOADS[args.workload]
-    E = w['E'] if args.scaling == 'weak' else max(1, w['E'] // world)
+    E0 = args.envs or w['E']
+    E = E0 if args.scaling == 'weak' else max(1, E0 // world)
     N, K = w['N'], w['K']
     steps, warmup = args.steps, max(args.warmup, 3)
     T = max(d for d in range(1, min(steps, args.graph_steps) + 1) if steps % d == 0)
@@ -328,8 +335,7 @@ def run_gpu(args):
         'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': steps,
         'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': w['desc'], 'envs_per_gpu': E, 'agents_per_env': N, 'action_type': w['mode'],
-                   'k_hops': K, 'comm_range': w['R'], 'state_fn': 'cat(pos,vel) D=6', 'parallelism': 'env-shard x%d' % world,
+        'config': {**workload_config(w, E, world),
                    'launch': 'CUDA graph of %d single-step launches, %d replays' % (T, replays),
                    'l2': 'no flush: per-step streamed bytes (actions+X+A) are distinct every step and exceed L2 over the '
                          'region; state is re-read as the previous step left it; see l2_flushed'},
@@ -376,8 +382,8 @@ def run_reference(args):
         'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': Tc, 'warmup': 1,
         'ms_per_step': wall / Tc * 1e3, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': w['desc'], 'agents_per_env': w['N'], 'action_type': w['mode'], 'k_hops': w['K'],
-                   'comm_range': w['R'], 'state_fn': 'cat(pos,vel) D=6'},
+        'config': {**workload_config(w, args.envs or w['E'], int(os.environ.get('WORLD_SIZE', '1'))),
+                   'cpu_sample': 'bounded sample of the workload: %d processes x %d envs per step' % (procs, Ep)},
         'cpu_baseline': {'value': v, 'unit': 'agent-steps/s', 'cores': procs, 'kind': 'port',
                          'sample': '%d processes x %d envs x %d agents x %d steps (oracle/spec.py numpy port of the '
                                    'reference step + restated Bullet; PyBullet itself is not installable here)'
@@ -418,6 +424,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=50)
     ap.add_argument('--clock-seconds', type=float, default=1.0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--envs', type=int, default=0, help='override envs per GPU (size sweeps; not the BASELINE config)')
     args = ap.parse_args()
     _quiet_stdout()
     if args.impl == 'reference':

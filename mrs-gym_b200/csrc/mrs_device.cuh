@@ -41,7 +41,10 @@ template <> struct ModeTraits<MRS_SET_TARGET_ACCEL> { static constexpr int A = 3
 template <> struct ModeTraits<MRS_SET_FORCE>        { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = 6; };
 template <> struct ModeTraits<MRS_SET_TARGET_ORI>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = 6; };
 template <> struct ModeTraits<MRS_SET_CONTROL>      { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
-template <> struct ModeTraits<MRS_SET_SPEEDS>       { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
+#ifndef MRS_MINB_SPEEDS
+#define MRS_MINB_SPEEDS 7
+#endif
+template <> struct ModeTraits<MRS_SET_SPEEDS>       { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = MRS_MINB_SPEEDS; };
 template <> struct ModeTraits<MRS_NO_ACTION>        { static constexpr int A = 0; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
 
 // PID planes a mode carries through the prefetch stage, in stage order: io (planes 0-2), then ip

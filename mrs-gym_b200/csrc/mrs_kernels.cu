@@ -352,6 +352,12 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
             }
             if (nan_act) status |= MRS_STATUS_NAN_ACTION;
 
+#ifdef MRS_EXP_COPYONLY      // experiment (profiles/README.md): memory movement of a step only, no physics
+            st.px += act[0] * 1e-12f;
+            if (false) {
+#else
+            {
+#endif
             float R[9];
             quat_to_mat(st, R);
             action_to_rpm<MODE>(c, d, st, R, act, k, rpm);
@@ -401,6 +407,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
             integrate(c, d, st);
             if (!agent_finite(st)) status |= MRS_STATUS_NONFINITE;
 
+            }
             // ---- observation: newest X slice and newest A slice into their tape slots
             if (b.X_tape && c.state_layout != MRS_X_NONE && valid)
                 write_X(b.X_tape + (size_t)(a.slot_x - t) * xslot, c.state_layout, s, st);

@@ -6,8 +6,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from oracle import spec
-from oracle import bullet_model as bm
+# the oracle is imported lazily (make_spec): bench.py's GPU arm uses the input generators of this
+# module and must not pull the oracle in
 
 HOVER = 14475.809
 MODES = ['set_target_vel', 'set_target_pos', 'set_target_accel', 'set_force', 'set_target_ori', 'set_control',
@@ -74,6 +74,8 @@ def read_state(swarm):
 
 
 def make_spec(E, N, mode, K, comm_range, st, agent_radius=0.3, dt=0.01, **phys):
+    from oracle import spec
+    from oracle import bullet_model as bm
     P = bm.PhysicsParams(agent_radius=agent_radius, **phys)
     env = spec.SpecEnv(E, N, mode, K=K, comm_range=comm_range, dt=dt, phys=P)
     env.set_state(pos=st['pos'].astype(np.float64), quat=st['quat'].astype(np.float64),
