@@ -199,6 +199,18 @@ int mrs_tape_fill(const MrsConfig* cfg, const MrsBuffers* bufs, int which, int s
 int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host,
                   float* dev_actions, float* X_host, float* A_host, int slot_x, int slot_a, void* stream);
 
+/* On-device reset with the reference's DEFAULT start distribution for the envs selected by
+ * env_mask (NULL = all): positions z ~ U[z_lo, z_hi], xy ~ N(0, xy_sigma) pulled onto the disc of
+ * radius xy_radius, re-drawn until all agents of an env are >= 2*AGENT_RADIUS apart (at most
+ * max_rounds rounds; envs that did not converge are counted in *failed_envs, device u32, may be
+ * NULL); yaw ~ U[yaw_lo, yaw_hi], roll = pitch = 0; velocities zero.  Counter-based RNG: the result
+ * depends on (seed, env index) only.  N <= 32.
+ * Replaces MRS.generate_start_pos / generate_start_ori / default_spawn_dist + the set_state of
+ * MRS.reset (MRS.py:69-78,127-161,174-184) without the host round trip. */
+int mrs_spawn(const MrsConfig* cfg, const MrsBuffers* bufs, const unsigned char* env_mask,
+              unsigned long long seed, float z_lo, float z_hi, float xy_radius, float xy_sigma, float yaw_lo,
+              float yaw_hi, int max_rounds, unsigned int* failed_envs, void* stream);
+
 /* T steps over HOST buffers with the copies pipelined against the kernels (H2D of step t+1 and
  * D2H of step t-1 overlap the kernel of step t on two internal copy streams).  actions_host
  * float[T][E][N][ACTION_DIM] (pinned), dev_actions: caller-owned device staging, TWO action

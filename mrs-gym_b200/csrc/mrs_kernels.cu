@@ -734,6 +734,78 @@ set_state_kernel(float* __restrict__ st, size_t S, int N, const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------ spawn
+// On-device MRS.generate_start_pos / generate_start_ori + reset (MRS.py:127-161,174-184) for the
+// default spawn distribution (MRS.default_spawn_dist, MRS.py:69-78): z ~ U[z_lo, z_hi], xy ~ N(0,
+// sigma) pulled onto the disc of radius xy_radius when outside it (Util.SphereTransform within=True),
+// agents closer than 2*AGENT_RADIUS to another agent of their env are re-drawn until none collides
+// (the higher-indexed agent of a colliding pair is re-drawn, so at least one of them stays).
+// One warp per env (N <= 32), counter-based RNG (splitmix64 of seed / env / agent / draw), so a reset
+// is reproducible from (seed, env) alone and independent of the launch shape.
+struct SpawnArgs {
+    unsigned long long seed;
+    float z_lo, z_hi, xy_radius, xy_sigma;
+    float yaw_lo, yaw_hi;
+    int max_rounds;
+};
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ float u01(unsigned long long h) { return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f); }
+
+__global__ void __launch_bounds__(128)
+spawn_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const SpawnArgs sp,
+             const unsigned char* __restrict__ mask, unsigned* __restrict__ failed) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= c.E) return;
+    if (mask && !mask[e]) return;
+    const int N = c.N;
+    const unsigned S = (unsigned)c.E * (unsigned)N;
+    const bool valid = lane < N;
+    const float lim2 = 4.f * c.phys.agent_radius * c.phys.agent_radius;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool redraw = true;
+    int round = 0;
+    for (; round < sp.max_rounds; ++round) {
+        if (redraw && valid) {
+            const unsigned long long key = splitmix64(sp.seed ^ splitmix64(((unsigned long long)e << 20) ^ ((unsigned long long)lane << 12) ^ (unsigned long long)round));
+            const float u1 = u01(key), u2 = u01(splitmix64(key)), u3 = u01(splitmix64(key ^ 0x5851F42D4C957F2Dull));
+            const float r = sp.xy_sigma * sqrtf(-2.f * logf(u1));          // Box-Muller
+            float sn, cs;
+            sincosf(6.28318530717958647692f * u2, &sn, &cs);
+            x = r * cs; y = r * sn;
+            const float mag = fmaxf(sqrtf(x * x + y * y), sp.xy_radius);     // SphereTransform(within=True)
+            x = x / mag * sp.xy_radius; y = y / mag * sp.xy_radius;
+            z = sp.z_lo + (sp.z_hi - sp.z_lo) * u3;
+        }
+        bool hit = false;
+        for (int j = 0; j < N; ++j) {
+            const float xj = __shfl_sync(kFull, x, j), yj = __shfl_sync(kFull, y, j), zj = __shfl_sync(kFull, z, j);
+            const float dx = x - xj, dy = y - yj, dz = z - zj;
+            hit = hit || (valid && j < lane && dx * dx + dy * dy + dz * dz < lim2);
+        }
+        redraw = hit;
+        if (!__any_sync(kFull, hit)) break;
+    }
+    if (round >= sp.max_rounds && lane == 0 && failed) atomicAdd(failed, 1u);
+    if (!valid) return;
+    const unsigned s = (unsigned)e * (unsigned)N + (unsigned)lane;
+    float* st = b.state;
+    st[0 * (size_t)S + s] = x; st[1 * (size_t)S + s] = y; st[2 * (size_t)S + s] = z;
+    const unsigned long long ky = splitmix64(sp.seed ^ splitmix64(0xA5A5A5A5ull ^ ((unsigned long long)e << 20) ^ ((unsigned long long)lane << 12)));
+    const float yaw = sp.yaw_lo + (sp.yaw_hi - sp.yaw_lo) * u01(ky);
+    float sy, cy;
+    sincosf(0.5f * yaw, &sy, &cy);
+    st[3 * (size_t)S + s] = 0.f; st[4 * (size_t)S + s] = 0.f; st[5 * (size_t)S + s] = sy; st[6 * (size_t)S + s] = cy;
+#pragma unroll
+    for (int p = 7; p < 13; ++p) st[p * (size_t)S + s] = 0.f;
+}
+
 // tape maintenance: 128-bit grid-stride copy / zero fill (slot sizes are multiples of 4 floats
 // whenever E*N is; scalar tail otherwise)
 __global__ void __launch_bounds__(256)
@@ -1263,6 +1335,22 @@ int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
     if (cudaEventRecord(L->tail, L->d2h) != cudaSuccess) return MRS_ERR_CUDA;
     if (cudaStreamWaitEvent(st, L->tail, 0) != cudaSuccess) return MRS_ERR_CUDA;
     return cudaStreamSynchronize(st) == cudaSuccess ? MRS_OK : MRS_ERR_CUDA;
+}
+
+
+int mrs_spawn(const MrsConfig* cfg, const MrsBuffers* bufs, const unsigned char* env_mask, unsigned long long seed,
+              float z_lo, float z_hi, float xy_radius, float xy_sigma, float yaw_lo, float yaw_hi, int max_rounds,
+              unsigned int* failed_envs, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs || !bufs->state) return MRS_ERR_ARG;
+    if (cfg->N > 32) return MRS_ERR_UNSUPPORTED;
+    if (!(z_hi >= z_lo) || !(xy_radius > 0.f) || !(xy_sigma > 0.f) || max_rounds <= 0) return MRS_ERR_ARG;
+    SpawnArgs sp;
+    sp.seed = seed; sp.z_lo = z_lo; sp.z_hi = z_hi; sp.xy_radius = xy_radius; sp.xy_sigma = xy_sigma;
+    sp.yaw_lo = yaw_lo; sp.yaw_hi = yaw_hi; sp.max_rounds = max_rounds;
+    spawn_kernel<<<(unsigned)((cfg->E + 3) / 4), 128, 0, (cudaStream_t)stream>>>(*cfg, *bufs, sp, env_mask, failed_envs);
+    return last_error();
 }
 
 }  // extern "C"

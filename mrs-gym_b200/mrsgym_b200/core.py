@@ -271,6 +271,19 @@ class Swarm:
                                           _ptr(angvel), _ptr(env_mask), self._stream()), 'mrs_set_state')
         self.launches += 1
 
+    def spawn(self, seed, env_mask=None, z=(1.0, 3.0), xy_radius=1.0, xy_sigma=1.0, yaw=(-math.pi / 2, math.pi / 2),
+              max_rounds=256):
+        """On-device reset with the reference's default start distribution (mrs_spawn).  Returns the
+        device counter of envs whose rejection sampling did not converge (read it lazily)."""
+        if env_mask is not None:
+            env_mask = torch.as_tensor(env_mask).to(self.device).to(torch.uint8).reshape(self.E).contiguous()
+        failed = torch.zeros(1, device=self.device, dtype=torch.int32)
+        _abi.check(self.lib.mrs_spawn(C.byref(self.cfg), C.byref(self.bufs), _ptr(env_mask), C.c_ulonglong(int(seed)),
+                                      float(z[0]), float(z[1]), float(xy_radius), float(xy_sigma), float(yaw[0]),
+                                      float(yaw[1]), int(max_rounds), _ptr(failed), self._stream()), 'mrs_spawn')
+        self.launches += 1
+        return failed
+
     def set_quat(self, quat):
         """Exact quaternion upload (xyzw), bypassing the euler conversion (tests / checkpoints)."""
         q = torch.as_tensor(quat, dtype=torch.float32).to(self.device).reshape(self.S, 4)

@@ -145,6 +145,7 @@ class MRS:
         self.CHECK_NAN = 'auto'
         self.COPY_OBS = None
         self.BATCHED = None          # None: batched shapes iff N_ENVS > 1
+        self.SEED = 0                # seed of the on-device start-state sampler
         self.set_constants(kwargs)
         if env != 'simple':
             raise NotImplementedError("only the 'simple' world (N x cf2x + ground plane, EnvCreator.py:7-13) is in scope")
@@ -173,7 +174,10 @@ class MRS:
             custom_D = self.STATE_SIZE
         self._layout = layout
         self.swarm = None
+        self._spawn_count = 0
+        self.spawn_failed = None
         self._build(layout, custom_D)
+        self.env_steps = torch.zeros(self.N_ENVS, dtype=torch.int64, device=self.swarm.device)
         self.steps_since_reset = 0
         self.last_action = None
         self.last_obs = None
@@ -273,6 +277,7 @@ class MRS:
     def _after_state_change(self):
         """Tail of MRS.reset / MRS.set (MRS.py:185-192): clear rings, steps := 0, start_fn, X0."""
         self.steps_since_reset = 0
+        self.env_steps.zero_()
         if self.start_fn is not None:
             self.start_fn(self)
         self.swarm.reset_windows()
@@ -283,23 +288,73 @@ class MRS:
         self.last_obs = Xk
         return Xk
 
+    def _device_spawn_ok(self):
+        """The default START_POS / START_ORI (MRS.py:53-54) can be sampled on the device."""
+        if not isinstance(self.START_POS, _spawn.DefaultSpawn) or self.N_AGENTS > 32:
+            return False
+        ori = torch.as_tensor(self.START_ORI, dtype=torch.float32)
+        if ori.dim() != 2 or ori.shape[-1] != 6:
+            return False
+        same = bool((ori == ori[0]).all())
+        return same and bool((ori[0, [0, 1, 3, 4]] == 0).all())
+
+    def _after_masked_state_change(self, env_mask):
+        """Per-env reset in a batch: only the selected envs get their rings re-initialised (X history
+        := copies of X0, A history := zeros); the other envs keep theirs.  The reference has one env
+        per process, so this is the batched reading of MRS.reset's tail (MRS.py:185-192)."""
+        sw = self.swarm
+        m = torch.as_tensor(env_mask).to(sw.device).bool().reshape(sw.E)
+        self.env_steps[m] = 0
+        if self.start_fn is not None:
+            self.start_fn(self)
+        if sw.X_tape is not None:
+            if self._layout == _abi.X_NONE:
+                X0 = self._call_state_fn(sw)
+            elif self._layout == _abi.X_POS_VEL:
+                X0 = torch.cat([sw.get_pos(), sw.get_vel()], dim=-1)
+            else:
+                X0 = torch.cat([sw.get_pos(), sw.get_quat(), sw.get_vel(), sw.get_angvel()], dim=-1)
+            w = sw.X_tape[sw.hx:sw.hx + sw.K + 1]
+            w[:, m] = X0[m].unsqueeze(0).to(w.dtype)
+        if sw.A_tape is not None:
+            sw.A_tape[sw.ha:sw.ha + sw.K + 1][:, m] = 0
+        Xk = self.get_Xk()
+        self.last_obs = Xk
+        return Xk
+
     def reset(self, pos=None, ori=None, vel=None, angvel=None, env_mask=None):
-        """MRS.reset (MRS.py:174-192).  PID integrators are NOT reset (reference behaviour)."""
+        """MRS.reset (MRS.py:174-192).  PID integrators are NOT reset (reference behaviour).
+        env_mask ([E] bool) resets only the selected envs of the batch and keeps the rings of the rest.
+        With the default START_POS / START_ORI the start state is sampled on the device (mrs_spawn)."""
         self.is_initialised = True
-        if pos is None:
-            pos = self.generate_start_pos()
-        if ori is None:
-            ori = self.generate_start_ori()
-        if vel is None:
-            vel = torch.zeros(self.N_AGENTS, 3)
-        if angvel is None:
-            angvel = torch.zeros(self.N_AGENTS, 3)
-        self.swarm.set_state(pos=pos, ori=ori, vel=vel, angvel=angvel, env_mask=env_mask)
+        if pos is None and ori is None and self._device_spawn_ok():
+            ori6 = torch.as_tensor(self.START_ORI, dtype=torch.float32)[0]
+            sp = self.START_POS
+            self._spawn_count += 1
+            self.spawn_failed = self.swarm.spawn(self.SEED * 1000003 + self._spawn_count, env_mask=env_mask,
+                                                 z=(sp.z_low, sp.z_high), xy_radius=sp.xy_radius, xy_sigma=sp.xy_radius,
+                                                 yaw=(float(ori6[2]), float(ori6[5])))
+            if vel is not None or angvel is not None:
+                self.swarm.set_state(vel=vel, angvel=angvel, env_mask=env_mask)
+        else:
+            if pos is None:
+                pos = self.generate_start_pos()
+            if ori is None:
+                ori = self.generate_start_ori()
+            if vel is None:
+                vel = torch.zeros(self.N_AGENTS, 3)
+            if angvel is None:
+                angvel = torch.zeros(self.N_AGENTS, 3)
+            self.swarm.set_state(pos=pos, ori=ori, vel=vel, angvel=angvel, env_mask=env_mask)
+        if env_mask is not None:
+            return self._after_masked_state_change(env_mask)
         return self._after_state_change()
 
     def set(self, pos=None, ori=None, vel=None, angvel=None, env_mask=None):
         """MRS.set (MRS.py:196-205): like reset, but None keeps the current value."""
         self.swarm.set_state(pos=pos, ori=ori, vel=vel, angvel=angvel, env_mask=env_mask)
+        if env_mask is not None:
+            return self._after_masked_state_change(env_mask)
         return self._after_state_change()
 
     # ------------------------------------------------------------------ step
@@ -345,6 +400,7 @@ class MRS:
         done = self.done_fn(X=Xk, Xlast=self.last_obs, **kw)
         self.last_loop_time = time.monotonic()
         self.steps_since_reset += 1
+        self.env_steps += 1
         return Xk, reward, done, info
 
     def step_many(self, actions, ACTION_TYPE=None):
@@ -362,6 +418,7 @@ class MRS:
         actions = actions.reshape(T, self.N_ENVS, self.N_AGENTS, adim).contiguous()
         self.swarm.step_many(actions, T)
         self.steps_since_reset += T
+        self.env_steps += T
         Xk = self.get_Xk()
         self.last_obs = Xk
         return Xk, self.get_Ak()

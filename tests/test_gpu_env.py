@@ -121,3 +121,62 @@ def test_default_reset_spawns_collision_free():
     assert float(yaw.abs().max()) <= np.pi / 2 + 1e-5
     X = env.reset()
     assert tuple(X.shape) == (8, 1, 6, 6)
+
+
+def test_device_spawn_distribution_and_determinism():
+    """mrs_spawn: the reference's default start distribution (MRS.py:69-78,127-161) sampled on the
+    device -- separation >= 2*AGENT_RADIUS, xy inside the unit disc, z ~ U[1,3], yaw ~ U[-pi/2, pi/2],
+    zero velocities; reproducible from the seed; masked resets touch only the selected envs."""
+    import mrsgym_b200 as mrsgym
+    E, N = 4096, 8
+    sw = mrsgym.Swarm(E, N, 0, 'set_speeds')
+    failed = sw.spawn(seed=123)
+    p = sw.get_pos()
+    assert int(failed.item()) == 0
+    d = (p.unsqueeze(2) - p.unsqueeze(1)).norm(dim=-1) + 10 * torch.eye(N, device=p.device)
+    assert float(d.min()) >= 0.6 - 1e-6
+    assert float(p[..., :2].norm(dim=-1).max()) <= 1.0 + 1e-5
+    z = p[..., 2].flatten()
+    assert 1.0 <= float(z.min()) and float(z.max()) <= 3.0
+    # uniformity of z and yaw (KS distance against the uniform CDF; 32768 samples => 0.01 is > 5 sigma)
+    for v, lo, hi in ((z, 1.0, 3.0), (sw.get_ori()[..., 2].flatten(), -np.pi / 2, np.pi / 2)):
+        u = ((v - lo) / (hi - lo)).sort().values.cpu().double()
+        n = u.numel()
+        ks = (u - (torch.arange(n, dtype=torch.float64) + 0.5) / n).abs().max()
+        assert float(ks) < 0.015
+    assert float(sw.get_vel().abs().max()) == 0.0 and float(sw.get_angvel().abs().max()) == 0.0
+    assert float((sw.get_quat().norm(dim=-1) - 1).abs().max()) < 1e-6
+    # against the host sampler of the reference's distribution: same marginal radius statistics
+    host = mrsgym.sample_start_pos(mrsgym.DefaultSpawn(N), 2048, N, 0.3)
+    assert abs(float(host[..., :2].norm(dim=-1).mean()) - float(p[..., :2].norm(dim=-1).mean())) < 0.02
+    # determinism and masking
+    ref = sw.state.clone()
+    sw.spawn(seed=123)
+    assert torch.equal(sw.state, ref)
+    mask = torch.zeros(E, dtype=torch.bool)
+    mask[::3] = True
+    sw.spawn(seed=999, env_mask=mask)
+    new = sw.state.reshape(13, E, N)
+    old = ref.reshape(13, E, N)
+    assert torch.equal(new[:, ~mask.cuda()], old[:, ~mask.cuda()])
+    assert not torch.equal(new[0, mask.cuda()], old[0, mask.cuda()])
+
+
+def test_masked_reset_keeps_other_envs_history():
+    import mrsgym_b200 as mrsgym
+    E, N, K = 6, 4, 2
+    env = mrsgym.MRS(N_ENVS=E, N_AGENTS=N, K_HOPS=K, COMM_RANGE=3.0, ACTION_TYPE='set_target_vel', SEED=5)
+    for _ in range(4):
+        X, r, d, info = env.step(torch.zeros(E, N, 3))
+    Xb, Ab = env.get_Xk().clone(), env.get_Ak().clone()
+    mask = torch.tensor([True, False, False, True, False, False])
+    X = env.reset(env_mask=mask)
+    keep = ~mask.cuda()
+    assert torch.equal(X[keep], Xb[keep]) and torch.equal(env.get_Ak()[keep], Ab[keep])
+    # the reset envs: X history = copies of the new X0, A history = zeros, step counter back to 0
+    assert torch.equal(X[mask.cuda()][:, 0], X[mask.cuda()][:, K])
+    assert float(env.get_Ak()[mask.cuda()].abs().sum()) == 0.0
+    assert env.env_steps.tolist() == [0, 4, 4, 0, 4, 4]
+    assert not torch.equal(X[mask.cuda()][:, 0], Xb[mask.cuda()][:, 0])
+    env.step(torch.zeros(E, N, 3))
+    env.check_status()
