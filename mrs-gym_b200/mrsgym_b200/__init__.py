@@ -12,6 +12,7 @@ from ._abi import MrsError
 from .core import Swarm, shard_range
 from .env import MRS, Environment, AgentBatch
 from .spawn import DefaultSpawn, sample_start_pos
+from .rollout import rollout, reynolds_policy
 
 _REGISTRY = {'mrs-v0': MRS}
 

@@ -249,6 +249,23 @@ class MRS:
         self.swarm.push_A()
         return self.get_Ak()
 
+    def refresh_A(self, env_mask=None):
+        """After a reset the reference's callers push A0 with calc_Ak() (DataGenerator.py:23).  Batched
+        form: env_mask=None pushes for every env; with a mask only the NEWEST slice of the selected
+        envs is replaced by the adjacency of their current positions (the others keep their ring)."""
+        if env_mask is None:
+            return self.calc_Ak()
+        self._sync_cfg()
+        sw = self.swarm
+        m = torch.as_tensor(env_mask).to(sw.device).bool().reshape(sw.E)
+        A0 = sw.adjacency(sw.get_pos())
+        sw.A_tape[sw.ha][m] = A0[m]
+        return self.get_Ak()
+
+    def a_ring_empty(self):
+        """True right after a full reset / set: no A slice has been pushed yet (MRS.py:186)."""
+        return self.swarm.ha + self.swarm.K + 1 > self.swarm.L
+
     def calc_A(self):
         self._sync_cfg()
         A = self.swarm.adjacency(self.swarm.get_pos())

@@ -180,3 +180,37 @@ def test_masked_reset_keeps_other_envs_history():
     assert not torch.equal(X[mask.cuda()][:, 0], Xb[mask.cuda()][:, 0])
     env.step(torch.zeros(E, N, 3))
     env.check_status()
+
+
+def test_on_device_rollout_with_reynolds_policy():
+    """rollout(): closed loop policy -> step on the device with per-env auto-reset and a dataset of
+    device tensors (the generate_mrs loop of examples/simulating_data/helper/DataGenerator.py:8-48)."""
+    import mrsgym_b200 as mrsgym
+    E, N, K, T = 64, 8, 1, 30
+    env = mrsgym.MRS(N_ENVS=E, N_AGENTS=N, K_HOPS=K, COMM_RANGE=2.5, ACTION_TYPE='set_target_vel', SEED=11,
+                     reward_fn=lambda **kw: -kw['X'][:, 0, :, 3:6].norm(dim=-1).mean(dim=-1),
+                     done_fn=lambda **kw: kw['X'][:, 0, :, 2].min(dim=-1).values < 0.6)
+    pol = mrsgym.reynolds_policy()
+    data = mrsgym.rollout(env, pol, T, episode_length=12)
+    assert tuple(data['X'].shape) == (T, E, N, 6) and tuple(data['A'].shape) == (T, E, N, N)
+    assert tuple(data['action'].shape) == (T, E, N, 3) and tuple(data['reward'].shape) == (T, E)
+    assert data['done'].dtype == torch.bool and all(v.is_cuda for v in data.values())
+    # episode_length 12 => every env is reset at steps 11 and 23 (0-based), and starts again from a
+    # collision-free draw with zero velocity
+    assert bool(data['done'][11].all()) and bool(data['done'][23].all())
+    assert float(data['X'][12][..., 3:6].abs().max()) == 0.0
+    p = data['X'][12][..., :3]
+    d = (p.unsqueeze(2) - p.unsqueeze(1)).norm(dim=-1) + 10 * torch.eye(N, device=p.device)
+    assert float(d.min()) >= 0.6 - 1e-6
+    # the recorded A is the adjacency of the recorded X
+    from oracle import spec
+    np.testing.assert_array_equal(data['A'][5].cpu().numpy(), spec.adjacency(data['X'][5][..., :3].cpu().numpy(), 2.5))
+    # flocking: commanded speeds are bounded, the swarm stays finite
+    assert float(data['action'].norm(dim=-1).max()) <= 1.0 + 1e-5 and bool(torch.isfinite(data['X']).all())
+    env.check_status()
+    # reproducible from the seed
+    env2 = mrsgym.MRS(N_ENVS=E, N_AGENTS=N, K_HOPS=K, COMM_RANGE=2.5, ACTION_TYPE='set_target_vel', SEED=11,
+                      reward_fn=lambda **kw: -kw['X'][:, 0, :, 3:6].norm(dim=-1).mean(dim=-1),
+                      done_fn=lambda **kw: kw['X'][:, 0, :, 2].min(dim=-1).values < 0.6)
+    data2 = mrsgym.rollout(env2, pol, T, episode_length=12)
+    assert torch.equal(data['X'], data2['X']) and torch.equal(data['action'], data2['action'])
