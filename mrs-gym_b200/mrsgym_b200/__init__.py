@@ -13,14 +13,17 @@ from .core import Swarm, shard_range
 from .env import MRS, Environment, AgentBatch
 from .spawn import DefaultSpawn, sample_start_pos
 from .rollout import rollout, reynolds_policy
+from .wrappers import MRS_RLlib, MRS_RLlib_MultiAgent
 
-_REGISTRY = {'mrs-v0': MRS}
+_REGISTRY = {'mrs-v0': MRS, 'mrs-rllib-v0': MRS_RLlib, 'mrs-rllib-multiagent-v0': MRS_RLlib_MultiAgent}
 
 
 def make(env_id, **kwargs):
     """gym.make stand-in: make('mrs-v0', **kwargs) -> MRS(**kwargs)."""
     if env_id not in _REGISTRY:
         raise KeyError('unknown environment id %r (known: %s)' % (env_id, ', '.join(_REGISTRY)))
+    if env_id != 'mrs-v0':
+        return _REGISTRY[env_id](kwargs.get('config', kwargs))
     return _REGISTRY[env_id](**kwargs)
 
 
@@ -29,6 +32,8 @@ def _register():
         try:
             mod = __import__(modname + '.envs.registration', fromlist=['register'])
             mod.register(id='mrs-v0', entry_point='mrsgym_b200:MRS')
+            mod.register(id='mrs-rllib-v0', entry_point='mrsgym_b200:MRS_RLlib')
+            mod.register(id='mrs-rllib-multiagent-v0', entry_point='mrsgym_b200:MRS_RLlib_MultiAgent')
         except Exception:
             pass
 

@@ -214,3 +214,25 @@ def test_on_device_rollout_with_reynolds_policy():
                       done_fn=lambda **kw: kw['X'][:, 0, :, 2].min(dim=-1).values < 0.6)
     data2 = mrsgym.rollout(env2, pol, T, episode_length=12)
     assert torch.equal(data['X'], data2['X']) and torch.equal(data['action'], data2['action'])
+
+
+def test_rllib_style_wrappers():
+    """flat-numpy and dict-per-agent adapters (reference MRSWrapper.py:11-55), no ray needed"""
+    import mrsgym_b200 as mrsgym
+    pos = torch.tensor(H.grid_positions(1, 3)[0], dtype=torch.float32)
+    cfg = dict(N_AGENTS=3, K_HOPS=1, ACTION_TYPE='set_target_vel', START_POS=pos, START_ORI=torch.zeros(3, 3),
+               action_fn=lambda a: np.asarray(a) * 0.5)
+    flat = mrsgym.make('mrs-rllib-v0', config=cfg)
+    obs = flat.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (2 * 3 * 6,)
+    obs, r, d, info = flat.step(np.ones((3, 3), np.float32))
+    assert obs.shape == (36,) and 'A' in info
+    multi = mrsgym.make('mrs-rllib-multiagent-v0', config=cfg)
+    o = multi.reset()
+    assert set(o) == {'agent1', 'agent2', 'agent3'} and o['agent2'].shape == (6,)
+    o, r, d, info = multi.step({'agent1': [1.0, 0, 0], 'agent3': [0, 1.0, 0]})
+    assert set(o) == {'agent1', 'agent2', 'agent3'}
+    # both wrappers drive the same dynamics: agent 1 was commanded +x
+    for _ in range(20):
+        o, r, d, info = multi.step({'agent1': [1.0, 0, 0]})
+    assert o['agent1'][3] > 0.05 and abs(o['agent2'][3]) < 0.02
