@@ -516,14 +516,27 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
     bool near = false;
     const bool pair_contact = c.phys.agent_contact && N > 1;
     if (MODE != MRS_NO_ACTION || pair_contact) {
+        // Uniform trip count for the whole warp (the vote below needs every lane).  The SFU part of the
+        // downwash is skipped for a whole warp when none of its 32 pairs can contribute: partner not
+        // above (rz <= 0), dxy >= 10, or exp(-0.5 (dxy/beta)^2) underflowing float32 (0.5 q^2 > 104).
+        // Consecutive partners share a height layer in a lattice-like swarm, so the vote is mostly uniform.
 #pragma unroll 4
-        for (int j = l; j < N; j += LPA) {
-            const float rx = px[j] - pix, ry = py[j] - piy, rz = pz[j] - piz;
-            if (j != ai) {
-                const float dxy2 = rx * rx + ry * ry;
-                if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, d, dxy2, rz);
-                near = near || (dxy2 + rz * rz < d.lim2);
+        for (int j0 = 0; j0 < N; j0 += LPA) {
+            const int j = j0 + l;
+            const bool in = j < N;
+            const int jj = in ? j : ai;
+            const float rx = px[jj] - pix, ry = py[jj] - piy, rz = pz[jj] - piz;
+            const float dxy2 = rx * rx + ry * ry;
+            const bool other = in && j != ai;
+            if (MODE != MRS_NO_ACTION) {
+                const float beta = c.quad.dw2 * rz + c.quad.dw3;
+                const bool live = other && rz > 0.f && dxy2 < 100.f && !(dxy2 > 208.f * beta * beta);
+                if (__any_sync(kFull, live)) {
+                    const float f = downwash_pair(c.quad, d, dxy2, rz);
+                    dw += live ? f : 0.f;
+                }
             }
+            near = near || (other && dxy2 + rz * rz < d.lim2);
         }
     }
     dw = group_sum<LPA>(dw);
@@ -960,20 +973,54 @@ static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, in
     return last_error();
 }
 
+// Side stream of the wide path: the adjacency kernel of step t (a pure streaming store that only
+// reads the new positions) runs next to the compute-bound pair kernel of step t+1; it has to be done
+// before post(t+1) overwrites the positions.  Fork / join through events, so it is capturable.
+namespace {
+struct SideLane {
+    cudaStream_t s = nullptr;
+    cudaEvent_t posted = nullptr, adj_done = nullptr;
+    bool ok = false;
+};
+SideLane g_side[64];
+SideLane* side_lane() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideLane& L = g_side[dev];
+    if (!L.ok) {
+        if (cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&L.posted, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&L.adj_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        L.ok = true;
+    }
+    return &L;
+}
+}  // namespace
+
 template <int MODE, int LPA>
 static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     const size_t S = (size_t)c.E * c.N;
     constexpr int A = ModeTraits<MODE>::A;
     const unsigned blocks = (unsigned)((S * LPA + kBlock - 1) / kBlock);
+    SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
     for (int t = 0; t < a.T; ++t) {
         step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, a.actions ? a.actions + (size_t)t * S * A : nullptr);
+        if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
         step_post_kernel<LPA><<<blocks, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
         if (b.A_tape) {
+            cudaStream_t as = st;
+            if (L) {
+                if (cudaEventRecord(L->posted, st) != cudaSuccess) return MRS_ERR_CUDA;
+                if (cudaStreamWaitEvent(L->s, L->posted, 0) != cudaSuccess) return MRS_ERR_CUDA;
+                as = L->s;
+            }
             const int rc = launch_adjacency(b.state, S, 1, b.A_tape + (size_t)(a.slot_a - t) * S * c.N, c.E, c.N, d.s_max,
-                                            d.comm_inf, st);
+                                            d.comm_inf, as);
             if (rc) return rc;
+            if (L && cudaEventRecord(L->adj_done, L->s) != cudaSuccess) return MRS_ERR_CUDA;
         }
     }
+    if (L && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
     return last_error();
 }
 

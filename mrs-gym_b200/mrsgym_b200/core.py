@@ -43,6 +43,10 @@ class Swarm:
             raise _abi.MrsError('mrsgym_b200 runs on CUDA devices only (no CPU fallback); got %s' % device)
         if self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
+        if self.device.index != torch.cuda.current_device():
+            # kernels are launched on the CURRENT device with raw pointers: one process per GPU
+            raise _abi.MrsError('the swarm lives on %s but the current CUDA device is %d: call '
+                                'torch.cuda.set_device first (one process per GPU)' % (self.device, torch.cuda.current_device()))
         self.E, self.N, self.K = int(E), int(N), int(K)
         self.S = self.E * self.N
         self.cfg = _abi.default_config()
@@ -86,6 +90,8 @@ class Swarm:
         b.status, b.stats = self.status.data_ptr(), self.stats.data_ptr()
 
     def _stream(self):
+        if torch.cuda.current_device() != self.device.index:
+            raise _abi.MrsError('current CUDA device changed to %d; the swarm lives on %s' % (torch.cuda.current_device(), self.device))
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def set_action_type(self, action_type):
@@ -162,8 +168,27 @@ class Swarm:
         return self.A_tape[self.ha:self.ha + self.K + 1]          # [K+1, E, N, N]
 
     # ------------------------------------------------------------------ the step
+    def _check_actions(self, actions, T=1, host=False):
+        """The C ABI reads raw pointers: refuse anything that is not float32, contiguous, of the
+        right size and on the right device before it gets there."""
+        adim = self.action_dim
+        if adim == 0:
+            return
+        if actions is None:
+            raise ValueError('ACTION_TYPE needs actions of shape [%d, %d, %d]' % (self.E, self.N, adim))
+        if actions.dtype != torch.float32 or not actions.is_contiguous():
+            raise ValueError('actions must be a contiguous float32 tensor')
+        if actions.numel() != T * self.S * adim:
+            raise ValueError('actions has %d elements, expected %d x %d x %d x %d' % (actions.numel(), T, self.E, self.N, adim))
+        if host:
+            if actions.is_cuda or not actions.is_pinned():
+                raise ValueError('host actions must live in pinned host memory')
+        elif actions.device != self.device:
+            raise ValueError('actions live on %s, the swarm on %s' % (actions.device, self.device))
+
     def step(self, actions):
         """One env.step for all envs.  actions: device float32 [E,N,A] contiguous, or None."""
+        self._check_actions(actions)
         hx = self._make_room(1) - 1 if self.X_tape is not None else 0
         ha = self._make_room(2) - 1 if self.A_tape is not None else 0
         _abi.check(self.lib.mrs_step(C.byref(self.cfg), C.byref(self.bufs), _ptr(actions), hx, ha, self._stream()),
@@ -176,6 +201,7 @@ class Swarm:
 
     def step_many(self, actions, T: int):
         """T steps with pre-computed actions [T,E,N,A]; chunks at tape wrap-arounds."""
+        self._check_actions(actions, T)
         done = 0
         while done < T:
             hx = self._make_room(1) if self.X_tape is not None else T
@@ -221,6 +247,7 @@ class Swarm:
 
     def step_host(self, actions_host, dev_actions, X_host, A_host):
         """mrs_step_host: pinned host actions in, newest X/A slice out, synchronous."""
+        self._check_actions(actions_host, host=True)
         hx = self._make_room(1) - 1 if self.X_tape is not None else 0
         ha = self._make_room(2) - 1 if self.A_tape is not None else 0
         _abi.check(self.lib.mrs_step_host(C.byref(self.cfg), C.byref(self.bufs), _ptr(actions_host), _ptr(dev_actions),
@@ -236,6 +263,7 @@ class Swarm:
         every step copied to pinned host arrays [T,E,N,D] / [T,E,N,N]; copies overlap the kernels.
         Chunks at tape wrap-arounds."""
         T = int(actions_host.shape[0])
+        self._check_actions(actions_host, T, host=True)
         done = 0
         while done < T:
             hx = self._make_room(1) if self.X_tape is not None else T
@@ -388,7 +416,10 @@ class GraphRollout:
                                                     sw.L - sw.K + i, 1, sw._stream()), 'mrs_tape_fill')
                     sw.launches += 1
         sw.hx = sw.ha = sw.L - sw.K
-        sw.step_many_single(self.actions, self.T)
+        if sw.N > 32:
+            sw.step_many(self.actions, self.T)       # wide path: per-step kernels anyway, adjacency overlapped
+        else:
+            sw.step_many_single(self.actions, self.T)
 
     def replay(self):
         self.graph.replay()

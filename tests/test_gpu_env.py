@@ -80,6 +80,16 @@ def test_error_behaviour():
         env.check_status()
     with pytest.raises(mrsgym.MrsError):
         mrsgym.Swarm(1, 2, device='cpu')
+    # raw-pointer boundary: wrong shape / dtype / device never reaches the C ABI
+    sw = mrsgym.Swarm(4, 2, 0, 'set_speeds')
+    for bad in (torch.zeros(4, 2, 3, device='cuda'), torch.zeros(4, 2, 4, device='cuda', dtype=torch.float64),
+                torch.zeros(4, 2, 4), torch.zeros(4, 2, 8, device='cuda')[..., ::2], None):
+        with pytest.raises(ValueError):
+            sw.step(bad)
+    lib = mrsgym._abi.lib()
+    import ctypes
+    assert lib.mrs_step(ctypes.byref(sw.cfg), ctypes.byref(sw.bufs), None, 0, 0, None) == -1      # NULL actions
+    assert lib.mrs_step(ctypes.byref(sw.cfg), ctypes.byref(sw.bufs), ctypes.c_void_p(sw.state.data_ptr()), sw.L, 0, None) == -1   # slot out of range
 
 
 def test_batched_env_shapes_and_modes():
