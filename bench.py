@@ -198,6 +198,7 @@ def run_gpu(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_bound = D.bind_to_gpu_numa(physical_gpu_index(local)) if world > 1 else False
     w = WORKLOADS[args.workload]
     E0 = args.envs or w['E']
     E = E0 if args.scaling == 'weak' else max(1, E0 // world)
@@ -351,7 +352,8 @@ def run_gpu(args):
         'e2e': {'value': e2e_pipe_value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'steps': n_e, 'api': 'mrs_rollout_host (C ABI, pinned host buffers; every step: H2D actions, kernel, D2H '
                                      'newest X and A; copies of neighbouring steps overlap the kernels)',
-                'sync_per_step': {'value': e2e_value, 'api': 'mrs_step_host (same copies, stream sync after every step)'}},
+                'sync_per_step': {'value': e2e_value, 'api': 'mrs_step_host (same copies, stream sync after every step)'},
+                'numa_bound': numa_bound},
         'gpu_launches': gpu_launches,
         'clocks': sampler.summary(),
         'status_word': sw_status,

@@ -368,12 +368,13 @@ __device__ __forceinline__ bool agent_contact_pair(const MrsPhysicsParams& ph, c
 __device__ __forceinline__ bool ground_contact(const MrsPhysicsParams& ph, const Derived& d, Agent& s) {
     if (s.pz >= d.gnd_skip_z) return false;
     const float R22 = 1.f - 2.f * (s.qx * s.qx + s.qy * s.qy);
-    const float ext = ph.col_radius * sqrtf(fmaxf(1.f - R22 * R22, 0.f)) + ph.col_halfheight * fabsf(R22) + ph.col_margin;
+    // SFU sqrt / rcp: a swarm resting on the ground takes this path for every agent and step
+    const float ext = ph.col_radius * fast_sqrt(fmaxf(1.f - R22 * R22, 0.f)) + ph.col_halfheight * fabsf(R22) + ph.col_margin;
     const float dist = s.pz - ext - ph.ground_z;
     if (!(dist < ph.contact_margin)) return false;
     const float jn = contact_rhs(ph, d, dist, s.vz);
-    const float vt = sqrtf(s.vx * s.vx + s.vy * s.vy);
-    const float scale = (vt > 0.f) ? fminf(vt, ph.mu_ground * jn) / vt : 0.f;
+    const float vt2 = s.vx * s.vx + s.vy * s.vy;
+    const float scale = (vt2 > 0.f) ? fminf(1.f, ph.mu_ground * jn * fast_rsqrt(vt2)) : 0.f;
     s.vz += jn;
     s.vx -= s.vx * scale;
     s.vy -= s.vy * scale;

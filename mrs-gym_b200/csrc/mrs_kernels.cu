@@ -181,6 +181,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
     float4* sh_vel = sh_pos + WPB * 32;
     float* sh_stage = reinterpret_cast<float*>(sh_vel + WPB * 32);
     __shared__ int sh_counter;
+    __shared__ unsigned sh_events[5];       // CTA-level status word + the four statistics counters
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float4* wpos = sh_pos + wib * 32;
     float4* wvel = sh_vel + wib * 32;
@@ -206,10 +207,9 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
     const int gw = blockIdx.x * WPB + wib;
     const int cta_lo = kLocal ? (int)(((long long)blockIdx.x * a.nchunks) / gridDim.x) : 0;
     const int cta_hi = kLocal ? (int)(((long long)(blockIdx.x + 1) * a.nchunks) / gridDim.x) : a.nchunks;
-    if (kLocal) {
-        if (threadIdx.x == 0) sh_counter = 0;
-        __syncthreads();
-    }
+    if (threadIdx.x < 5) sh_events[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) sh_counter = 0;
+    __syncthreads();
     auto issue_fetch = [&]() -> int {
         int v = 0;
         if (kLocal && lane == 0) v = atomicAdd(&sh_counter, 1);
@@ -457,25 +457,36 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
 #ifdef MRS_TRACE
         stamp();
 #endif
-        // warp-aggregated status / statistics (atomics only when something happened)
+        // status / statistics: warp-reduce, then CTA-level shared-memory counters; the global atomics
+        // happen once per CTA at the end.  (A swarm resting on the ground reports a ground contact per
+        // agent per step: with one global atomic per warp-chunk that was 10 k same-address L2 atomics
+        // per launch at C5 and cost ~15 % of the step.)
         const unsigned any_status = __reduce_or_sync(kFull, status);
         const unsigned events = __reduce_or_sync(kFull, n_agent_rows | n_ground);
         if (any_status | events) {
             const unsigned sum_rows = __reduce_add_sync(kFull, n_agent_rows);
             const unsigned sum_gnd = __reduce_add_sync(kFull, n_ground);
             if (lane == 0) {
-                if (any_status && b.status) atomicOr(b.status, any_status);
-                if (b.stats) {
-                    if (sum_rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)sum_rows);
-                    if (sum_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)sum_gnd);
-                    if (any_status & MRS_STATUS_NONFINITE) atomicAdd(b.stats + MRS_STAT_NONFINITE, 1ull);
-                    if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
-                }
+                if (any_status) atomicOr(&sh_events[0], any_status);
+                if (sum_rows) atomicAdd(&sh_events[1], sum_rows);
+                if (sum_gnd) atomicAdd(&sh_events[2], sum_gnd);
+                if (any_status & MRS_STATUS_NONFINITE) atomicAdd(&sh_events[3], 1u);
+                if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(&sh_events[4], 1u);
             }
         }
         const int chunk_next2 = resolve_fetch(fetch_ticket, chunk_next);
         chunk = chunk_next;
         chunk_next = chunk_next2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sh_events[0] && b.status) atomicOr(b.status, sh_events[0]);
+        if (b.stats) {
+            if (sh_events[1]) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)sh_events[1]);
+            if (sh_events[2]) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)sh_events[2]);
+            if (sh_events[3]) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)sh_events[3]);
+            if (sh_events[4]) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, (unsigned long long)sh_events[4]);
+        }
     }
 #ifdef MRS_TRACE
     stamp_end();
@@ -618,23 +629,31 @@ step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ De
     // every lane of the warp takes part in the shuffles (groups without contact add zeros)
     acc[0] = group_sum<LPA>(acc[0]); acc[1] = group_sum<LPA>(acc[1]); acc[2] = group_sum<LPA>(acc[2]);
     rows = (unsigned)group_sum<LPA>((float)rows);
-    if (l != 0 || !valid) return;
-    st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
-    st.qx = b.state[3 * (size_t)S + s]; st.qy = b.state[4 * (size_t)S + s]; st.qz = b.state[5 * (size_t)S + s];
-    st.qw = b.state[6 * (size_t)S + s];
-    st.wx = b.state[10 * (size_t)S + s]; st.wy = b.state[11 * (size_t)S + s]; st.wz = b.state[12 * (size_t)S + s];
-    unsigned gnd = 0;
-    if (ph.ground_contact && ground_contact(ph, d, st)) ++gnd;
-    integrate(c, d, st);
-    store_agent(b.state, S, s, st);
-    if (b.X_tape && c.state_layout != MRS_X_NONE)
-        write_X(b.X_tape + (size_t)slot * S * state_dim(c.state_layout), c.state_layout, s, st);
-    const bool bad = !agent_finite(st);
-    if (bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
-    if (b.stats) {
-        if (rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)rows);
-        if (gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)gnd);
-        if (bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, 1ull);
+    const bool lead = (l == 0) && valid;
+    unsigned gnd = 0, bad = 0;
+    if (lead) {
+        st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
+        st.qx = b.state[3 * (size_t)S + s]; st.qy = b.state[4 * (size_t)S + s]; st.qz = b.state[5 * (size_t)S + s];
+        st.qw = b.state[6 * (size_t)S + s];
+        st.wx = b.state[10 * (size_t)S + s]; st.wy = b.state[11 * (size_t)S + s]; st.wz = b.state[12 * (size_t)S + s];
+        if (ph.ground_contact && ground_contact(ph, d, st)) gnd = 1;
+        integrate(c, d, st);
+        store_agent(b.state, S, s, st);
+        if (b.X_tape && c.state_layout != MRS_X_NONE)
+            write_X(b.X_tape + (size_t)slot * S * state_dim(c.state_layout), c.state_layout, s, st);
+        bad = agent_finite(st) ? 0u : 1u;
+    }
+    // statistics: one warp reduction, then at most three global atomics per warp (not per agent)
+    const unsigned w_rows = __reduce_add_sync(kFull, lead ? rows : 0u);
+    const unsigned w_gnd = __reduce_add_sync(kFull, gnd);
+    const unsigned w_bad = __reduce_add_sync(kFull, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (w_bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
+        if (b.stats) {
+            if (w_rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)w_rows);
+            if (w_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)w_gnd);
+            if (w_bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)w_bad);
+        }
     }
 }
 

@@ -41,3 +41,23 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def bind_to_gpu_numa(gpu_index: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to the GPU, so that pinned host
+    buffers are first-touched on the GPU's NUMA node (matters for the host-buffer paths when 8 ranks
+    share one box).  Best effort: returns False when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return True
+    except Exception:
+        pass
+    return False
