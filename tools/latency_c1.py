@@ -1,0 +1,24 @@
+"""Wall-clock latency of MRS.step for the README example (C1: one env, 3 agents) and small batches."""
+import os, sys, time
+import torch
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', 'mrs-gym_b200'))
+import mrsgym_b200 as mrsgym
+for E, N, mode in ((1, 3, 'set_target_vel'), (1, 32, 'set_target_pos'), (256, 32, 'set_target_pos'), (4096, 16, 'set_control')):
+    env = mrsgym.make('mrs-v0', N_ENVS=E, N_AGENTS=N, K_HOPS=3 if N == 32 else 0, COMM_RANGE=2.0, ACTION_TYPE=mode,
+                      START_POS=torch.rand(N, 3) * 4 + torch.tensor([0., 0, 2]), START_ORI=torch.zeros(N, 3))
+    adim = env.swarm.action_dim
+    a_host = torch.zeros(E, N, adim) if E > 1 else torch.zeros(N, adim)
+    if mode == 'set_control':
+        a_host[..., 0] = 9.81
+    a_dev = a_host.cuda()
+    for name, a in (('host actions', a_host), ('device actions', a_dev)):
+        for _ in range(20):
+            env.step(a)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 300
+        for _ in range(n):
+            X, r, d, info = env.step(a)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n
+        print('E=%d N=%d %s, %s: %.1f us per env.step (%.3g agent-steps/s)' % (E, N, mode, name, dt * 1e6, E * N / dt))
