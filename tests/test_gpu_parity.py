@@ -6,7 +6,7 @@ Tolerances (BASELINE.json north_star):
   * adjacency A: bit-exact given identical positions;
   * one-step state deltas: |d_gpu - d_ref| <= 1e-4 * |d_ref| + floor, the floor being the float32
     resolution of the stored quantity (the GPU state is float32, Bullet's is float64):
-    pos 5e-7 m (1 ulp at 4-8 m), vel 5e-7 m/s, angvel 1e-5 rad/s, quaternion 3e-7;
+    pos max(5e-7 m, 1 ulp of the coordinate), vel 5e-7 m/s, angvel 1e-5 rad/s, quaternion 3e-7;
   * 100-step free-flight trajectories: position <= 1e-3 m, attitude <= 1e-3 rad;
     contact trajectories (approximate by design): position <= 5e-2 m.
 """
@@ -47,7 +47,10 @@ def _check_delta(tag, s0, g1, r1):
             flip = np.sum(g1[k] * r1[k], axis=-1, keepdims=True) < 0
             dg = np.where(flip, -g1[k], g1[k]) - base
         err = np.abs(dg - dr)
-        tol = REL * np.abs(dr) + FLOOR[k]
+        floor = FLOOR[k]
+        if k == 'pos':     # one float32 ulp of the stored coordinate (5e-7 m up to 8 m, 1e-6 m up to 16 m, ...)
+            floor = np.maximum(floor, np.spacing(np.abs(g1[k]).astype(np.float32)).astype(np.float64))
+        tol = REL * np.abs(dr) + floor
         worst[k] = float(np.max(err / tol))
         assert np.all(err <= tol), '%s: %s delta off by %.3g x tolerance (max err %.3g)' % (
             tag, k, worst[k], err.max())
@@ -383,3 +386,93 @@ def test_full_size_properties_c5():
         ref.step(a1[t])
     assert np.abs(sw.get_pos()[0].cpu().numpy() - ref.pos[0]).max() < 1e-4
     assert sw.read_status() == 0
+
+
+# ------------------------------------------------------------------------------ BASELINE configs at full size
+def _subset_vs_oracle(E, N, mode, K, R, T, spacing, z0, pick, seed, ptol, vtol, step_many=True, noise=None):
+    """Envs are independent: run the GPU on the full batch and the oracle on a handful of its envs
+    with the same inputs; trajectories must agree within the free-flight / contact tolerance."""
+    rng = np.random.default_rng(seed)
+    st = H.random_state(rng, E, N, spacing=spacing, z0=z0, jitter=0.1, tilt=0.02, vel=0.05, angvel=0.05)
+    act = H.random_actions(rng, mode, T, E, N, start_pos=st['pos'])
+    if mode == 'set_control':
+        act[::5, :, :, 1:] /= 60.0                      # keep C3 in the regular mixer branch mostly
+    if noise is not None:
+        act = noise(rng, act)
+    sw = _swarm(E, N, mode, K, R)
+    H.upload_state(sw, st)
+    if step_many:
+        sw.step_many(_dev(act), T)
+    else:
+        for t in range(T):
+            sw.step(_dev(act[t]))
+    g = H.read_state(sw)
+    sub = {k: v[pick] for k, v in st.items()}
+    ref = H.make_spec(len(pick), N, mode, K, R, sub)
+    for t in range(T):
+        Xr, Ar = ref.step(act[t][pick])
+    assert np.abs(g['pos'][pick] - ref.pos).max() <= ptol
+    assert np.abs(g['vel'][pick] - ref.vel).max() <= vtol
+    X = sw.X_window()[:, pick].cpu().numpy()
+    A = sw.A_window()[:, pick].cpu().numpy()
+    for k in range(K + 1):
+        np.testing.assert_array_equal(A[k], spec.adjacency(X[k][..., :3], R))
+    assert sw.read_status() == 0
+    return sw
+
+
+def test_full_size_c2_swarm32_target_pos():
+    """BASELINE configs[1]: 256 envs x 32 agents, set_target_pos, K_HOPS=3, COMM_RANGE=2.0"""
+    _subset_vs_oracle(256, 32, 'set_target_pos', 3, 2.0, T=15, spacing=1.0, z0=3.0, pick=[0, 17, 255], seed=71,
+                      ptol=1e-4, vtol=2e-3)
+
+
+def test_full_size_c3_control_with_contact():
+    """BASELINE configs[2]: 4096 envs x 16 agents, set_control, ground + agent-agent contact"""
+    sw = _subset_vs_oracle(4096, 16, 'set_control', 0, float('inf'), T=12, spacing=0.58, z0=0.56, pick=[0, 1000, 4095],
+                           seed=72, ptol=5e-2, vtol=0.5, step_many=False)
+    stats = sw.read_stats()
+    assert stats['agent_contact_rows'] > 0 and stats['ground_contacts'] > 0
+
+
+def test_full_size_c4_single_env_4096_agents():
+    """BASELINE configs[3]: one env of 4096 agents, set_force, adjacency dominated -- one step against the
+    oracle (float64 pair arrays of 4096^2), A bit-exact on the GPU's own positions"""
+    E, N, R = 1, 4096, 2.0
+    rng = np.random.default_rng(73)
+    st = H.random_state(rng, E, N, spacing=1.0, z0=2.0, jitter=0.2, tilt=0.02, vel=0.1, angvel=0.1)
+    act = H.random_actions(rng, 'set_force', 1, E, N)
+    sw = _swarm(E, N, 'set_force', 0, R)
+    H.upload_state(sw, st)
+    sw.step(_dev(act[0]))
+    ref = H.make_spec(E, N, 'set_force', 0, R, st)
+    ref.step(act[0])
+    _check_delta('c4', st, H.read_state(sw), H.spec_state(ref))
+    X = sw.X_window()[0].cpu().numpy()
+    A = sw.A_window()[0].cpu()
+    assert int((A != H.torch_cpu_adjacency(X[..., :3], R)).sum()) == 0
+    deg = A.sum(-1)
+    assert 3 <= float(deg.mean()) <= 40            # ~ tens of neighbours at COMM_RANGE 2.0 on a 1 m lattice
+
+
+def test_full_size_c5_subset_vs_oracle():
+    """BASELINE configs[4]: 65536 envs x 8 agents, set_speeds, K_HOPS=3 -- three envs of the full batch
+    against the oracle over 40 steps (free flight)"""
+    _subset_vs_oracle(65536, 8, 'set_speeds', 3, 2.0, T=40, spacing=1.0, z0=3.0, pick=[0, 31337, 65535], seed=74,
+                      ptol=1e-4, vtol=1e-3)
+
+
+@pytest.mark.parametrize('E,N', [(1, 1), (3, 31), (2, 33), (1, 2), (257, 5)])
+def test_ragged_shapes_one_step(E, N):
+    """group widths that do not fill a warp, the first wide-path size, single agent"""
+    rng = np.random.default_rng(80 + N)
+    st = H.random_state(rng, E, N, spacing=0.9)
+    act = H.random_actions(rng, 'set_target_vel', 1, E, N)
+    sw = _swarm(E, N, 'set_target_vel', 1, 1.5)
+    H.upload_state(sw, st)
+    sw.step(_dev(act[0]))
+    ref = H.make_spec(E, N, 'set_target_vel', 1, 1.5, st)
+    ref.step(act[0])
+    _check_delta('ragged E%d N%d' % (E, N), st, H.read_state(sw), H.spec_state(ref))
+    X = sw.X_window()[0].cpu().numpy()
+    np.testing.assert_array_equal(sw.A_window()[0].cpu().numpy(), spec.adjacency(X[..., :3], 1.5))
