@@ -25,10 +25,11 @@ ANCHOR_STATE = dict(pos=[[1.0, 2.0, 3.0]], rpy=[0.1, -0.2, 0.3], vel=[[0.3, -0.1
                     angvel=[[0.5, -0.4, 0.2]])
 
 
-def rollout(mrsgym, fake, name, N, mode, T, K, comm_range, start, actions, agent_radius=0.3, dt=0.01):
+def rollout(mrsgym, fake, name, N, mode, T, K, comm_range, start, actions, agent_radius=0.3, dt=0.01, gravity=9.81,
+            none_steps=()):
     import torch
     env = ref_runner.make_env(mrsgym, fake, N, mode, K=K, comm_range=comm_range,
-                              agent_radius=agent_radius, dt=dt)
+                              agent_radius=agent_radius, dt=dt, GRAVITY=gravity)
     ref_runner.write_state64(env, fake, **start)
     X0 = env.set()          # MRS.set with no args: keeps state, clears rings (MRS.py:196-205)
     # Object.set_state round-trips the state through float32 getters / euler: re-upload exact
@@ -38,7 +39,7 @@ def rollout(mrsgym, fake, name, N, mode, T, K, comm_range, start, actions, agent
     rec = {k: [] for k in ('pos', 'quat', 'vel', 'angvel', 'rpm', 'force', 'torque', 'X', 'A')}
     for t in range(T):
         fake.RECORD = []
-        X, reward, done, info = env.step(torch.tensor(actions[t]))
+        X, reward, done, info = env.step(None if t in none_steps else torch.tensor(actions[t]))
         st = ref_runner.read_state64(env, fake)
         for k in ('pos', 'quat', 'vel', 'angvel'):
             rec[k].append(st[k])
@@ -52,7 +53,8 @@ def rollout(mrsgym, fake, name, N, mode, T, K, comm_range, start, actions, agent
     out.update(start_pos=np.asarray(start['pos'], np.float64), start_quat=np.asarray(start['quat'], np.float64),
                start_vel=np.asarray(start['vel'], np.float64), start_angvel=np.asarray(start['angvel'], np.float64),
                X0=X0.numpy(), actions=np.asarray(actions, np.float32), mode=mode, N=N, K=K, T=T,
-               comm_range=comm_range, agent_radius=agent_radius, dt=dt)
+               comm_range=comm_range, agent_radius=agent_radius, dt=dt, gravity=gravity,
+               none_steps=np.asarray(sorted(none_steps), np.int64))
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, 'ref_%s.npz' % name), **out)
     print('wrote ref_%s.npz  N=%d T=%d mode=%s' % (name, N, T, mode))
@@ -116,6 +118,17 @@ def main():
             a = hover * (1 + 0.05 * rng.normal(0, 1, (T, N, 4)))
         rollout(mrsgym, fake, 'traj_' + nm, N, mode, T, 3 if mode != 'set_target_vel' else 2, 1.5, st,
                 a.astype(np.float32))
+
+    # --- sim constants other than the defaults (BulletSim DT / GRAVITY kwargs, BulletSim.py:11-24): the
+    # controller keeps DefaultSim's 0.01 / 9.81 (QuadControl.py:10) while the integrator follows the kwargs
+    st = rand_start(rng, 6, spacing=1.1)
+    a = rng.normal(0, 0.4, (1, 6, 3)).repeat(60, 0).astype(np.float32)
+    rollout(mrsgym, fake, 'traj_vel_dt005_g371', 6, 'set_target_vel', 60, 1, 2.0, st, a, dt=0.005, gravity=3.71)
+    # --- MRS.step(None) interleaved with actions: no forces at all on those steps (MRS.py:243,252)
+    st = rand_start(rng, 5, spacing=1.0)
+    a = (hover * (1 + 0.03 * rng.normal(0, 1, (40, 5, 4)))).astype(np.float32)
+    rollout(mrsgym, fake, 'traj_speeds_none_steps', 5, 'set_speeds', 40, 2, float('inf'), st, a,
+            none_steps=(0, 7, 8, 9, 25))
 
     # --- contact: ground landing + sphere-sphere (AGENT_RADIUS 0.3), set_control free-fall-ish
     N = 4

@@ -188,7 +188,8 @@ def test_trajectory_vs_reference_golden(path):
     st = dict(pos=g['start_pos'][None], quat=g['start_quat'][None], vel=g['start_vel'][None],
               angvel=g['start_angvel'][None])
     st = {k: v.astype(np.float32) for k, v in st.items()}
-    sw = _swarm(1, N, mode, K, R, agent_radius=float(g['agent_radius']), dt=float(g['dt']))
+    sw = _swarm(1, N, mode, K, R, agent_radius=float(g['agent_radius']), dt=float(g['dt']), gravity=float(g['gravity']))
+    none_steps = set(int(t) for t in g['none_steps'])
     H.upload_state(sw, st)
     contact = 'contact' in path
     ptol, atol = (5e-2, 5e-2) if contact else (1e-3, 1e-3)
@@ -201,7 +202,12 @@ def test_trajectory_vs_reference_golden(path):
         if t == t_sing:
             assert worst_p <= ptol and worst_a <= atol, (worst_p, worst_a)
             ptol, atol = 5e-2, 5e-2
-        sw.step(_dev(g['actions'][t][None]))
+        if t in none_steps:                 # MRS.step(None): no forces on this step
+            sw.set_action_type(None)
+            sw.step(None)
+            sw.set_action_type(mode)
+        else:
+            sw.step(_dev(g['actions'][t][None]))
         s = H.read_state(sw)
         worst_p = max(worst_p, float(np.abs(s['pos'][0] - g['pos'][t]).max()))
         worst_a = max(worst_a, float(H.quat_angle(s['quat'][0], g['quat'][t]).max()))

@@ -18,12 +18,14 @@ def run_spec(g, T=None):
     N, K = int(g['N']), int(g['K'])
     T = T or int(g['T'])
     phys = bm.PhysicsParams(agent_radius=float(g['agent_radius']))
-    env = spec.SpecEnv(1, N, str(g['mode']), K=K, comm_range=float(g['comm_range']), dt=float(g['dt']), phys=phys)
+    env = spec.SpecEnv(1, N, str(g['mode']), K=K, comm_range=float(g['comm_range']), dt=float(g['dt']),
+                       gravity=float(g['gravity']), phys=phys)
+    none_steps = set(int(t) for t in g['none_steps'])
     env.set_state(pos=g['start_pos'], quat=g['start_quat'], vel=g['start_vel'], angvel=g['start_angvel'])
     X0 = env.reset_rings()
     out = dict(X0=X0[0], pos=[], quat=[], vel=[], angvel=[], rpm=[], force=[], torque=[], X=[], A=[])
     for t in range(T):
-        X, A = env.step(g['actions'][t][None])
+        X, A = env.step(None if t in none_steps else g['actions'][t][None])
         for k in ('pos', 'quat', 'vel', 'angvel'):
             out[k].append(getattr(env, k)[0].copy())
         for k in ('rpm', 'force', 'torque'):
@@ -52,4 +54,4 @@ def test_spec_matches_reference_verbatim(path):
 
 
 def test_goldens_exist():
-    assert len(FILES) >= 15
+    assert len(FILES) >= 17
