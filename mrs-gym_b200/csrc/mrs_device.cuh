@@ -274,8 +274,10 @@ __device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Derived&
 // a term that is itself <= ~0.3 of the weight; the parity floor is 5e-7 m/s per step).
 __device__ __forceinline__ float downwash_pair(const MrsQuadParams& q, const Derived& d, float dxy2, float rz) {
     const float beta = q.dw2 * rz + q.dw3;
-    const float e = -0.72134752044448170368f * dxy2 * fast_rcp(beta * beta);   // -0.5*log2(e)*(dxy/beta)^2
-    const float f = -d.dw_c * fast_rcp(rz * rz) * fast_ex2(e);
+    const float bb = beta * beta, zz = rz * rz;
+    const float rc = fast_rcp(bb * zz);            // one SFU reciprocal serves both 1/beta^2 and 1/dz^2
+    const float e = -0.72134752044448170368f * dxy2 * (zz * rc);   // -0.5*log2(e)*(dxy/beta)^2
+    const float f = -d.dw_c * (bb * rc) * fast_ex2(e);
     return (rz > 0.f && dxy2 < 100.f) ? f : 0.f;
 }
 

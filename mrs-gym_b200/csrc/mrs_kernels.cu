@@ -507,6 +507,39 @@ __device__ __forceinline__ float group_sum(float v) {
     return v;
 }
 
+// per-agent part of the wide pre pass: controller -> rotor wrench + aero (dw = downwash sum) ->
+// unconstrained velocities; stashes v*, the pre-step position and the proximity flag in scratch
+template <int MODE>
+__device__ __forceinline__ void agent_pre(const MrsConfig& c, const Derived& d, const MrsBuffers& b,
+                                          const float* __restrict__ actions, unsigned S, unsigned s, float dw, bool near) {
+    Agent st;
+    Ctrl k;
+    load_agent(b.state, S, s, st);
+    load_ctrl<MODE>(b.ctrl, S, s, k);
+    const float pix = st.px, piy = st.py, piz = st.pz;
+    float act[4];
+    unsigned status = 0;
+    if (load_action<MODE>(actions, s, act)) status |= MRS_STATUS_NAN_ACTION;
+    float R[9], rpm[4];
+    quat_to_mat(st, R);
+    action_to_rpm<MODE>(c, d, st, R, act, k, rpm);
+    apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
+    float* sc = b.scratch;
+    sc[0 * (size_t)S + s] = st.vx; sc[1 * (size_t)S + s] = st.vy; sc[2 * (size_t)S + s] = st.vz;
+    sc[3 * (size_t)S + s] = pix; sc[4 * (size_t)S + s] = piy; sc[5 * (size_t)S + s] = piz;
+    sc[6 * (size_t)S + s] = near ? 1.f : 0.f;
+    b.state[10 * (size_t)S + s] = st.wx; b.state[11 * (size_t)S + s] = st.wy; b.state[12 * (size_t)S + s] = st.wz;
+    store_ctrl<MODE>(b.ctrl, S, s, k);
+    if (b.rpm && MODE != MRS_NO_ACTION) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b.rpm[i * (size_t)S + s] = rpm[i];
+    }
+    if (status && b.status) {
+        atomicOr(b.status, status);
+        if (b.stats) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
+    }
+}
+
 template <int MODE, int LPA>
 __global__ void __launch_bounds__(kBlock)
 step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
@@ -531,55 +564,76 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
         // downwash is skipped for a whole warp when none of its 32 pairs can contribute: partner not
         // above (rz <= 0), dxy >= 10, or exp(-0.5 (dxy/beta)^2) underflowing float32 (0.5 q^2 > 104).
         // Consecutive partners share a height layer in a lattice-like swarm, so the vote is mostly uniform.
-#pragma unroll 4
-        for (int j0 = 0; j0 < N; j0 += LPA) {
-            const int j = j0 + l;
-            const bool in = j < N;
-            const int jj = in ? j : ai;
-            const float rx = px[jj] - pix, ry = py[jj] - piy, rz = pz[jj] - piz;
-            const float dxy2 = rx * rx + ry * ry;
-            const bool other = in && j != ai;
-            if (MODE != MRS_NO_ACTION) {
-                const float beta = c.quad.dw2 * rz + c.quad.dw3;
-                const bool live = other && rz > 0.f && dxy2 < 100.f && !(dxy2 > 208.f * beta * beta);
-                if (__any_sync(kFull, live)) {
-                    const float f = downwash_pair(c.quad, d, dxy2, rz);
-                    dw += live ? f : 0.f;
+        // four partners per lane and iteration: independent loads in flight, one vote per four pairs
+        for (int j0 = 0; j0 < N; j0 += 4 * LPA) {
+            float dxy2[4], rz[4];
+            bool live[4], any_live = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * LPA + l;
+                const bool in = j < N;
+                const int jj = in ? j : ai;
+                const float rx = px[jj] - pix, ry = py[jj] - piy;
+                rz[u] = pz[jj] - piz;
+                dxy2[u] = rx * rx + ry * ry;
+                const bool other = in && j != ai;
+                const float beta = c.quad.dw2 * rz[u] + c.quad.dw3;
+                live[u] = MODE != MRS_NO_ACTION && other && rz[u] > 0.f && dxy2[u] < 100.f &&
+                          !(dxy2[u] > 208.f * beta * beta);
+                any_live = any_live || live[u];
+                near = near || (other && dxy2[u] + rz[u] * rz[u] < d.lim2);
+            }
+            if (MODE != MRS_NO_ACTION && __any_sync(kFull, any_live)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float f = downwash_pair(c.quad, d, dxy2[u], rz[u]);
+                    dw += live[u] ? f : 0.f;
                 }
             }
-            near = near || (other && dxy2 + rz * rz < d.lim2);
         }
     }
-    dw = group_sum<LPA>(dw);
-    const unsigned gmask = (LPA == 32) ? kFull : (((1u << LPA) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
-    near = (__ballot_sync(kFull, near) & gmask) != 0u;
-    if (l != 0 || !valid) return;
-
-    Agent st;
-    Ctrl k;
-    load_agent(b.state, S, s, st);
-    load_ctrl<MODE>(b.ctrl, S, s, k);
-    float act[4];
-    unsigned status = 0;
-    if (load_action<MODE>(actions, s, act)) status |= MRS_STATUS_NAN_ACTION;
-    float R[9], rpm[4];
-    quat_to_mat(st, R);
-    action_to_rpm<MODE>(c, d, st, R, act, k, rpm);
-    apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
-    float* sc = b.scratch;
-    sc[0 * (size_t)S + s] = st.vx; sc[1 * (size_t)S + s] = st.vy; sc[2 * (size_t)S + s] = st.vz;
-    sc[3 * (size_t)S + s] = pix; sc[4 * (size_t)S + s] = piy; sc[5 * (size_t)S + s] = piz;
-    sc[6 * (size_t)S + s] = (near && pair_contact) ? 1.f : 0.f;
-    b.state[10 * (size_t)S + s] = st.wx; b.state[11 * (size_t)S + s] = st.wy; b.state[12 * (size_t)S + s] = st.wz;
-    store_ctrl<MODE>(b.ctrl, S, s, k);
-    if (b.rpm && MODE != MRS_NO_ACTION) {
+    if constexpr (LPA <= 32) {
+        dw = group_sum<LPA>(dw);
+        const unsigned gmask = (LPA == 32) ? kFull : (((1u << (LPA & 31)) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
+        near = (__ballot_sync(kFull, near) & gmask) != 0u;
+    } else {
+        // one CTA per agent (N >= 1024): warp sums in a fixed order through shared memory
+        __shared__ float part[kBlock / 32];
+        __shared__ int near_any;
+        if (threadIdx.x == 0) near_any = 0;
+        dw = group_sum<32>(dw);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = dw;
+        if (near) near_any = 1;
+        __syncthreads();
+        dw = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) b.rpm[i * (size_t)S + s] = rpm[i];
+        for (int w = 0; w < kBlock / 32; ++w) dw += part[w];
+        near = near_any != 0;
     }
-    if (status && b.status) {
-        atomicOr(b.status, status);
-        if (b.stats) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
+    if constexpr (LPA > 32) {
+        // N >= 1024: the per-agent part runs in its own thread-per-agent kernel (agent_pre_kernel); with
+        // one CTA per agent a single lane doing ~500 dependent instructions was the critical path
+        if (threadIdx.x == 0 && valid) {
+            b.scratch[0 * (size_t)S + s] = dw;
+            b.scratch[6 * (size_t)S + s] = (near && pair_contact) ? 1.f : 0.f;
+        }
+        return;
+    } else {
+        if (l != 0 || !valid) return;
+        agent_pre<MODE>(c, d, b, actions, S, s, dw, near && pair_contact);
     }
+}
+
+// thread-per-agent half of the wide pre pass for N >= 1024 (dw and the proximity flag come from scratch)
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+agent_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
+                 const float* __restrict__ actions) {
+    const unsigned S = (unsigned)c.E * (unsigned)c.N;
+    const unsigned s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= S) return;
+    agent_pre<MODE>(c, d, b, actions, S, s, b.scratch[0 * (size_t)S + s], b.scratch[6 * (size_t)S + s] != 0.f);
 }
 
 template <int LPA>
@@ -1016,16 +1070,19 @@ SideLane* side_lane() {
 }
 }  // namespace
 
-template <int MODE, int LPA>
+template <int MODE, int LPA, int LPB>
 static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     const size_t S = (size_t)c.E * c.N;
     constexpr int A = ModeTraits<MODE>::A;
     const unsigned blocks = (unsigned)((S * LPA + kBlock - 1) / kBlock);
+    const unsigned blocks_post = (unsigned)((S * LPB + kBlock - 1) / kBlock);
     SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
     for (int t = 0; t < a.T; ++t) {
-        step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, a.actions ? a.actions + (size_t)t * S * A : nullptr);
+        const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
+        step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
+        if (LPA > 32) agent_pre_kernel<MODE><<<(unsigned)((S + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, d, b, act_t);
         if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
-        step_post_kernel<LPA><<<blocks, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
+        step_post_kernel<LPB><<<blocks_post, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
         if (b.A_tape) {
             cudaStream_t as = st;
             if (L) {
@@ -1046,8 +1103,10 @@ static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffer
 template <int MODE>
 static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     if (!b.scratch) return MRS_ERR_ARG;
-    if ((unsigned long long)c.E * c.N * 32ull >= 0x7fffffffull * (unsigned long long)kBlock) return MRS_ERR_UNSUPPORTED;
-    return c.N <= 128 ? launch_wide_lpa<MODE, 8>(c, d, b, a, st) : launch_wide_lpa<MODE, 32>(c, d, b, a, st);
+    if ((unsigned long long)c.E * c.N * 128ull >= 0x7fffffffull * (unsigned long long)kBlock) return MRS_ERR_UNSUPPORTED;
+    if (c.N <= 128) return launch_wide_lpa<MODE, 8, 8>(c, d, b, a, st);
+    if (c.N < 1024) return launch_wide_lpa<MODE, 32, 32>(c, d, b, a, st);
+    return launch_wide_lpa<MODE, 128, 32>(c, d, b, a, st);     // a whole CTA walks the partners of one agent
 }
 
 static int pow2ceil(int n) {
