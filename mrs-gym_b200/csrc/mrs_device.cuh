@@ -274,7 +274,9 @@ __device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Derived&
 // a term that is itself <= ~0.3 of the weight; the parity floor is 5e-7 m/s per step).
 __device__ __forceinline__ float downwash_pair(const MrsQuadParams& q, const Derived& d, float dxy2, float rz) {
     const float beta = q.dw2 * rz + q.dw3;
-    const float bb = beta * beta, zz = rz * rz;
+    // beta^2 is floored at 1e-30: at beta == 0 the reference gets exp(-inf) = 0 (or NaN for dxy == 0, a
+    // bug of its own); the floor keeps both factors finite and yields the same 0
+    const float bb = fmaxf(beta * beta, 1e-30f), zz = rz * rz;
     const float rc = fast_rcp(bb * zz);            // one SFU reciprocal serves both 1/beta^2 and 1/dz^2
     const float e = -0.72134752044448170368f * dxy2 * (zz * rc);   // -0.5*log2(e)*(dxy/beta)^2
     const float f = -d.dw_c * (bb * rc) * fast_ex2(e);
