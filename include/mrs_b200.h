@@ -211,6 +211,21 @@ int mrs_spawn(const MrsConfig* cfg, const MrsBuffers* bufs, const unsigned char*
               unsigned long long seed, float z_lo, float z_hi, float xy_radius, float xy_sigma, float yaw_lo,
               float yaw_hi, int max_rounds, unsigned int* failed_envs, void* stream);
 
+/* Analytic sensors on the primitives of the 'simple' world (ground box top at ground_z, agents as
+ * AGENT_RADIUS spheres: the contact geometry of the step), for all agents of all envs at once.
+ * mrs_proximity: per agent the gap to the nearest other agent (centre distance - 2*AGENT_RADIUS) and
+ * its index, the gap of the collision cylinder to the ground, and collision = any gap < threshold
+ * (the reference uses 0.04).  Any output pointer may be NULL.  Device arrays of E*N elements.
+ * Replaces Object.collision / get_dist / get_contact_points distances (Object.py:98-140).
+ * mrs_raycast: n_rays rays per agent, directions device float[n_rays][3] in the body frame
+ * (body_frame != 0) or the world frame, start = position + R * offset3 (HOST float[3], may be NULL);
+ * hit_dist float[E*N][n_rays] (inf = nothing within range), hit_id int[E*N][n_rays]: -1 none,
+ * N = ground, j = agent j of the same env.  Replaces Object.raycast (Object.py:143-174). */
+int mrs_proximity(const MrsConfig* cfg, const MrsBuffers* bufs, float threshold, float* gap_agent, int* nearest,
+                  float* gap_ground, unsigned char* collision, void* stream);
+int mrs_raycast(const MrsConfig* cfg, const MrsBuffers* bufs, const float* directions, int n_rays,
+                const float* offset3, int body_frame, float range, float* hit_dist, int* hit_id, void* stream);
+
 /* T steps over HOST buffers with the copies pipelined against the kernels (H2D of step t+1 and
  * D2H of step t-1 overlap the kernel of step t on two internal copy streams).  actions_host
  * float[T][E][N][ACTION_DIM] (pinned), dev_actions: caller-owned device staging, TWO action

@@ -892,6 +892,100 @@ spawn_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const Spaw
     for (int p = 7; p < 13; ++p) st[p * (size_t)S + s] = 0.f;
 }
 
+// ------------------------------------------------------------------------------ sensors (row f4)
+// Analytic sensors of the 'simple' world (ground box top at ground_z, agents as AGENT_RADIUS
+// spheres -- the same contact geometry as the step).  One thread per agent (proximity) or per
+// (agent, ray) (raycast); partners are walked from the L1/L2-resident position planes.
+// Object.collision / get_dist / get_contact_points / raycast (Object.py:100-174) on these primitives.
+__global__ void __launch_bounds__(128)
+proximity_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, float thresh, float* __restrict__ gap_agent,
+                 int* __restrict__ nearest, float* __restrict__ gap_ground, unsigned char* __restrict__ collision) {
+    const unsigned S = (unsigned)c.E * (unsigned)c.N;
+    const unsigned s = blockIdx.x * 128u + threadIdx.x;
+    if (s >= S) return;
+    const int N = c.N;
+    const unsigned env0 = (s / (unsigned)N) * (unsigned)N;
+    const int ai = (int)(s - env0);
+    const float* px = b.state + env0;
+    const float* py = b.state + (size_t)S + env0;
+    const float* pz = b.state + 2 * (size_t)S + env0;
+    const float x = px[ai], y = py[ai], z = pz[ai];
+    float best = INFINITY;
+    int arg = -1;
+    for (int j = 0; j < N; ++j) {
+        if (j == ai) continue;
+        const float dx = x - px[j], dy = y - py[j], dz = z - pz[j];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < best) { best = d2; arg = j; }
+    }
+    const float ga = sqrtf(best) - 2.f * c.phys.agent_radius;
+    // ground: same support extent of the collision cylinder as the contact row of the step
+    const float qx = b.state[3 * (size_t)S + s], qy = b.state[4 * (size_t)S + s];
+    const float R22 = 1.f - 2.f * (qx * qx + qy * qy);
+    const float ext = c.phys.col_radius * sqrtf(fmaxf(1.f - R22 * R22, 0.f)) + c.phys.col_halfheight * fabsf(R22) +
+                      c.phys.col_margin;
+    const float gg = z - ext - c.phys.ground_z;
+    if (gap_agent) gap_agent[s] = ga;
+    if (nearest) nearest[s] = arg;
+    if (gap_ground) gap_ground[s] = gg;
+    if (collision) collision[s] = (ga < thresh || gg < thresh) ? 1 : 0;
+}
+
+// rays: [R][3] directions in the body frame (body != 0) or world frame, start = pos + R * offset;
+// hit_dist [S][R] (inf = no hit within range), hit_id [S][R]: -1 none, N = ground, j = agent j
+__global__ void __launch_bounds__(128)
+raycast_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const float* __restrict__ dirs, int nrays, float ox,
+               float oy, float oz, int body, float range, float* __restrict__ hit_dist, int* __restrict__ hit_id) {
+    const unsigned S = (unsigned)c.E * (unsigned)c.N;
+    const unsigned tid = blockIdx.x * 128u + threadIdx.x;
+    if (tid >= S * (unsigned)nrays) return;
+    const unsigned s = tid / (unsigned)nrays;
+    const int r = (int)(tid - s * (unsigned)nrays);
+    const int N = c.N;
+    const unsigned env0 = (s / (unsigned)N) * (unsigned)N;
+    const int ai = (int)(s - env0);
+    Agent st;
+    load_agent(b.state, S, s, st);
+    float Rm[9];
+    quat_to_mat(st, Rm);
+    float dx = dirs[3 * r], dy = dirs[3 * r + 1], dz = dirs[3 * r + 2];
+    float sx = ox, sy = oy, sz = oz;
+    if (body) {
+        const float tx = Rm[0] * dx + Rm[1] * dy + Rm[2] * dz, ty = Rm[3] * dx + Rm[4] * dy + Rm[5] * dz,
+                    tz = Rm[6] * dx + Rm[7] * dy + Rm[8] * dz;
+        dx = tx; dy = ty; dz = tz;
+        const float ux = Rm[0] * ox + Rm[1] * oy + Rm[2] * oz, uy = Rm[3] * ox + Rm[4] * oy + Rm[5] * oz,
+                    uz = Rm[6] * ox + Rm[7] * oy + Rm[8] * oz;
+        sx = ux; sy = uy; sz = uz;
+    }
+    const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= inv; dy *= inv; dz *= inv;
+    sx += st.px; sy += st.py; sz += st.pz;
+    float best = range;
+    int id = -1;
+    // ground: top face of the 30 x 30 x 1 box centred at the origin (plane.urdf:21-26)
+    if (dz < 0.f && sz > c.phys.ground_z) {
+        const float t = (c.phys.ground_z - sz) / dz;
+        const float hx = sx + t * dx, hy = sy + t * dy;
+        if (t < best && fabsf(hx) <= 15.f && fabsf(hy) <= 15.f) { best = t; id = N; }
+    }
+    const float* px = b.state + env0;
+    const float* py = b.state + (size_t)S + env0;
+    const float* pz = b.state + 2 * (size_t)S + env0;
+    const float rad2 = c.phys.agent_radius * c.phys.agent_radius;
+    for (int j = 0; j < N; ++j) {
+        if (j == ai) continue;
+        const float cx = px[j] - sx, cy = py[j] - sy, cz = pz[j] - sz;
+        const float tc = cx * dx + cy * dy + cz * dz;                  // closest approach along the ray
+        const float d2 = cx * cx + cy * cy + cz * cz - tc * tc;
+        if (d2 > rad2) continue;
+        const float t = tc - sqrtf(rad2 - d2);
+        if (t >= 0.f && t < best) { best = t; id = j; }
+    }
+    hit_dist[tid] = (id >= 0) ? best : INFINITY;
+    hit_id[tid] = id;
+}
+
 // tape maintenance: 128-bit grid-stride copy / zero fill (slot sizes are multiples of 4 floats
 // whenever E*N is; scalar tail otherwise)
 __global__ void __launch_bounds__(256)
@@ -1475,6 +1569,31 @@ int mrs_spawn(const MrsConfig* cfg, const MrsBuffers* bufs, const unsigned char*
     sp.seed = seed; sp.z_lo = z_lo; sp.z_hi = z_hi; sp.xy_radius = xy_radius; sp.xy_sigma = xy_sigma;
     sp.yaw_lo = yaw_lo; sp.yaw_hi = yaw_hi; sp.max_rounds = max_rounds;
     spawn_kernel<<<(unsigned)((cfg->E + 3) / 4), 128, 0, (cudaStream_t)stream>>>(*cfg, *bufs, sp, env_mask, failed_envs);
+    return last_error();
+}
+
+
+int mrs_proximity(const MrsConfig* cfg, const MrsBuffers* bufs, float threshold, float* gap_agent, int* nearest,
+                  float* gap_ground, unsigned char* collision, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs || !bufs->state) return MRS_ERR_ARG;
+    const size_t S = (size_t)cfg->E * cfg->N;
+    proximity_kernel<<<(unsigned)((S + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*cfg, *bufs, threshold, gap_agent,
+                                                                                   nearest, gap_ground, collision);
+    return last_error();
+}
+
+int mrs_raycast(const MrsConfig* cfg, const MrsBuffers* bufs, const float* directions, int n_rays, const float* offset3,
+                int body_frame, float range, float* hit_dist, int* hit_id, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bufs || !bufs->state || !directions || n_rays <= 0 || !hit_dist || !hit_id || !(range > 0.f)) return MRS_ERR_ARG;
+    const size_t total = (size_t)cfg->E * cfg->N * n_rays;
+    if (total >= 0xffffffffull) return MRS_ERR_UNSUPPORTED;
+    const float ox = offset3 ? offset3[0] : 0.f, oy = offset3 ? offset3[1] : 0.f, oz = offset3 ? offset3[2] : 0.f;
+    raycast_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*cfg, *bufs, directions, n_rays, ox, oy,
+                                                                                     oz, body_frame, range, hit_dist, hit_id);
     return last_error();
 }
 

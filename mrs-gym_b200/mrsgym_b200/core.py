@@ -348,6 +348,32 @@ class Swarm:
         self.launches += 1
         return A
 
+    def proximity(self, threshold=0.04):
+        """mrs_proximity: dict of [E,N] tensors -- 'gap_agent' (to the nearest other agent), 'nearest'
+        (its index, -1 if N == 1), 'gap_ground', 'collision' (bool, any gap < threshold)."""
+        z = dict(device=self.device)
+        ga = torch.empty(self.E, self.N, dtype=torch.float32, **z)
+        ne = torch.empty(self.E, self.N, dtype=torch.int32, **z)
+        gg = torch.empty(self.E, self.N, dtype=torch.float32, **z)
+        co = torch.empty(self.E, self.N, dtype=torch.uint8, **z)
+        _abi.check(self.lib.mrs_proximity(C.byref(self.cfg), C.byref(self.bufs), float(threshold), _ptr(ga), _ptr(ne),
+                                          _ptr(gg), _ptr(co), self._stream()), 'mrs_proximity')
+        self.launches += 1
+        return {'gap_agent': ga, 'nearest': ne, 'gap_ground': gg, 'collision': co.bool()}
+
+    def raycast(self, directions, offset=(0.0, 0.0, 0.0), body=True, RANGE=100.0):
+        """mrs_raycast: directions [R,3] (body or world frame) for every agent -> {'dist' [E,N,R] (inf =
+        no hit), 'object' [E,N,R] int (-1 none, N ground, j agent j)} (Object.raycast, Object.py:143-174)."""
+        d = torch.as_tensor(directions, dtype=torch.float32).reshape(-1, 3).to(self.device).contiguous()
+        R = d.shape[0]
+        dist = torch.empty(self.E, self.N, R, dtype=torch.float32, device=self.device)
+        obj = torch.empty(self.E, self.N, R, dtype=torch.int32, device=self.device)
+        off = (C.c_float * 3)(*[float(v) for v in offset])
+        _abi.check(self.lib.mrs_raycast(C.byref(self.cfg), C.byref(self.bufs), _ptr(d), R, off, 1 if body else 0,
+                                        float(RANGE), _ptr(dist), _ptr(obj), self._stream()), 'mrs_raycast')
+        self.launches += 1
+        return {'dist': dist, 'object': obj}
+
     def read_status(self, clear=True):
         v = int(self.status.item())
         if clear and v:

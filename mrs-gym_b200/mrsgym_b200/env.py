@@ -95,6 +95,20 @@ class Environment:
     def get_data(self, name):
         return self.data.get(name, None)
 
+    # analytic sensors on the simple world's primitives (Object.py:98-174), all agents at once
+    def collision(self, threshold=0.04):
+        """Object.collision (Object.py:136-137): any contact closer than 0.04 -> bool [E,N] ([N])."""
+        return self._out(self.swarm.proximity(threshold)['collision'])
+
+    def get_dist(self):
+        """Gap to the nearest other agent and to the ground, [E,N] each (Object.get_dist, Object.py:118-133)."""
+        p = self.swarm.proximity()
+        return {k: self._out(v) for k, v in p.items()}
+
+    def raycast(self, directions, offset=(0.0, 0.0, 0.0), body=True, RANGE=100.0):
+        r = self.swarm.raycast(directions, offset, body, RANGE)
+        return {k: self._out(v) for k, v in r.items()}
+
     # GUI / debug helpers of the reference (Environment.py:127-306) are no-ops headless
     def draw_links(self, A):
         pass

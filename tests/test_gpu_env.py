@@ -246,3 +246,43 @@ def test_rllib_style_wrappers():
     for _ in range(20):
         o, r, d, info = multi.step({'agent1': [1.0, 0, 0]})
     assert o['agent1'][3] > 0.05 and abs(o['agent2'][3]) < 0.02
+
+
+def test_analytic_sensors_vs_oracle():
+    """mrs_proximity / mrs_raycast (Object.collision / get_dist / raycast on the simple world's
+    primitives) against oracle/sensors.py"""
+    import mrsgym_b200 as mrsgym
+    from oracle import sensors, bullet_model as bm
+    E, N = 7, 12
+    rng = np.random.default_rng(91)
+    st = H.random_state(rng, E, N, spacing=0.62, z0=0.56, jitter=0.05, tilt=0.4)
+    st['pos'][:, 6:, 2] += 1.5                               # half of them well above the ground
+    sw = mrsgym.Swarm(E, N, 0, 'set_speeds')
+    H.upload_state(sw, st)
+    P = bm.PhysicsParams()
+    p = sw.proximity(0.04)
+    ga, ne, gg, co = sensors.proximity(st['pos'], st['quat'], P, 0.04)
+    np.testing.assert_allclose(p['gap_agent'].cpu().numpy(), ga, atol=2e-6)
+    np.testing.assert_allclose(p['gap_ground'].cpu().numpy(), gg, atol=2e-6)
+    np.testing.assert_array_equal(p['nearest'].cpu().numpy(), ne)
+    safe = (np.abs(ga - 0.04) > 1e-5) & (np.abs(gg - 0.04) > 1e-5)
+    np.testing.assert_array_equal(p['collision'].cpu().numpy()[safe], co[safe])
+    assert co.any() and (~co).any()
+    dirs = np.array([[1, 0, 0], [0, 0, -1], [0.3, -0.5, -0.2], [-1, 1, 0.1], [0, 0, 1]], np.float32)
+    for body in (True, False):
+        r = sw.raycast(dirs, offset=(0.0, 0.0, -0.02), body=body, RANGE=30.0)
+        dist, obj = sensors.raycast(st['pos'], st['quat'], dirs, (0.0, 0.0, -0.02), body, 30.0, P)
+        got_d, got_o = r['dist'].cpu().numpy(), r['object'].cpu().numpy()
+        hit = np.isfinite(dist)
+        agree = got_o == obj
+        assert agree.mean() > 0.995                          # grazing rays may flip at float32 resolution
+        both = agree & hit
+        np.testing.assert_allclose(got_d[both], dist[both], rtol=2e-5, atol=2e-5)
+        assert np.all(np.isinf(got_d[agree & ~hit]))
+        assert (obj == N).any() and ((obj >= 0) & (obj < N)).any() and (obj == -1).any()
+    # the env-level view used by reward functions (magent.py:42: -1 if agent.collision() else 0)
+    env = mrsgym.MRS(N_ENVS=3, N_AGENTS=4, START_POS=torch.tensor([[0., 0, 0.52], [0.5, 0, 2], [3, 0, 2], [3, 0.5, 2.]]),
+                     START_ORI=torch.zeros(4, 3))
+    c = env.env.collision()
+    assert tuple(c.shape) == (3, 4) and bool(c[:, 0].all())
+    assert bool(c[:, 2].all()) and bool(c[:, 3].all()) and not bool(c[:, 1].any())
