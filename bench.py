@@ -359,7 +359,7 @@ def run_gpu(args):
         'status_word': sw_status,
     }
     if world == 1 and not args.no_cpu:
-        procs = os.cpu_count() or 1
+        procs = min(os.cpu_count() or 1, 64)
         Ep, Tc = cpu_sample_sizes(args.workload)
         v, wall, total = cpu_port_throughput(args.workload, procs, Ep, Tc)
         out['cpu_baseline'] = {'value': v, 'unit': 'agent-steps/s', 'cores': procs, 'kind': 'port',
@@ -373,7 +373,7 @@ def run_reference(args):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    procs = os.cpu_count() or 1
+    procs = min(os.cpu_count() or 1, 64)
     Ep, _ = cpu_sample_sizes(args.workload)
     steps, warmup = args.steps, args.warmup
     # bounded: each "step" here is one env.step of the sample batch (procs x Ep envs)

@@ -4,10 +4,9 @@ CUDA path (through the C ABI) and to the CPU oracle (oracle/spec.py).  Nothing h
 from __future__ import annotations
 
 import numpy as np
-import torch
 
-# the oracle is imported lazily (make_spec): bench.py's GPU arm uses the input generators of this
-# module and must not pull the oracle in
+# torch and the oracle are imported lazily: bench.py's CPU workers use the input generators of this
+# module and should not pay for a torch import each; bench.py's GPU arm must not pull the oracle in
 
 HOVER = 14475.809
 MODES = ['set_target_vel', 'set_target_pos', 'set_target_accel', 'set_force', 'set_target_ori', 'set_control',
@@ -59,6 +58,7 @@ def random_actions(rng, mode, T, E, N, start_pos=None):
 
 def upload_state(swarm, st):
     """Exact float32 upload into the SoA planes (bypasses the euler conversion of set_state)."""
+    import torch
     S = swarm.S
     planes = np.concatenate([st['pos'].reshape(S, 3), st['quat'].reshape(S, 4), st['vel'].reshape(S, 3),
                              st['angvel'].reshape(S, 3)], axis=1).T.copy()
@@ -96,6 +96,7 @@ def quat_angle(q1, q2):
 
 def torch_cpu_adjacency(pos32, comm_range):
     """MRS.calc_A exactly as the reference computes it (MRS.py:117-124,166-170), on torch CPU."""
+    import torch
     pos = torch.as_tensor(pos32, dtype=torch.float32)
     N = pos.shape[-2]
     if comm_range == float('inf'):
