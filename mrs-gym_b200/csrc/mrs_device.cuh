@@ -353,13 +353,14 @@ __device__ __forceinline__ float contact_rhs(const MrsPhysicsParams& ph, const D
 
 // sphere-sphere contact of agent i with agent j (bullet_model.agent_contact_dv): d = p_i - p_j,
 // dv = v*_i - v*_j; returns true and adds this row's velocity change to acc when it pushes.
-// Rare path (only pairs closer than 2*AGENT_RADIUS + margin): IEEE sqrt / division kept.
+// 1/|d| from the SFU with one Newton step (full float32 accuracy): a swarm that has come to rest on
+// the ground in a heap takes this path for every pair and step.
 __device__ __forceinline__ bool agent_contact_pair(const MrsPhysicsParams& ph, const Derived& dd, float dx, float dy,
                                                    float dz, float dvx, float dvy, float dvz, float* acc) {
     const float d2 = dx * dx + dy * dy + dz * dz;
     if (!(d2 < dd.lim2) || !(d2 > 0.f)) return false;
-    const float d = sqrtf(d2);
-    const float inv = 1.f / d;
+    const float inv = rsqrt_nr(d2);
+    const float d = d2 * inv;
     const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
     const float vn = dvx * nx + dvy * ny + dvz * nz;
     const float rhs = 0.5f * contact_rhs(ph, dd, d - 2.f * ph.agent_radius, vn);
