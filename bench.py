@@ -208,11 +208,20 @@ def run_gpu(args):
     replays = steps // T
 
     st, act_np = make_inputs(w, E, T, seed=1234 + 4 + rank)
-    sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T + 2 * K + 2,
+    use_graph = T >= K + 1
+    sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T if use_graph else 2 * K + 2, ring=use_graph,
                  want_A=not os.environ.get('MRS_EXP_NO_A'))
     H.upload_state(sw, st)
     actions = torch.from_numpy(act_np).to(dev)
-    roll = sw.capture_rollout(actions, T)
+    if use_graph:
+        roll = sw.capture_rollout(actions, T)
+    else:                                   # fewer steps than the observation window: plain launches
+        class _Plain:
+            launches_per_replay = T
+
+            def replay(self):
+                sw.step_many_single(actions, T)
+        roll = _Plain()
 
     def barrier():
         if world > 1:
@@ -337,7 +346,7 @@ def run_gpu(args):
         'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {**workload_config(w, E, world),
-                   'launch': 'CUDA graph of %d single-step launches, %d replays' % (T, replays),
+                   'launch': ('CUDA graph of %d single-step launches, %d replays' if use_graph else '%d plain launches x %d') % (T, replays),
                    'l2': 'no flush: per-step streamed bytes (actions+X+A) are distinct every step and exceed L2 over the '
                          'region; state is re-read as the previous step left it; see l2_flushed'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,

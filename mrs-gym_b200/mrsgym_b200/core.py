@@ -36,7 +36,7 @@ def shard_range(E_total: int, rank: int, world: int):
 class Swarm:
     def __init__(self, E: int, N: int, K: int = 0, action_type='set_target_vel', state_layout=_abi.X_POS_VEL,
                  comm_range=float('inf'), dt=0.01, gravity=9.81, agent_radius=0.3, device='cuda',
-                 tape_slots=None, want_A=True, custom_D=0, keep_rpm=False):
+                 tape_slots=None, want_A=True, custom_D=0, keep_rpm=False, ring=False):
         self.lib = _abi.lib()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -58,8 +58,8 @@ class Swarm:
         self.cfg.phys.agent_radius = float(agent_radius)
         self.D = _abi.STATE_DIMS[state_layout] if state_layout != _abi.X_NONE else int(custom_D)
         self.L = int(tape_slots) if tape_slots else max(2 * self.K + 2, 16)
-        if self.L < 2 * self.K + 2:
-            raise ValueError('tape_slots must be >= 2*K_HOPS+2')
+        if self.L < (self.K + 1 if ring else 2 * self.K + 2):
+            raise ValueError('tape_slots must be >= 2*K_HOPS+2 (K_HOPS+1 in ring mode)')
         self.cfg.L = self.L
         dev = self.device
         z = dict(device=dev, dtype=torch.float32)
@@ -77,6 +77,8 @@ class Swarm:
         self._bind()
         self.hx = self.L - self.K - 1
         self.ha = self.L - self.K - 1
+        self.ring = bool(ring)     # True: heads wrap around the tape, nothing is ever moved (graph rollouts)
+        self.a_empty = True        # no A slice pushed since the last full reset (MRS.py:186)
         self.launches = 0          # kernel launches issued through the ABI (bench: gpu_launches)
 
     # ------------------------------------------------------------------ plumbing
@@ -117,6 +119,8 @@ class Swarm:
         if head >= need:
             return head
         K, L = self.K, self.L
+        if self.ring:                # ring mode (graph rollouts): wrap around, nothing is moved
+            return L
         tape = self.X_tape if which == 1 else self.A_tape
         if tape is not None and K > 0 and which == 1 and self.cfg.state_layout == _abi.X_NONE:
             tape[L - K:L] = tape[head:head + K].clone()      # python-written X (custom state_fn)
@@ -155,17 +159,28 @@ class Swarm:
                        'mrs_tape_fill')
             self.launches += 1
             self.ha += 1          # empty deque: the first push lands on slot L-K-1
+        self.a_empty = True
 
     def fill_X_history(self):
         """Custom state_fn path: replicate slot hx into the K older slots (python wrote X0 there)."""
-        if self.K > 0:
-            self.X_tape[self.hx + 1:self.hx + 1 + self.K] = self.X_tape[self.hx]
+        for sl in self.window_slots(1)[1:]:
+            self.X_tape[sl] = self.X_tape[self.hx]
+
+    def window_slots(self, which: int):
+        """Tape slots of the newest-first K+1 window of tape `which` (1 = X, 2 = A)."""
+        h = self.hx if which == 1 else self.ha
+        return [(h + k) % self.L for k in range(self.K + 1)] if self.ring else list(range(h, min(h + self.K + 1, self.L)))
+
+    def _window(self, tape, h):
+        if self.ring and h + self.K + 1 > self.L:      # wrapped: the only case that copies
+            return torch.cat([tape[h:], tape[:h + self.K + 1 - self.L]], dim=0)
+        return tape[h:h + self.K + 1]
 
     def X_window(self):
-        return self.X_tape[self.hx:self.hx + self.K + 1]          # [K+1, E, N, D], newest first
+        return self._window(self.X_tape, self.hx)                 # [K+1, E, N, D], newest first
 
     def A_window(self):
-        return self.A_tape[self.ha:self.ha + self.K + 1]          # [K+1, E, N, N]
+        return self._window(self.A_tape, self.ha)                 # [K+1, E, N, N]
 
     # ------------------------------------------------------------------ the step
     def _check_actions(self, actions, T=1, host=False):
@@ -198,6 +213,7 @@ class Swarm:
             self.hx = hx
         if self.A_tape is not None:
             self.ha = ha
+            self.a_empty = False
 
     def step_many(self, actions, T: int):
         """T steps with pre-computed actions [T,E,N,A]; chunks at tape wrap-arounds."""
@@ -215,6 +231,7 @@ class Swarm:
                 self.hx = hx - n
             if self.A_tape is not None:
                 self.ha = ha - n
+                self.a_empty = False
             done += n
 
     def step_many_single(self, actions, T: int):
@@ -225,9 +242,9 @@ class Swarm:
     def capture_rollout(self, actions, T: int):
         """CUDA-graph a T-step rollout (launch-bound loops belong in graphs): returns a
         GraphRollout whose replay() advances all envs by T steps reading actions[t] from the
-        given device buffer (refill it between replays).  Ring semantics are preserved: each
-        replay first moves the K newest slots to the top of the tapes, then writes T slots
-        downwards, ending where it started."""
+        given device buffer (refill it between replays).  The swarm switches to ring mode (tape heads
+        wrap around, no slots are moved); T must be a multiple of the tape size, so every replay
+        ends on the slots it started from (pass tape_slots=T to the constructor)."""
         return GraphRollout(self, actions, T)
 
     def push_A(self):
@@ -236,6 +253,7 @@ class Swarm:
         _abi.check(self.lib.mrs_observe(C.byref(self.cfg), C.byref(self.bufs), ha, 0, 1, self._stream()), 'mrs_observe')
         self.launches += 1
         self.ha = ha
+        self.a_empty = False
 
     def push_X(self):
         hx = self._make_room(1) - 1
@@ -257,6 +275,7 @@ class Swarm:
             self.hx = hx
         if self.A_tape is not None:
             self.ha = ha
+            self.a_empty = False
 
     def rollout_host(self, actions_host, dev_actions2, X_host=None, A_host=None):
         """mrs_rollout_host: T steps from pinned host actions [T,E,N,A] with the newest X / A slice of
@@ -279,6 +298,7 @@ class Swarm:
                 self.hx = hx - n
             if self.A_tape is not None:
                 self.ha = ha - n
+                self.a_empty = False
             done += n
 
     # ------------------------------------------------------------------ state access
@@ -394,54 +414,32 @@ class Swarm:
 class GraphRollout:
     def __init__(self, swarm: Swarm, actions, T: int):
         sw = self.swarm = swarm
-        K, L = sw.K, sw.L
-        if T < 1 or T > L - 2 * K - (1 if K == 0 else 0):
-            raise ValueError('capture_rollout: T=%d needs tape_slots >= T + 2*K_HOPS (+1), have %d' % (T, L))
+        if T < 1 or T % sw.L != 0:
+            raise ValueError('capture_rollout: T=%d must be a multiple of the tape size (%d slots); build the '
+                             'swarm with tape_slots=T' % (T, sw.L))
+        if sw.X_tape is not None and sw.cfg.state_layout == _abi.X_NONE:
+            raise RuntimeError('capture_rollout needs a fused state layout')
         if actions is not None and tuple(actions.shape[:3]) != (T, sw.E, sw.N):
             raise ValueError('actions must be [T, E, N, A]')
         self.T, self.actions = T, actions
-        self.h_end = L - K - T
+        sw.ring = True
         self.launches_per_replay = 0
-        # park the current windows at the slots where every replay ends
-        for which, tape, head in ((1, sw.X_tape, sw.hx), (2, sw.A_tape, sw.ha)):
-            if tape is None:
-                continue
-            if which == 1 and sw.cfg.state_layout == _abi.X_NONE:
-                raise RuntimeError('capture_rollout needs a fused state layout')
-            n = min(K + 1, L - head)
-            if head != self.h_end:
-                tape[self.h_end:self.h_end + n] = tape[head:head + n].clone()
-        sw.hx = sw.ha = self.h_end
         torch.cuda.synchronize(sw.device)
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=sw.device)
         side.wait_stream(torch.cuda.current_stream(sw.device))
         with torch.cuda.stream(side):
-            before = sw.launches
             self._body()            # warm-up outside capture (lazy module load, occupancy query)
-            sw.hx = sw.ha = self.h_end
             torch.cuda.synchronize(sw.device)
             with torch.cuda.graph(self.graph, stream=side):
                 before = sw.launches
-                self._body()
+                self._body()        # the heads come back to where they were: T is a multiple of L
                 self.launches_per_replay = sw.launches - before
         torch.cuda.current_stream(sw.device).wait_stream(side)
         torch.cuda.synchronize(sw.device)
 
     def _body(self):
         sw = self.swarm
-        sw.hx = sw.ha = 0 if sw.K > 0 else sw.L - sw.K      # force the move-to-top, then step down
-        if sw.K > 0:
-            # heads sit at h_end; _make_room moves [h_end, h_end+K) to the top when head == 0, so
-            # do the move explicitly from h_end
-            for which, tape in ((1, sw.X_tape), (2, sw.A_tape)):
-                if tape is None:
-                    continue
-                for i in range(sw.K - 1, -1, -1):
-                    _abi.check(sw.lib.mrs_tape_fill(C.byref(sw.cfg), C.byref(sw.bufs), which, self.h_end + i,
-                                                    sw.L - sw.K + i, 1, sw._stream()), 'mrs_tape_fill')
-                    sw.launches += 1
-        sw.hx = sw.ha = sw.L - sw.K
         if sw.N > 32:
             sw.step_many(self.actions, self.T)       # wide path: per-step kernels anyway, adjacency overlapped
         else:
@@ -450,4 +448,4 @@ class GraphRollout:
     def replay(self):
         self.graph.replay()
         self.swarm.launches += self.launches_per_replay
-        self.swarm.hx = self.swarm.ha = self.h_end
+        self.swarm.a_empty = False

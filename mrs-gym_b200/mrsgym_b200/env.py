@@ -278,7 +278,7 @@ class MRS:
 
     def a_ring_empty(self):
         """True right after a full reset / set: no A slice has been pushed yet (MRS.py:186)."""
-        return self.swarm.ha + self.swarm.K + 1 > self.swarm.L
+        return self.swarm.a_empty
 
     def calc_A(self):
         self._sync_cfg()
@@ -345,10 +345,11 @@ class MRS:
                 X0 = torch.cat([sw.get_pos(), sw.get_vel()], dim=-1)
             else:
                 X0 = torch.cat([sw.get_pos(), sw.get_quat(), sw.get_vel(), sw.get_angvel()], dim=-1)
-            w = sw.X_tape[sw.hx:sw.hx + sw.K + 1]
-            w[:, m] = X0[m].unsqueeze(0).to(w.dtype)
+            for sl in sw.window_slots(1):
+                sw.X_tape[sl][m] = X0[m].to(sw.X_tape.dtype)
         if sw.A_tape is not None:
-            sw.A_tape[sw.ha:sw.ha + sw.K + 1][:, m] = 0
+            for sl in sw.window_slots(2):
+                sw.A_tape[sl][m] = 0
         Xk = self.get_Xk()
         self.last_obs = Xk
         return Xk

@@ -52,7 +52,7 @@ class FakeLib:
         return 0
 
 
-def make_swarm(K, L):
+def make_swarm(K, L, ring=False):
     sw = object.__new__(Swarm)              # bypass the CUDA-only constructor: host logic only
     sw.E, sw.N, sw.K, sw.L, sw.S, sw.D = 1, 1, K, L, 1, 1
     sw.cfg = _abi.MrsConfig()
@@ -66,6 +66,8 @@ def make_swarm(K, L):
     sw.device = torch.device('cpu')
     sw.launches = 0
     sw.hx = sw.ha = L - K - 1
+    sw.ring = ring
+    sw.a_empty = True
     sw.lib = FakeLib(sw)
     sw._stream = lambda: None
     return sw
@@ -97,10 +99,11 @@ class RefRings:
             self.A.append(0.0)
 
 
+@pytest.mark.parametrize('ring', [False, True])
 @pytest.mark.parametrize('K,L', [(0, 2), (0, 5), (1, 4), (2, 6), (3, 8), (3, 16), (5, 12)])
-def test_tape_windows_follow_the_reference_deques(K, L):
+def test_tape_windows_follow_the_reference_deques(K, L, ring):
     rnd = random.Random(K * 100 + L)
-    sw = make_swarm(K, L)
+    sw = make_swarm(K, L, ring)
     ref = RefRings(K)
     sw.reset_windows()
     ref.reset(float(sw.lib.serial))
@@ -126,10 +129,10 @@ def test_tape_windows_follow_the_reference_deques(K, L):
         assert sw.X_window().flatten().tolist() == list(ref.X), (it, 'X')
         got_A = sw.A_window().flatten().tolist()
         if len(ref.A) == 0:
-            assert len(got_A) == K                       # empty deque: no window yet (reference would raise)
+            assert sw.a_empty                            # empty deque: no window yet (reference would raise)
         else:
-            assert got_A == list(ref.A), (it, 'A')
-        assert 0 <= sw.hx <= L - K - 1 and 0 <= sw.ha <= L - K
+            assert not sw.a_empty and got_A == list(ref.A), (it, 'A')
+        assert 0 <= sw.hx < L and 0 <= sw.ha <= L
 
 
 def test_capture_needs_room_and_action_checks():
@@ -148,3 +151,22 @@ def test_capture_needs_room_and_action_checks():
     with pytest.raises(AttributeError):
         sw.set_action_type('set_nothing')
     assert sw.set_action_type('set_target_pos') == 3 and sw.set_action_type(None) == 0
+
+
+@pytest.mark.parametrize('K,L', [(0, 1), (2, 3), (3, 4), (3, 10)])
+def test_ring_mode_small_tapes(K, L):
+    """ring mode needs only K_HOPS+1 slots: the window is the whole tape, rotated"""
+    sw = make_swarm(K, L, ring=True)
+    ref = RefRings(K)
+    sw.reset_windows()
+    ref.reset(float(sw.lib.serial))
+    for it in range(5 * L + 3):
+        if it % 4 == 3:
+            sw.step_many(None, L)                        # a whole lap, like a graph replay
+            for s in range(sw.lib.serial - L + 1, sw.lib.serial + 1):
+                ref.push_X(float(s)); ref.push_A(float(s))
+        else:
+            sw.step(None)
+            ref.push_X(float(sw.lib.serial)); ref.push_A(float(sw.lib.serial))
+        assert sw.X_window().flatten().tolist() == list(ref.X)
+        assert sw.A_window().flatten().tolist() == list(ref.A)

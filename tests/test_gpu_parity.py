@@ -340,6 +340,31 @@ def test_step_host_roundtrip():
     assert torch.equal(Xh, a.X_window()[0].cpu()) and torch.equal(Ah, a.A_window()[0].cpu())
 
 
+@pytest.mark.parametrize('N,mode', [(8, 'set_speeds'), (40, 'set_target_vel')])
+def test_graph_rollout_ring_mode_equals_steps(N, mode):
+    """capture_rollout: CUDA graph of T steps on a ring tape (tape_slots = T, nothing is ever moved);
+    two replays == 2 T plain steps, bit for bit, windows included"""
+    E, K, T = 48, 3, 8
+    rng = np.random.default_rng(53)
+    st = H.random_state(rng, E, N)
+    act = _dev(H.random_actions(rng, mode, T, E, N, start_pos=st['pos']))
+    a = _swarm(E, N, mode, K, 1.5)
+    b = _swarm(E, N, mode, K, 1.5, tape_slots=T, ring=True)
+    H.upload_state(a, st)
+    H.upload_state(b, st)
+    roll = b.capture_rollout(act, T)
+    H.upload_state(b, st)                     # the capture warm-up stepped b: start again from st
+    b.ctrl.copy_(a.ctrl)
+    for rep in range(2):
+        for t in range(T):
+            a.step(act[t])
+        roll.replay()
+        assert torch.equal(a.state, b.state), rep
+        assert torch.equal(a.X_window(), b.X_window()) and torch.equal(a.A_window(), b.A_window()), rep
+    with pytest.raises(ValueError):
+        b.capture_rollout(act[:5], 5)
+
+
 def test_rollout_host_pipelined_equals_steps():
     E, N, K, T = 256, 8, 2, 37
     rng = np.random.default_rng(52)
