@@ -123,13 +123,23 @@ __device__ __forceinline__ bool load_action(const float* __restrict__ actions, s
     }
 }
 
+// tape stores are write-once streams (nobody on the device re-reads a slot soon): streaming hint
+#ifndef MRS_TAPE_STREAMING
+#define MRS_TAPE_STREAMING 1
+#endif
+#if MRS_TAPE_STREAMING
+#define MRS_TAPE_ST(ptr, val) __stcs((ptr), (val))
+#else
+#define MRS_TAPE_ST(ptr, val) (*(ptr) = (val))
+#endif
+
 // newest X slice of one agent (Environment.get_X with the built-in state_fn layouts)
 __device__ __forceinline__ void write_X(float* __restrict__ Xs, int layout, unsigned s, const Agent& a) {
     if (layout == MRS_X_POS_VEL) {
         float2* p = reinterpret_cast<float2*>(Xs + (size_t)s * 6);
-        p[0] = make_float2(a.px, a.py);
-        p[1] = make_float2(a.pz, a.vx);
-        p[2] = make_float2(a.vy, a.vz);
+        MRS_TAPE_ST(p + 0, make_float2(a.px, a.py));
+        MRS_TAPE_ST(p + 1, make_float2(a.pz, a.vx));
+        MRS_TAPE_ST(p + 2, make_float2(a.vy, a.vz));
     } else if (layout == MRS_X_FULL) {
         float* p = Xs + (size_t)s * 13;
         p[0] = a.px; p[1] = a.py; p[2] = a.pz;
@@ -431,7 +441,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
                                     v[u] = (j + u == ai) ? 0.f
                                                          : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
                                 }
-                                *reinterpret_cast<float4*>(Arow + j) = make_float4(v[0], v[1], v[2], v[3]);
+                                MRS_TAPE_ST(reinterpret_cast<float4*>(Arow + j), make_float4(v[0], v[1], v[2], v[3]));
                             }
                         } else {
                             for (int j = 0; j < N; ++j) {
@@ -1081,13 +1091,15 @@ static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffe
     constexpr bool kStage = MRS_PREFETCH && GT != 0;
     constexpr size_t smem = (size_t)WPB * 32 * 2 * sizeof(float4) +
                             (kStage ? (size_t)WPB * mode_stage_floats<MODE>() * sizeof(float) : 16);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};          // per device: the attribute belongs to the function ON a device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MRS_ERR_CUDA;
+    if (!configured[dev]) {
         if (smem > 48 * 1024 &&
             cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
                 cudaSuccess)
             return MRS_ERR_CUDA;
-        configured = true;
+        configured[dev] = true;
     }
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)blocks);
