@@ -154,6 +154,18 @@ size_t mrs_sizeof_buffers(void);
  * Replaces Quadcopter.read_attributes/calculate_parameters (Quadcopter.py:119-168). */
 int mrs_default_config(MrsConfig* cfg);
 
+/* 1 when cfg carries exactly the reference's constants (every field mrs_default_config fills:
+ * cf2x.urdf, QuadControl gains, Bullet defaults, DT 0.01, GRAVITY 9.81, AGENT_RADIUS 0.3), 0
+ * otherwise.  For such a configuration the N <= 32 step runs kernels that hold these constants
+ * as immediates (generated csrc/mrs_baked.cuh); any other configuration runs the generic kernels
+ * that read them from MrsConfig.  Same arithmetic, same results; no reference counterpart. */
+int mrs_config_is_baked(const MrsConfig* cfg);
+
+/* Debug / build tooling: copies the host-derived constants of cfg (struct Derived of
+ * csrc/mrs_device.cuh, out_bytes must equal its size) to `out`.  tools/gen_baked.py reads the
+ * library's own numbers through this call when it generates csrc/mrs_baked.cuh. */
+int mrs_debug_derived(const MrsConfig* cfg, void* out, size_t out_bytes);
+
 /* One env.step for all E envs: actions -> controller -> rotor wrench + aero (ground
  * effect, drag, downwash) -> Bullet step (contact) -> newest X slice into X tape slot
  * `slot_x`, newest A slice into A tape slot `slot_a` (the reference shifts its X and A deques

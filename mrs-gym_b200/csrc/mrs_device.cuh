@@ -195,17 +195,19 @@ __device__ __noinline__ void nnls_enumerate(const MrsQuadParams& q, const float*
     }
 }
 
-__device__ __forceinline__ void set_control(const MrsQuadParams& q, const float* act, float* rpm) {
+// q: scalar model constants (compile-time values in the baked kernels), qt: the mixer tables, always
+// read from the kernel parameter (they are indexed at run time)
+__device__ __forceinline__ void set_control(const MrsQuadParams& q, const MrsQuadParams& qt, const float* act, float* rpm) {
     const float inv_kfl = 1.f / (q.kf * q.arm);
     const float B[4] = {act[0] * q.mass / q.kf, act[1] * q.ixx * inv_kfl, act[2] * q.iyy * inv_kfl,
                         act[3] * q.izz / q.km};
     float sq[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float* a = q.mix_ainv + i * 4;
+        const float* a = qt.mix_ainv + i * 4;
         sq[i] = a[0] * B[0] + a[1] * B[1] + a[2] * B[2] + a[3] * B[3];
     }
-    if (fminf(fminf(sq[0], sq[1]), fminf(sq[2], sq[3])) < 0.f) nnls_enumerate(q, B, sq);
+    if (fminf(fminf(sq[0], sq[1]), fminf(sq[2], sq[3])) < 0.f) nnls_enumerate(qt, B, sq);
 #pragma unroll
     for (int i = 0; i < 4; ++i) rpm[i] = sqrtf(sq[i]);
 }
@@ -213,14 +215,14 @@ __device__ __forceinline__ void set_control(const MrsQuadParams& q, const float*
 // ------------------------------------------------------------------------------------------
 // action -> rpm for one agent (Quadcopter.set_* -> QuadControl.*).
 template <int MODE>
-__device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const Derived& d, const Agent& s, const float* R,
-                                              const float* act, Ctrl& k, float* rpm) {
+__device__ __forceinline__ void action_to_rpm(const MrsConfig& c, const MrsQuadParams& qt, const Derived& d, const Agent& s,
+                                              const float* R, const float* act, Ctrl& k, float* rpm) {
     const MrsQuadParams& q = c.quad;
     if constexpr (MODE == MRS_SET_SPEEDS) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) rpm[i] = act[i];
     } else if constexpr (MODE == MRS_SET_CONTROL) {
-        set_control(q, act, rpm);
+        set_control(q, qt, act, rpm);
     } else if constexpr (MODE == MRS_SET_TARGET_ORI) {
         float Rt[9];
         euler_to_mat(act[0], act[1], act[2], Rt);

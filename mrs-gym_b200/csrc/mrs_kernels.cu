@@ -26,18 +26,24 @@
 
 #include "mrs_b200.h"
 #include "mrs_device.cuh"
+#include "mrs_baked.cuh"
 
 namespace mrs {
 
 constexpr int kBlock = 128;
-constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned kFull32 = 0xffffffffu;
 
 struct StepArgs {
     const float* actions;  // [T][E][N][A]
     int T;
     int slot_x, slot_a;    // step t writes X tape slot slot_x - t and A tape slot slot_a - t
+    // group path: the same as pointers, resolved once on the host (NULL = that tape is not written):
+    // step t writes X to X0 - t * xstride and A to A0 - t * astride (strides in floats)
+    float* X0;
+    float* A0;
+    long long xstride, astride;
     int G;                 // group width (power of two >= N), group path only
-    int nchunks;           // warp-sized work items, group path only
+    int chunk_lo, nchunks; // this launch walks the warp-sized work items [chunk_lo, nchunks), group path only
 };
 
 // ------------------------------------------------------------------------------ state planes
@@ -170,8 +176,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------ group path
-// GT > 0: compile-time group width with N == GT (8, 16, 32: pair loops unrolled, no bounds tests);
-// GT == 0: run-time width a.G >= N (any N <= 32).
+// GT > 0: compile-time group width with N == GT (8, 16, 32: pair loops unrolled) and FULL chunks only:
+//         every chunk is 32 consecutive valid agent slots, so the kernel carries no bounds logic at
+//         all; a ragged last chunk (E not a multiple of 32/N) is a second, one-chunk launch of the
+//         GT == 0 kernel (dispatch_step).
+// GT == 0: run-time width a.G >= N (any N <= 32), lanes >= N of a group idle.
 // WPB = warps per CTA.  WPB = 4: many small CTAs, chunks handed out grid-stride (small jobs).
 // WPB = 4 * minb (one CTA owns a whole SM): the CTA takes a contiguous share of the chunks and its
 // warps pull them from a shared-memory counter.  Per-warp timestamps at C5 (tools/trace_c5.py)
@@ -180,12 +189,34 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // warp; the SM-local dynamic hand-out keeps all warps of an SM busy until its share is done
 // (first / last warp end 14.7 / 20.2 us).  A device-wide atomic counter was tried first: 12k
 // same-address L2 atomics per launch serialise and cost +40 %.
-template <int MODE, int GT, int WPB>
+//
+// BAKED: the model constants (cf2x.urdf, QuadControl gains, Bullet defaults, DT, GRAVITY and what the
+// host derives from them) are compile-time values taken from the generated mrs_baked.cuh instead of
+// kernel parameters.  sm_100a has no constant-bank operands on its FP instructions: every parameter a
+// chunk uses costs an LDC/LDCU issue slot (~10 % of the generic kernel's instructions), immediates cost
+// nothing and fold.  The host picks the baked kernel only when the caller's MrsConfig carries exactly
+// those values (config_is_baked: bitwise compare); anything else runs the generic kernel.
+
+// plane `pl` of an SoA buffer given the pointer to the agent's slot in plane 0: one IMAD.WIDE.U32
+__device__ __forceinline__ float* plane_ptr(float* p0, unsigned S, int pl) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(p0) + (unsigned long long)S * (unsigned)(pl * 4));
+}
+__device__ __forceinline__ const float* plane_ptr(const float* p0, unsigned S, int pl) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p0) + (unsigned long long)S * (unsigned)(pl * 4));
+}
+
+template <int MODE, int GT, int WPB, bool BAKED>
 __global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : 1)
-step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
+step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant__ Derived d_in, const MrsBuffers b,
                   const StepArgs a) {
+    MrsConfig c_bk;
+    Derived d_bk;
+    if constexpr (BAKED) baked_fill(c_bk, d_bk, c_in, d_in);
+    const MrsConfig& c = BAKED ? c_bk : c_in;
+    const Derived& d = BAKED ? d_bk : d_in;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr bool kStage = MRS_PREFETCH && GT != 0;
+    constexpr bool kFull = GT != 0;
+    constexpr bool kStage = MRS_PREFETCH && kFull;
     constexpr int kStageFloats = mode_stage_floats<MODE>();
     float4* sh_pos = reinterpret_cast<float4*>(smem_raw);
     float4* sh_vel = sh_pos + WPB * 32;
@@ -206,17 +237,16 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
     const int wtotal = gridDim.x * WPB;
     const MrsPhysicsParams& ph = c.phys;
     const bool pair_contact = ph.agent_contact && N > 1;
-    const size_t xslot = (size_t)S * (size_t)state_dim(c.state_layout);
-    const size_t aslot = (size_t)S * (size_t)N;
 
-    // Work distribution (see the comment above the kernel): two static rounds, then the CTA-local
-    // counter.  The hand-out for the chunk after next is issued at the top of an iteration
-    // (shared-memory atomic) and consumed at the bottom, so the stage prefetch of the next chunk can
-    // always be issued immediately.
+    // Work distribution (see the comment above the kernel) over the chunks [a.chunk_lo, a.nchunks): two
+    // static rounds, then the CTA-local counter.  The hand-out for the chunk after next is issued at the
+    // top of an iteration (shared-memory atomic) and consumed at the bottom, so the stage prefetch of the
+    // next chunk can always be issued immediately.
     constexpr bool kLocal = WPB > 4;
     const int gw = blockIdx.x * WPB + wib;
-    const int cta_lo = kLocal ? (int)(((long long)blockIdx.x * a.nchunks) / gridDim.x) : 0;
-    const int cta_hi = kLocal ? (int)(((long long)(blockIdx.x + 1) * a.nchunks) / gridDim.x) : a.nchunks;
+    const int nwork = a.nchunks - a.chunk_lo;
+    const int cta_lo = a.chunk_lo + (kLocal ? (int)(((long long)blockIdx.x * nwork) / gridDim.x) : 0);
+    const int cta_hi = kLocal ? a.chunk_lo + (int)(((long long)(blockIdx.x + 1) * nwork) / gridDim.x) : a.nchunks;
     if (threadIdx.x < 5) sh_events[threadIdx.x] = 0u;
     if (threadIdx.x == 0) sh_counter = 0;
     __syncthreads();
@@ -227,37 +257,35 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
     };
     auto resolve_fetch = [&](int v, int cur_next) -> int {
         int nx;
-        if (kLocal) nx = cta_lo + 2 * WPB + __shfl_sync(kFull, v, 0);
+        if (kLocal) nx = cta_lo + 2 * WPB + __shfl_sync(kFull32, v, 0);
         else nx = cur_next + wtotal;
         return (cur_next >= 0 && nx < cta_hi) ? nx : -1;
     };
-    // chunk = 32 consecutive agent slots (GT != 0).  Piece q (16 B) of the stage lives at float offset
+    // chunk = 32 consecutive agent slots (kFull).  Piece q (16 B) of the stage lives at float offset
     // 4 q: q < 104 state (plane q >> 3, sub-piece q & 7), then 8 pieces per PID plane, then the actions
-    // (32 * ACTION_DIM contiguous floats).  Lane l moves pieces l, l + 32, ...
+    // (32 * ACTION_DIM contiguous floats).  Lane l moves pieces l, l + 32, ...: its plane advances by 4
+    // per round, so all global addresses are one 32-bit element index (lane part + round part + chunk
+    // part) widened once per piece.
     constexpr int kNC = mode_nctrl<MODE>();
     constexpr int kA = ModeTraits<MODE>::A;
-    constexpr int kPieces = 8 * (13 + kNC) + 8 * kA;
+    constexpr int kStatePieces = 8 * 13, kCtrlPieces = 8 * kNC, kPieces = kStatePieces + kCtrlPieces + 8 * kA;
+    const unsigned lane_el = (unsigned)(lane >> 3) * S + (unsigned)(lane & 7) * 4u;   // plane (l>>3), sub-piece (l&7)
     auto prefetch = [&](int chunk) {
         const unsigned s0 = (unsigned)chunk * 32u;
-        const unsigned left = min(32u, S - s0);            // agents of this chunk (multiple of N >= 8)
 #pragma unroll
         for (int i = 0; i < (kPieces + 31) / 32; ++i) {
             const int q = lane + 32 * i;
-            if (q < kPieces) {
-                const float* g;
-                bool ok;
-                if (q < 104 + 8 * kNC) {
-                    const int pl = q >> 3, sub = q & 7;
-                    const float* base = (pl < 13) ? b.state + (size_t)pl * S
-                                                  : b.ctrl + (size_t)mode_ctrl_plane<MODE>(pl - 13) * S;
-                    g = base + s0 + sub * 4;
-                    ok = (unsigned)(sub * 4) < left;
-                } else {
-                    const int aq = q - (104 + 8 * kNC);
-                    g = a.actions + (size_t)s0 * kA + aq * 4;
-                    ok = (unsigned)(aq * 4) < left * kA;
-                }
-                if (ok) cp_async16(stage + 4 * q, g);
+            if (32 * i + 31 < kStatePieces || q < kStatePieces) {
+                if (32 * i < kStatePieces) cp_async16(stage + 4 * q, b.state + (lane_el + s0 + (unsigned)(4 * i) * S));
+            }
+            if (32 * i + 31 >= kStatePieces && 32 * i < kStatePieces + kCtrlPieces && q >= kStatePieces &&
+                q < kStatePieces + kCtrlPieces) {
+                const int pl = (q - kStatePieces) >> 3;
+                cp_async16(stage + 4 * q, b.ctrl + ((unsigned)mode_ctrl_plane<MODE>(pl) * S + s0 + (unsigned)(q & 7) * 4u));
+            }
+            if (32 * i + 31 >= kStatePieces + kCtrlPieces && q >= kStatePieces + kCtrlPieces && q < kPieces) {
+                const int aq = q - (kStatePieces + kCtrlPieces);
+                cp_async16(stage + 4 * q, a.actions + ((size_t)s0 * kA + (unsigned)aq * 4u));
             }
         }
         cp_async_commit();
@@ -288,53 +316,48 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
 #ifdef MRS_TRACE
     stamp();
 #endif
-    const int first = kLocal ? cta_lo + wib : gw;
+    const int first = kLocal ? cta_lo + wib : a.chunk_lo + gw;
     const int stride0 = kLocal ? WPB : wtotal;
     int chunk = first < cta_hi ? first : -1;
     int chunk_next = (chunk >= 0 && first + stride0 < cta_hi) ? first + stride0 : -1;
     if (kStage && chunk >= 0) prefetch(chunk);
     while (chunk >= 0) {
         const int fetch_ticket = (chunk_next >= 0) ? issue_fetch() : 0;   // warp-uniform condition
-        // GT != 0: the chunk is 32 consecutive slots; else lanes >= N of a group idle
+        // kFull: the chunk is 32 consecutive valid slots; else lanes >= N of a group (and envs >= E) idle
         const int e = chunk * gpw + (lane / G);
-        const bool valid = GT ? ((unsigned)chunk * 32u + (unsigned)lane < S) : ((e < E) && (ai < N));
-        const unsigned s = valid ? (GT ? (unsigned)chunk * 32u + (unsigned)lane : (unsigned)e * (unsigned)N + (unsigned)ai) : 0u;
+        const bool valid = kFull ? true : ((e < E) && (ai < N));
+        const unsigned s = kFull ? (unsigned)chunk * 32u + (unsigned)lane
+                                 : (valid ? (unsigned)e * (unsigned)N + (unsigned)ai : 0u);
         Agent st;
         Ctrl k;
         float4 act0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kStage) {
+        if constexpr (kStage) {
             cp_async_wait_all();
             __syncwarp();           // pieces were fetched by other lanes
-            if (valid) {
-                st.px = stage[0 * 32 + lane]; st.py = stage[1 * 32 + lane]; st.pz = stage[2 * 32 + lane];
-                st.qx = stage[3 * 32 + lane]; st.qy = stage[4 * 32 + lane]; st.qz = stage[5 * 32 + lane];
-                st.qw = stage[6 * 32 + lane];
-                st.vx = stage[7 * 32 + lane]; st.vy = stage[8 * 32 + lane]; st.vz = stage[9 * 32 + lane];
-                st.wx = stage[10 * 32 + lane]; st.wy = stage[11 * 32 + lane]; st.wz = stage[12 * 32 + lane];
-                const float* cs = stage + 13 * 32 + lane;
-                if constexpr (ModeTraits<MODE>::io) {
+            st.px = stage[0 * 32 + lane]; st.py = stage[1 * 32 + lane]; st.pz = stage[2 * 32 + lane];
+            st.qx = stage[3 * 32 + lane]; st.qy = stage[4 * 32 + lane]; st.qz = stage[5 * 32 + lane];
+            st.qw = stage[6 * 32 + lane];
+            st.vx = stage[7 * 32 + lane]; st.vy = stage[8 * 32 + lane]; st.vz = stage[9 * 32 + lane];
+            st.wx = stage[10 * 32 + lane]; st.wy = stage[11 * 32 + lane]; st.wz = stage[12 * 32 + lane];
+            const float* cs = stage + 13 * 32 + lane;
+            if constexpr (ModeTraits<MODE>::io) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) k.io[i] = cs[i * 32];
-                }
-                if constexpr (ModeTraits<MODE>::ip) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) k.ip[i] = cs[(3 + i) * 32];
-                }
-                if constexpr (ModeTraits<MODE>::vel) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        k.iv[i] = cs[(3 + i) * 32]; k.lve[i] = cs[(6 + i) * 32];
-                        k.dve[i] = cs[(9 + i) * 32]; k.ltv[i] = cs[(12 + i) * 32];
-                    }
-                }
-                const float* as = stage + (13 + kNC) * 32 + kA * lane;
-                if constexpr (kA == 4) act0 = *reinterpret_cast<const float4*>(as);
-                if constexpr (kA == 3) act0 = make_float4(as[0], as[1], as[2], 0.f);
-            } else {
-                dummy_agent(st);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) k.io[i] = k.ip[i] = k.iv[i] = k.lve[i] = k.dve[i] = k.ltv[i] = 0.f;
+                for (int i = 0; i < 3; ++i) k.io[i] = cs[i * 32];
             }
+            if constexpr (ModeTraits<MODE>::ip) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) k.ip[i] = cs[(3 + i) * 32];
+            }
+            if constexpr (ModeTraits<MODE>::vel) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    k.iv[i] = cs[(3 + i) * 32]; k.lve[i] = cs[(6 + i) * 32];
+                    k.dve[i] = cs[(9 + i) * 32]; k.ltv[i] = cs[(12 + i) * 32];
+                }
+            }
+            const float* as = stage + (13 + kNC) * 32 + kA * lane;
+            if constexpr (kA == 4) act0 = *reinterpret_cast<const float4*>(as);
+            if constexpr (kA == 3) act0 = make_float4(as[0], as[1], as[2], 0.f);
             __syncwarp();           // everyone has read its column before the stage is refilled
             if (chunk_next >= 0) prefetch(chunk_next);
         } else if (valid) {
@@ -349,12 +372,14 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
         unsigned n_agent_rows = 0, n_ground = 0;
         float rpm[4] = {0.f, 0.f, 0.f, 0.f};
 
-        for (int t = 0; t < a.T; ++t) {
+        float* Xs = a.X0;       // tape slots of step t (they move down one slot per step)
+        float* As = a.A0;
+        for (int t = 0; t < a.T; ++t, Xs -= a.xstride, As -= a.astride) {
             float act[4];
             bool nan_act = false;
             if (kStage && t == 0) {
                 act[0] = act0.x; act[1] = act0.y; act[2] = act0.z; act[3] = act0.w;
-                nan_act = valid && kA > 0 && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || isnan(act0.w));
+                nan_act = kA > 0 && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || isnan(act0.w));
             } else if (valid) {
                 nan_act = load_action<MODE>(a.actions, (size_t)t * S + s, act);
             } else {
@@ -370,7 +395,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
 #endif
             float R[9];
             quat_to_mat(st, R);
-            action_to_rpm<MODE>(c, d, st, R, act, k, rpm);
+            action_to_rpm<MODE>(c, c_in.quad, d, st, R, act, k, rpm);
 
             // ---- pair pass 1: downwash + contact proximity on the pre-step positions
             __syncwarp();
@@ -395,7 +420,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
             apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
 
             // ---- pair pass 2 (rare): sphere-sphere contact on the unconstrained velocities
-            if (pair_contact && __any_sync(kFull, near && valid)) {
+            if (pair_contact && __any_sync(kFull32, near && valid)) {
                 wvel[lane] = make_float4(st.vx, st.vy, st.vz, 0.f);
                 __syncwarp();
                 if (near) {
@@ -419,10 +444,9 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
 
             }
             // ---- observation: newest X slice and newest A slice into their tape slots
-            if (b.X_tape && c.state_layout != MRS_X_NONE && valid)
-                write_X(b.X_tape + (size_t)(a.slot_x - t) * xslot, c.state_layout, s, st);
-            if (b.A_tape) {
-                float* Arow = b.A_tape + (size_t)(a.slot_a - t) * aslot + (size_t)s * N;
+            if (a.X0 && valid) write_X(Xs, c.state_layout, s, st);
+            if (a.A0) {
+                float* Arow = As + (size_t)s * N;
                 if (d.comm_inf) {
                     if (valid)
                         for (int j = 0; j < N; ++j) Arow[j] = (j == ai) ? 0.f : 1.f;
@@ -434,19 +458,25 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
                         if ((N & 3) == 0) {
 #pragma unroll 2
                             for (int j = 0; j < N; j += 4) {
+                                // loads and arithmetic unconditional, the diagonal is a select afterwards: a
+                                // conditional around the shared-memory load compiles to one divergent
+                                // BSSY/BRA/BSYNC block per element (no overlap between the pairs)
+                                float4 pj[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) pj[u] = wpos[gb + j + u];
                                 float v[4];
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
-                                    const float4 pj = wpos[gb + j + u];
-                                    v[u] = (j + u == ai) ? 0.f
-                                                         : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
+                                    const float hit = adjacency_pair(st.px, st.py, st.pz, pj[u].x, pj[u].y, pj[u].z, d.s_max);
+                                    v[u] = (j + u == ai) ? 0.f : hit;
                                 }
                                 MRS_TAPE_ST(reinterpret_cast<float4*>(Arow + j), make_float4(v[0], v[1], v[2], v[3]));
                             }
                         } else {
                             for (int j = 0; j < N; ++j) {
                                 const float4 pj = wpos[gb + j];
-                                Arow[j] = (j == ai) ? 0.f : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
+                                const float hit = adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
+                                Arow[j] = (j == ai) ? 0.f : hit;
                             }
                         }
                     }
@@ -455,11 +485,16 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
         }
 
         if (valid) {
-            store_agent(b.state, S, s, st);
+            float* p0 = b.state + s;
+            *plane_ptr(p0, S, 0) = st.px; *plane_ptr(p0, S, 1) = st.py; *plane_ptr(p0, S, 2) = st.pz;
+            *plane_ptr(p0, S, 3) = st.qx; *plane_ptr(p0, S, 4) = st.qy; *plane_ptr(p0, S, 5) = st.qz;
+            *plane_ptr(p0, S, 6) = st.qw;
+            *plane_ptr(p0, S, 7) = st.vx; *plane_ptr(p0, S, 8) = st.vy; *plane_ptr(p0, S, 9) = st.vz;
+            *plane_ptr(p0, S, 10) = st.wx; *plane_ptr(p0, S, 11) = st.wy; *plane_ptr(p0, S, 12) = st.wz;
             store_ctrl<MODE>(b.ctrl, S, s, k);
             if (b.rpm && MODE != MRS_NO_ACTION) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) b.rpm[i * S + s] = rpm[i];
+                for (int i = 0; i < 4; ++i) *plane_ptr(b.rpm + s, S, i) = rpm[i];
             }
         } else {
             status = 0; n_agent_rows = 0; n_ground = 0;
@@ -471,11 +506,11 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
         // happen once per CTA at the end.  (A swarm resting on the ground reports a ground contact per
         // agent per step: with one global atomic per warp-chunk that was 10 k same-address L2 atomics
         // per launch at C5 and cost ~15 % of the step.)
-        const unsigned any_status = __reduce_or_sync(kFull, status);
-        const unsigned events = __reduce_or_sync(kFull, n_agent_rows | n_ground);
+        const unsigned any_status = __reduce_or_sync(kFull32, status);
+        const unsigned events = __reduce_or_sync(kFull32, n_agent_rows | n_ground);
         if (any_status | events) {
-            const unsigned sum_rows = __reduce_add_sync(kFull, n_agent_rows);
-            const unsigned sum_gnd = __reduce_add_sync(kFull, n_ground);
+            const unsigned sum_rows = __reduce_add_sync(kFull32, n_agent_rows);
+            const unsigned sum_gnd = __reduce_add_sync(kFull32, n_ground);
             if (lane == 0) {
                 if (any_status) atomicOr(&sh_events[0], any_status);
                 if (sum_rows) atomicAdd(&sh_events[1], sum_rows);
@@ -513,7 +548,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ D
 template <int LPA>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-    for (int o = LPA / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    for (int o = LPA / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull32, v, o);
     return v;
 }
 
@@ -532,7 +567,7 @@ __device__ __forceinline__ void agent_pre(const MrsConfig& c, const Derived& d, 
     if (load_action<MODE>(actions, s, act)) status |= MRS_STATUS_NAN_ACTION;
     float R[9], rpm[4];
     quat_to_mat(st, R);
-    action_to_rpm<MODE>(c, d, st, R, act, k, rpm);
+    action_to_rpm<MODE>(c, c.quad, d, st, R, act, k, rpm);
     apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
     float* sc = b.scratch;
     sc[0 * (size_t)S + s] = st.vx; sc[1 * (size_t)S + s] = st.vy; sc[2 * (size_t)S + s] = st.vz;
@@ -593,7 +628,7 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
                 any_live = any_live || live[u];
                 near = near || (other && dxy2[u] + rz[u] * rz[u] < d.lim2);
             }
-            if (MODE != MRS_NO_ACTION && __any_sync(kFull, any_live)) {
+            if (MODE != MRS_NO_ACTION && __any_sync(kFull32, any_live)) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float f = downwash_pair(c.quad, d, dxy2[u], rz[u]);
@@ -604,8 +639,8 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
     }
     if constexpr (LPA <= 32) {
         dw = group_sum<LPA>(dw);
-        const unsigned gmask = (LPA == 32) ? kFull : (((1u << (LPA & 31)) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
-        near = (__ballot_sync(kFull, near) & gmask) != 0u;
+        const unsigned gmask = (LPA == 32) ? kFull32 : (((1u << (LPA & 31)) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
+        near = (__ballot_sync(kFull32, near) & gmask) != 0u;
     } else {
         // one CTA per agent (N >= 1024): warp sums in a fixed order through shared memory
         __shared__ float part[kBlock / 32];
@@ -708,9 +743,9 @@ step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ De
         bad = agent_finite(st) ? 0u : 1u;
     }
     // statistics: one warp reduction, then at most three global atomics per warp (not per agent)
-    const unsigned w_rows = __reduce_add_sync(kFull, lead ? rows : 0u);
-    const unsigned w_gnd = __reduce_add_sync(kFull, gnd);
-    const unsigned w_bad = __reduce_add_sync(kFull, bad);
+    const unsigned w_rows = __reduce_add_sync(kFull32, lead ? rows : 0u);
+    const unsigned w_gnd = __reduce_add_sync(kFull32, gnd);
+    const unsigned w_bad = __reduce_add_sync(kFull32, bad);
     if ((threadIdx.x & 31) == 0) {
         if (w_bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
         if (b.stats) {
@@ -881,12 +916,12 @@ spawn_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const Spaw
         }
         bool hit = false;
         for (int j = 0; j < N; ++j) {
-            const float xj = __shfl_sync(kFull, x, j), yj = __shfl_sync(kFull, y, j), zj = __shfl_sync(kFull, z, j);
+            const float xj = __shfl_sync(kFull32, x, j), yj = __shfl_sync(kFull32, y, j), zj = __shfl_sync(kFull32, z, j);
             const float dx = x - xj, dy = y - yj, dz = z - zj;
             hit = hit || (valid && j < lane && dx * dx + dy * dy + dz * dz < lim2);
         }
         redraw = hit;
-        if (!__any_sync(kFull, hit)) break;
+        if (!__any_sync(kFull32, hit)) break;
     }
     if (round >= sp.max_rounds && lane == 0 && failed) atomicAdd(failed, 1u);
     if (!valid) return;
@@ -1085,7 +1120,15 @@ static Derived make_derived(const MrsConfig& c) {
     return d;
 }
 
-template <int MODE, int GT, int WPB>
+// true iff the caller's configuration carries exactly the constants mrs_baked.cuh was generated from
+static bool config_is_baked(const MrsConfig& c, const Derived& d) {
+    MrsConfig cc = c;
+    Derived dd = d;
+    baked_constants(cc, dd);
+    return memcmp(&cc, &c, sizeof(MrsConfig)) == 0 && memcmp(&dd, &d, sizeof(Derived)) == 0;
+}
+
+template <int MODE, int GT, int WPB, bool BAKED>
 static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
                             bool pdl, cudaStream_t st) {
     constexpr bool kStage = MRS_PREFETCH && GT != 0;
@@ -1096,7 +1139,7 @@ static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffe
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MRS_ERR_CUDA;
     if (!configured[dev]) {
         if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB, BAKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
                 cudaSuccess)
             return MRS_ERR_CUDA;
         configured[dev] = true;
@@ -1111,7 +1154,7 @@ static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffe
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&lc, step_group_kernel<MODE, GT, WPB>, c, d, b, a) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&lc, step_group_kernel<MODE, GT, WPB, BAKED>, c, d, b, a) != cudaSuccess) {
         (void)cudaGetLastError();
         return MRS_ERR_CUDA;
     }
@@ -1128,11 +1171,18 @@ static int launch_group(const MrsConfig& c, const Derived& d, const MrsBuffers& 
     // large jobs (every warp of the GPU gets more than two chunks): one SM-sized CTA per SM with the
     // shared-memory hand-out.  Programmatic dependent launch pays off for full waves (measured
     // -2.3 % at C5); partial waves are faster with plain stream order (C3: +11 % with PDL).
-    if (use_big && a.nchunks > 2 * sms * kBig)
-        return launch_group_wpb<MODE, GT, kBig>(c, d, b, a, sms, use_pdl != 0, st);
-    const long long need = ((long long)a.nchunks + 3) / 4;
+    static const int use_baked = env_int("MRS_B200_BAKED", 1);
+    const bool baked = use_baked && config_is_baked(c, d);
+    const int nwork = a.nchunks - a.chunk_lo;
+    if (use_big && nwork > 2 * sms * kBig)
+        return baked ? launch_group_wpb<MODE, GT, kBig, true>(c, d, b, a, sms, use_pdl != 0, st)
+                     : launch_group_wpb<MODE, GT, kBig, false>(c, d, b, a, sms, use_pdl != 0, st);
+    const long long need = ((long long)nwork + 3) / 4;
     const long long cap = (long long)sms * ModeTraits<MODE>::minb;
-    return launch_group_wpb<MODE, GT, 4>(c, d, b, a, need < cap ? need : cap, use_pdl && need >= cap, st);
+    const long long blocks = need < cap ? need : cap;
+    const bool pdl = use_pdl && need >= cap;
+    return baked ? launch_group_wpb<MODE, GT, 4, true>(c, d, b, a, blocks, pdl, st)
+                 : launch_group_wpb<MODE, GT, 4, false>(c, d, b, a, blocks, pdl, st);
 }
 
 static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, int N, float s_max, int comm_inf,
@@ -1226,14 +1276,34 @@ static int dispatch_step(const MrsConfig& c, const MrsBuffers& b, StepArgs a, cu
     const Derived d = make_derived(c);
     if (c.N <= 32) {
         a.G = pow2ceil(c.N);
+        const size_t S = (size_t)c.E * c.N;
+        a.xstride = (long long)(S * (size_t)state_dim(c.state_layout));
+        a.astride = (long long)(S * (size_t)c.N);
+        a.X0 = (b.X_tape && c.state_layout != MRS_X_NONE) ? b.X_tape + (size_t)a.slot_x * (size_t)a.xstride : nullptr;
+        a.A0 = b.A_tape ? b.A_tape + (size_t)a.slot_a * (size_t)a.astride : nullptr;
         const int gpw = 32 / a.G;
-        a.nchunks = (c.E + gpw - 1) / gpw;
-        switch (c.N) {   // power-of-two swarms get the unrolled pair loops
-            case 8:  return launch_group<MODE, 8>(c, d, b, a, st);
-            case 16: return launch_group<MODE, 16>(c, d, b, a, st);
-            case 32: return launch_group<MODE, 32>(c, d, b, a, st);
-            default: return launch_group<MODE, 0>(c, d, b, a, st);
+        const int nchunks = (c.E + gpw - 1) / gpw;
+        a.chunk_lo = 0;
+        a.nchunks = nchunks;
+        if (c.N != 8 && c.N != 16 && c.N != 32) return launch_group<MODE, 0>(c, d, b, a, st);
+        // power-of-two swarms: unrolled pair loops over FULL chunks (32 valid slots); a ragged last chunk
+        // (E not a multiple of 32/N) goes to the run-time-width kernel as a one-chunk launch
+        const int nfull = c.E / gpw;
+        int rc = MRS_OK;
+        if (nfull > 0) {
+            a.nchunks = nfull;
+            switch (c.N) {
+                case 8:  rc = launch_group<MODE, 8>(c, d, b, a, st); break;
+                case 16: rc = launch_group<MODE, 16>(c, d, b, a, st); break;
+                default: rc = launch_group<MODE, 32>(c, d, b, a, st); break;
+            }
         }
+        if (rc == MRS_OK && nfull < nchunks) {
+            a.chunk_lo = nfull;
+            a.nchunks = nchunks;
+            rc = launch_group<MODE, 0>(c, d, b, a, st);
+        }
+        return rc;
     }
     return launch_tiled<MODE>(c, d, b, a, st);
 }
@@ -1253,9 +1323,16 @@ static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
     a.slot_x = slot_x;
     a.slot_a = slot_a;
     a.G = 0;
+    a.chunk_lo = 0;
     a.nchunks = 0;
+    a.X0 = a.A0 = nullptr;
+    a.xstride = a.astride = 0;
     if ((unsigned long long)cfg->E * cfg->N * (cfg->N > 18 ? cfg->N : 18) >= 0xffffffffull) return MRS_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+#ifdef MRS_DEV_ONLY_MODE     // development builds: one action mode only (compile time / 8)
+    if (cfg->action_type != MRS_DEV_ONLY_MODE) return MRS_ERR_UNSUPPORTED;
+    return dispatch_step<MRS_DEV_ONLY_MODE>(*cfg, *bufs, a, st);
+#else
     switch (cfg->action_type) {
         case MRS_SET_TARGET_VEL:   return dispatch_step<MRS_SET_TARGET_VEL>(*cfg, *bufs, a, st);
         case MRS_SET_TARGET_POS:   return dispatch_step<MRS_SET_TARGET_POS>(*cfg, *bufs, a, st);
@@ -1267,6 +1344,7 @@ static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
         case MRS_NO_ACTION:        return dispatch_step<MRS_NO_ACTION>(*cfg, *bufs, a, st);
     }
     return MRS_ERR_ARG;
+#endif
 }
 
 }  // namespace mrs
@@ -1388,6 +1466,18 @@ int mrs_default_config(MrsConfig* cfg) {
     p.col_radius = 0.06f; p.col_halfheight = 0.0125f; p.col_margin = 0.001f;
     p.ground_contact = 1; p.agent_contact = 1;
     p.agent_radius = 0.3f;
+    return MRS_OK;
+}
+
+int mrs_config_is_baked(const MrsConfig* cfg) {
+    if (check_cfg(cfg)) return 0;
+    return config_is_baked(*cfg, make_derived(*cfg)) ? 1 : 0;
+}
+
+int mrs_debug_derived(const MrsConfig* cfg, void* out, size_t out_bytes) {
+    if (!cfg || !out || out_bytes != sizeof(Derived)) return MRS_ERR_ARG;
+    const Derived d = make_derived(*cfg);
+    memcpy(out, &d, sizeof(Derived));
     return MRS_OK;
 }
 

@@ -85,6 +85,8 @@ _SIGNATURES = {
     'mrs_sizeof_config': (C.c_size_t, []),
     'mrs_sizeof_buffers': (C.c_size_t, []),
     'mrs_default_config': (C.c_int, [C.POINTER(MrsConfig)]),
+    'mrs_config_is_baked': (C.c_int, [C.POINTER(MrsConfig)]),
+    'mrs_debug_derived': (C.c_int, [C.POINTER(MrsConfig), C.c_void_p, C.c_size_t]),
     'mrs_step': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'mrs_step_many': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p]),

@@ -56,6 +56,36 @@ def test_struct_mirror_and_defaults():
     assert lib.mrs_state_dim(_abi.X_POS_VEL) == 6 and lib.mrs_state_dim(_abi.X_FULL) == 13
 
 
+def test_baked_constants_match_the_library_defaults():
+    """csrc/mrs_baked.cuh (immediates of the specialised kernels) is generated from the library's own
+    mrs_default_config + host derivation: the committed header must be current, the default configuration
+    must select the baked kernels and any other value must not."""
+    _abi = _lib()
+    lib = _abi.lib()
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rc = subprocess.run([sys.executable, os.path.join(root, 'tools', 'gen_baked.py'), '--check']).returncode
+    assert rc == 0, 'mrs_baked.cuh is stale: run tools/gen_baked.py and rebuild'
+    cfg = _abi.default_config()
+    cfg.E, cfg.N, cfg.K, cfg.L = 7, 5, 2, 9                       # run-time fields do not matter
+    cfg.comm_range = 1.25
+    assert lib.mrs_config_is_baked(ctypes.byref(cfg)) == 1
+    for poke in ('dt', 'gravity'):
+        c2 = _abi.default_config()
+        setattr(c2, poke, float(np.nextafter(np.float32(getattr(c2, poke)), np.float32(np.inf))))
+        assert lib.mrs_config_is_baked(ctypes.byref(c2)) == 0, poke
+    c3 = _abi.default_config()
+    c3.quad.kf = float(np.nextafter(np.float32(c3.quad.kf), np.float32(1)))
+    assert lib.mrs_config_is_baked(ctypes.byref(c3)) == 0
+    c4 = _abi.default_config()
+    c4.phys.gyro = 0
+    assert lib.mrs_config_is_baked(ctypes.byref(c4)) == 0
+    c5 = _abi.default_config()
+    c5.quad.nnls_tab[3] = 0.5                                      # tables are read at run time: still baked
+    assert lib.mrs_config_is_baked(ctypes.byref(c5)) == 1
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
 def test_no_cpu_fallback():
     import mrsgym_b200 as M

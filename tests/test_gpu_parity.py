@@ -493,9 +493,10 @@ def test_full_size_c5_subset_vs_oracle():
                       ptol=1e-4, vtol=1e-3)
 
 
-@pytest.mark.parametrize('E,N', [(1, 1), (3, 31), (2, 33), (1, 2), (257, 5)])
+@pytest.mark.parametrize('E,N', [(1, 1), (3, 31), (2, 33), (1, 2), (257, 5), (3, 8), (1, 16), (4101, 8), (9, 16)])
 def test_ragged_shapes_one_step(E, N):
-    """group widths that do not fill a warp, the first wide-path size, single agent"""
+    """group widths that do not fill a warp, the first wide-path size, single agent; N = 8 / 16 with a ragged
+    last warp-chunk (full chunks go to the unrolled kernel, the tail to the run-time-width kernel)"""
     rng = np.random.default_rng(80 + N)
     st = H.random_state(rng, E, N, spacing=0.9)
     act = H.random_actions(rng, 'set_target_vel', 1, E, N)
@@ -507,3 +508,37 @@ def test_ragged_shapes_one_step(E, N):
     _check_delta('ragged E%d N%d' % (E, N), st, H.read_state(sw), H.spec_state(ref))
     X = sw.X_window()[0].cpu().numpy()
     np.testing.assert_array_equal(sw.A_window()[0].cpu().numpy(), spec.adjacency(X[..., :3], 1.5))
+
+
+@pytest.mark.parametrize('mode', ['set_speeds', 'set_target_pos', 'set_target_vel', 'set_control', 'set_target_ori', 'set_force'])
+@pytest.mark.parametrize('E,N', [(67, 8), (5, 3)])
+def test_baked_kernels_agree_with_generic_kernels(mode, E, N):
+    """The default model runs kernels with the constants as immediates (mrs_config_is_baked); a configuration
+    that differs in a field this mode never reads runs the generic kernels on the same numbers.  Same
+    arithmetic: A bit-exact, states equal to float32 rounding of differently contracted expressions."""
+    import ctypes
+    T, K, R = 12, 2, 1.5
+    rng = np.random.default_rng(91)
+    st = H.random_state(rng, E, N, spacing=0.8)
+    act = _dev(H.random_actions(rng, mode, T, E, N, start_pos=st['pos']))
+    a = _swarm(E, N, mode, K, R, tape_slots=T + K + 1)
+    b = _swarm(E, N, mode, K, R, tape_slots=T + K + 1)
+    assert a.lib.mrs_config_is_baked(ctypes.byref(a.cfg)) == 1
+    if mode == 'set_control':
+        b.cfg.quad.pos_p = 1.25          # position gain: unused by set_control
+    else:
+        b.cfg.quad.arm = 0.04            # arm length: only set_control scales torques with it
+    assert b.lib.mrs_config_is_baked(ctypes.byref(b.cfg)) == 0
+    H.upload_state(a, st)
+    H.upload_state(b, st)
+    a.step(act[0])
+    b.step(act[0])
+    ga, gb = H.read_state(a), H.read_state(b)
+    for k in ('pos', 'vel', 'angvel', 'quat'):
+        np.testing.assert_allclose(ga[k], gb[k], rtol=2e-6, atol=1e-6, err_msg='%s %s' % (mode, k))
+    a.step_many(act[1:].contiguous(), T - 1)
+    b.step_many(act[1:].contiguous(), T - 1)
+    ga, gb = H.read_state(a), H.read_state(b)
+    for k in ('pos', 'vel'):
+        np.testing.assert_allclose(ga[k], gb[k], rtol=1e-4, atol=1e-4, err_msg='%s %s after %d steps' % (mode, k, T))
+    assert a.read_status() == 0 and b.read_status() == 0
