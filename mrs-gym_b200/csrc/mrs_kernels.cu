@@ -368,13 +368,13 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 3; ++i) k.io[i] = k.ip[i] = k.iv[i] = k.lve[i] = k.dve[i] = k.ltv[i] = 0.f;
         }
-        unsigned status = 0;
-        unsigned n_agent_rows = 0, n_ground = 0;
-        float rpm[4] = {0.f, 0.f, 0.f, 0.f};
-
         float* Xs = a.X0;       // tape slots of step t (they move down one slot per step)
         float* As = a.A0;
         for (int t = 0; t < a.T; ++t, Xs -= a.xstride, As -= a.astride) {
+            // per-step event word: the registers behind it live only as long as the step needs them
+            unsigned status = 0;
+            unsigned n_agent_rows = 0, n_ground = 0;
+            float rpm[4];
             float act[4];
             bool nan_act = false;
             if (kStage && t == 0) {
@@ -396,6 +396,10 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             float R[9];
             quat_to_mat(st, R);
             action_to_rpm<MODE>(c, c_in.quad, d, st, R, act, k, rpm);
+            if (b.rpm && MODE != MRS_NO_ACTION && valid) {       // optional Quadcopter.speeds mirror
+#pragma unroll
+                for (int i = 0; i < 4; ++i) *plane_ptr(b.rpm + s, S, i) = rpm[i];
+            }
 
             // ---- pair pass 1: downwash + contact proximity on the pre-step positions
             __syncwarp();
@@ -416,7 +420,6 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                     }
                 }
             }
-            const float p0x = st.px, p0y = st.py, p0z = st.pz;
             apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
 
             // ---- pair pass 2 (rare): sphere-sphere contact on the unconstrained velocities
@@ -424,6 +427,8 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                 wvel[lane] = make_float4(st.vx, st.vy, st.vz, 0.f);
                 __syncwarp();
                 if (near) {
+                    // st.p still is the pre-step position (integrate comes later)
+                    const float p0x = st.px, p0y = st.py, p0z = st.pz;
                     float acc[3] = {0.f, 0.f, 0.f};
                     for (int r = 1; r < G; ++r) {
                         const int j = ai ^ r;
@@ -482,6 +487,24 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                     }
                 }
             }
+            // status / statistics: warp-reduce, then CTA-level shared-memory counters; the global atomics
+            // happen once per CTA at the end.  (A swarm resting on the ground reports a ground contact per
+            // agent per step: with one global atomic per warp-chunk that was 10 k same-address L2 atomics
+            // per launch at C5 and cost ~15 % of the step.)
+            if (!valid) { status = 0; n_agent_rows = 0; n_ground = 0; }
+            const unsigned any_status = __reduce_or_sync(kFull32, status);
+            const unsigned events = __reduce_or_sync(kFull32, n_agent_rows | n_ground);
+            if (any_status | events) {
+                const unsigned sum_rows = __reduce_add_sync(kFull32, n_agent_rows);
+                const unsigned sum_gnd = __reduce_add_sync(kFull32, n_ground);
+                if (lane == 0) {
+                    if (any_status) atomicOr(&sh_events[0], any_status);
+                    if (sum_rows) atomicAdd(&sh_events[1], sum_rows);
+                    if (sum_gnd) atomicAdd(&sh_events[2], sum_gnd);
+                    if (any_status & MRS_STATUS_NONFINITE) atomicAdd(&sh_events[3], 1u);
+                    if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(&sh_events[4], 1u);
+                }
+            }
         }
 
         if (valid) {
@@ -492,33 +515,10 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             *plane_ptr(p0, S, 7) = st.vx; *plane_ptr(p0, S, 8) = st.vy; *plane_ptr(p0, S, 9) = st.vz;
             *plane_ptr(p0, S, 10) = st.wx; *plane_ptr(p0, S, 11) = st.wy; *plane_ptr(p0, S, 12) = st.wz;
             store_ctrl<MODE>(b.ctrl, S, s, k);
-            if (b.rpm && MODE != MRS_NO_ACTION) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) *plane_ptr(b.rpm + s, S, i) = rpm[i];
-            }
-        } else {
-            status = 0; n_agent_rows = 0; n_ground = 0;
         }
 #ifdef MRS_TRACE
         stamp();
 #endif
-        // status / statistics: warp-reduce, then CTA-level shared-memory counters; the global atomics
-        // happen once per CTA at the end.  (A swarm resting on the ground reports a ground contact per
-        // agent per step: with one global atomic per warp-chunk that was 10 k same-address L2 atomics
-        // per launch at C5 and cost ~15 % of the step.)
-        const unsigned any_status = __reduce_or_sync(kFull32, status);
-        const unsigned events = __reduce_or_sync(kFull32, n_agent_rows | n_ground);
-        if (any_status | events) {
-            const unsigned sum_rows = __reduce_add_sync(kFull32, n_agent_rows);
-            const unsigned sum_gnd = __reduce_add_sync(kFull32, n_ground);
-            if (lane == 0) {
-                if (any_status) atomicOr(&sh_events[0], any_status);
-                if (sum_rows) atomicAdd(&sh_events[1], sum_rows);
-                if (sum_gnd) atomicAdd(&sh_events[2], sum_gnd);
-                if (any_status & MRS_STATUS_NONFINITE) atomicAdd(&sh_events[3], 1u);
-                if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(&sh_events[4], 1u);
-            }
-        }
         const int chunk_next2 = resolve_fetch(fetch_ticket, chunk_next);
         chunk = chunk_next;
         chunk_next = chunk_next2;
