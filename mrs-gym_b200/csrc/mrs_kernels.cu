@@ -218,14 +218,13 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     constexpr bool kFull = GT != 0;
     constexpr bool kStage = MRS_PREFETCH && kFull;
     constexpr int kStageFloats = mode_stage_floats<MODE>();
-    float4* sh_pos = reinterpret_cast<float4*>(smem_raw);
-    float4* sh_vel = sh_pos + WPB * 32;
-    float* sh_stage = reinterpret_cast<float*>(sh_vel + WPB * 32);
+    float4* sh_tile = reinterpret_cast<float4*>(smem_raw);          // per warp: 32 positions | 32 velocities (1 KB)
+    float* sh_stage = reinterpret_cast<float*>(sh_tile + WPB * 64);
     __shared__ int sh_counter;
     __shared__ unsigned sh_events[5];       // CTA-level status word + the four statistics counters
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float4* wpos = sh_pos + wib * 32;
-    float4* wvel = sh_vel + wib * 32;
+    float4* wpos = sh_tile + wib * 64;
+    float4* wvel = wpos + 32;
     float* stage = sh_stage + (kStage ? wib * kStageFloats : 0);
     const int G = GT ? GT : a.G;
     const int N = GT ? GT : c.N;
@@ -449,6 +448,8 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
 
             }
             // ---- observation: newest X slice and newest A slice into their tape slots
+            // (X rows staged through shared memory and written as whole 16-byte pieces were measured: neutral
+            // at C5, 18.4 vs 18.1 us -- unlike the A rows below, the float2 stores are not the limiter)
             if (a.X0 && valid) write_X(Xs, c.state_layout, s, st);
             if (a.A0) {
                 float* Arow = As + (size_t)s * N;
@@ -459,7 +460,34 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                     __syncwarp();
                     wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
                     __syncwarp();
-                    if (valid) {
+                    if constexpr (GT != 0) {
+                        // Lane pair (2k, 2k+1) shares the two rows 2k, 2k+1 of A: the even lane computes the
+                        // even column quads of BOTH rows, the odd lane the odd quads.  One STG.128 of the pair
+                        // then covers 32 contiguous bytes, i.e. whole 32-byte sectors (a lane writing its own
+                        // row alone sends every sector twice, half filled), and every column position read
+                        // from shared memory serves two rows.
+                        const int h = lane & 1;
+                        const float4 r0 = wpos[lane & ~1], r1 = wpos[lane | 1];
+                        float* Arow0 = As + (size_t)(s & ~1u) * GT;
+                        const int d0 = (ai & ~1) - 4 * h;          // column of row 0's diagonal relative to quad h
+#pragma unroll
+                        for (int qq = 0; qq < GT / 8; ++qq) {       // this lane's quads: h, h + 2, ...
+                            const int col = 8 * qq + 4 * h;
+                            float4 pj[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) pj[u] = wpos[gb + col + u];
+                            float v0[4], v1[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float h0 = adjacency_pair(r0.x, r0.y, r0.z, pj[u].x, pj[u].y, pj[u].z, d.s_max);
+                                const float h1 = adjacency_pair(r1.x, r1.y, r1.z, pj[u].x, pj[u].y, pj[u].z, d.s_max);
+                                v0[u] = (8 * qq + u == d0) ? 0.f : h0;
+                                v1[u] = (8 * qq + u == d0 + 1) ? 0.f : h1;
+                            }
+                            MRS_TAPE_ST(reinterpret_cast<float4*>(Arow0 + col), make_float4(v0[0], v0[1], v0[2], v0[3]));
+                            MRS_TAPE_ST(reinterpret_cast<float4*>(Arow0 + GT + col), make_float4(v1[0], v1[1], v1[2], v1[3]));
+                        }
+                    } else if (valid) {
                         if ((N & 3) == 0) {
 #pragma unroll 2
                             for (int j = 0; j < N; j += 4) {
@@ -492,9 +520,8 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             // agent per step: with one global atomic per warp-chunk that was 10 k same-address L2 atomics
             // per launch at C5 and cost ~15 % of the step.)
             if (!valid) { status = 0; n_agent_rows = 0; n_ground = 0; }
-            const unsigned any_status = __reduce_or_sync(kFull32, status);
-            const unsigned events = __reduce_or_sync(kFull32, n_agent_rows | n_ground);
-            if (any_status | events) {
+            if (__reduce_or_sync(kFull32, status | n_agent_rows | n_ground)) {      // rare in free flight
+                const unsigned any_status = __reduce_or_sync(kFull32, status);
                 const unsigned sum_rows = __reduce_add_sync(kFull32, n_agent_rows);
                 const unsigned sum_gnd = __reduce_add_sync(kFull32, n_ground);
                 if (lane == 0) {
