@@ -205,6 +205,11 @@ __device__ __forceinline__ const float* plane_ptr(const float* p0, unsigned S, i
     return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p0) + (unsigned long long)S * (unsigned)(pl * 4));
 }
 
+// dynamic shared memory of one warp of the group kernel: pair tile (+ prefetch stage for full chunks)
+template <int MODE, int GT> __host__ __device__ constexpr int group_warp_smem_bytes() {
+    return 1024 + ((MRS_PREFETCH && GT != 0) ? mode_stage_floats<MODE>() * 4 : 0);
+}
+
 template <int MODE, int GT, int WPB, bool BAKED>
 __global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : 1)
 step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant__ Derived d_in, const MrsBuffers b,
@@ -217,15 +222,16 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool kFull = GT != 0;
     constexpr bool kStage = MRS_PREFETCH && kFull;
-    constexpr int kStageFloats = mode_stage_floats<MODE>();
-    float4* sh_tile = reinterpret_cast<float4*>(smem_raw);          // per warp: 32 positions | 32 velocities (1 KB)
-    float* sh_stage = reinterpret_cast<float*>(sh_tile + WPB * 64);
-    __shared__ int sh_counter;
+    // shared memory, one contiguous region per warp so that every address is one per-warp base plus an
+    // immediate: [32 positions | 32 velocities] (the pair tile, 1 KB) [prefetch stage]
+    constexpr int kWarpBytes = group_warp_smem_bytes<MODE, GT>();
+    __shared__ int sh_counter, sh_hi;
     __shared__ unsigned sh_events[5];       // CTA-level status word + the four statistics counters
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float4* wpos = sh_tile + wib * 64;
+    unsigned char* wbase = smem_raw + wib * kWarpBytes;
+    float4* wpos = reinterpret_cast<float4*>(wbase);
     float4* wvel = wpos + 32;
-    float* stage = sh_stage + (kStage ? wib * kStageFloats : 0);
+    float* stage = reinterpret_cast<float*>(wbase + 1024);
     const int G = GT ? GT : a.G;
     const int N = GT ? GT : c.N;
     const int E = c.E;
@@ -237,54 +243,59 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     const MrsPhysicsParams& ph = c.phys;
     const bool pair_contact = ph.agent_contact && N > 1;
 
-    // Work distribution (see the comment above the kernel) over the chunks [a.chunk_lo, a.nchunks): two
-    // static rounds, then the CTA-local counter.  The hand-out for the chunk after next is issued at the
-    // top of an iteration (shared-memory atomic) and consumed at the bottom, so the stage prefetch of the
-    // next chunk can always be issued immediately.
+    // Work distribution (see the comment above the kernel) over the chunks [a.chunk_lo, a.nchunks).
+    // kLocal: the CTA owns the contiguous share [cta_lo, cta_hi) and its warps draw chunk indices from
+    // a shared-memory counter; a warp always knows its next chunk (the stage prefetch needs it) and
+    // draws the one after next at the top of an iteration, so the atomic's latency is never waited for.
     constexpr bool kLocal = WPB > 4;
     const int gw = blockIdx.x * WPB + wib;
-    const int nwork = a.nchunks - a.chunk_lo;
-    const int cta_lo = a.chunk_lo + (kLocal ? (int)(((long long)blockIdx.x * nwork) / gridDim.x) : 0);
-    const int cta_hi = kLocal ? a.chunk_lo + (int)(((long long)(blockIdx.x + 1) * nwork) / gridDim.x) : a.nchunks;
     if (threadIdx.x < 5) sh_events[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) sh_counter = 0;
+    if (threadIdx.x == 0) {
+        const int nwork = a.nchunks - a.chunk_lo;
+        sh_counter = a.chunk_lo + (int)(((long long)blockIdx.x * nwork) / gridDim.x);
+        sh_hi = a.chunk_lo + (int)(((long long)(blockIdx.x + 1) * nwork) / gridDim.x);
+    }
     __syncthreads();
-    auto issue_fetch = [&]() -> int {
-        int v = 0;
-        if (kLocal && lane == 0) v = atomicAdd(&sh_counter, 1);
+    // lane 0 draws a chunk index (-1 when the share is used up); the others get it by shuffle later
+    auto draw = [&]() -> int {
+        int v = -1;
+        if (lane == 0) {
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;"
+                         : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(&sh_counter)) : "memory");
+            v = (v < sh_hi) ? v : -1;
+        }
         return v;
     };
-    auto resolve_fetch = [&](int v, int cur_next) -> int {
-        int nx;
-        if (kLocal) nx = cta_lo + 2 * WPB + __shfl_sync(kFull32, v, 0);
-        else nx = cur_next + wtotal;
-        return (cur_next >= 0 && nx < cta_hi) ? nx : -1;
-    };
-    // chunk = 32 consecutive agent slots (kFull).  Piece q (16 B) of the stage lives at float offset
-    // 4 q: q < 104 state (plane q >> 3, sub-piece q & 7), then 8 pieces per PID plane, then the actions
-    // (32 * ACTION_DIM contiguous floats).  Lane l moves pieces l, l + 32, ...: its plane advances by 4
-    // per round, so all global addresses are one 32-bit element index (lane part + round part + chunk
-    // part) widened once per piece.
+    // chunk = 32 consecutive agent slots (kFull).  The stage is filled in 16-byte pieces, piece q at float
+    // offset 4 q, lane l moves pieces l, l + 32, ...:  [0, 96) state planes 0-11 (plane q >> 3, sub-piece
+    // q & 7: a lane's plane advances by 4 per round, so its element index is lane part + round part +
+    // chunk part), then the chunk's actions (32 * ACTION_DIM contiguous floats: one whole round for
+    // ACTION_DIM 4), then plane 12, then 8 pieces per PID plane.
     constexpr int kNC = mode_nctrl<MODE>();
     constexpr int kA = ModeTraits<MODE>::A;
-    constexpr int kStatePieces = 8 * 13, kCtrlPieces = 8 * kNC, kPieces = kStatePieces + kCtrlPieces + 8 * kA;
+    constexpr int kActBeg = 96, kActEnd = kActBeg + 8 * kA;       // piece ranges
+    constexpr int kP12Beg = kActEnd, kP12End = kP12Beg + 8;
+    constexpr int kCtlBeg = kP12End, kCtlEnd = kCtlBeg + 8 * kNC;
+    constexpr int kPieces = kCtlEnd;
+    static_assert(kPieces * 4 == mode_stage_floats<MODE>(), "stage layout");
     const unsigned lane_el = (unsigned)(lane >> 3) * S + (unsigned)(lane & 7) * 4u;   // plane (l>>3), sub-piece (l&7)
     auto prefetch = [&](int chunk) {
         const unsigned s0 = (unsigned)chunk * 32u;
 #pragma unroll
         for (int i = 0; i < (kPieces + 31) / 32; ++i) {
             const int q = lane + 32 * i;
-            if (32 * i + 31 < kStatePieces || q < kStatePieces) {
-                if (32 * i < kStatePieces) cp_async16(stage + 4 * q, b.state + (lane_el + s0 + (unsigned)(4 * i) * S));
-            }
-            if (32 * i + 31 >= kStatePieces && 32 * i < kStatePieces + kCtrlPieces && q >= kStatePieces &&
-                q < kStatePieces + kCtrlPieces) {
-                const int pl = (q - kStatePieces) >> 3;
-                cp_async16(stage + 4 * q, b.ctrl + ((unsigned)mode_ctrl_plane<MODE>(pl) * S + s0 + (unsigned)(q & 7) * 4u));
-            }
-            if (32 * i + 31 >= kStatePieces + kCtrlPieces && q >= kStatePieces + kCtrlPieces && q < kPieces) {
-                const int aq = q - (kStatePieces + kCtrlPieces);
-                cp_async16(stage + 4 * q, a.actions + ((size_t)s0 * kA + (unsigned)aq * 4u));
+            const int lo = 32 * i, hi = 32 * i + 31;       // compile-time after unrolling: the tests below fold
+            if (hi < kActBeg) {
+                cp_async16(stage + 4 * q, b.state + (lane_el + s0 + (unsigned)(4 * i) * S));
+            } else {
+                if (lo < kActEnd && hi >= kActBeg && (lo >= kActBeg || q >= kActBeg) && (hi < kActEnd || q < kActEnd))
+                    cp_async16(stage + 4 * q, a.actions + (s0 * (unsigned)kA + (unsigned)(q - kActBeg) * 4u));
+                if (lo < kP12End && hi >= kP12Beg && (lo >= kP12Beg || q >= kP12Beg) && (hi < kP12End || q < kP12End))
+                    cp_async16(stage + 4 * q, b.state + (12u * S + s0 + (unsigned)(q - kP12Beg) * 4u));
+                if (kNC > 0 && lo < kCtlEnd && hi >= kCtlBeg && (lo >= kCtlBeg || q >= kCtlBeg) && (hi < kCtlEnd || q < kCtlEnd)) {
+                    const int cq = q - kCtlBeg;
+                    cp_async16(stage + 4 * q, b.ctrl + ((unsigned)mode_ctrl_plane<MODE>(cq >> 3) * S + s0 + (unsigned)(cq & 7) * 4u));
+                }
             }
         }
         cp_async_commit();
@@ -315,13 +326,19 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
 #ifdef MRS_TRACE
     stamp();
 #endif
-    const int first = kLocal ? cta_lo + wib : a.chunk_lo + gw;
-    const int stride0 = kLocal ? WPB : wtotal;
-    int chunk = first < cta_hi ? first : -1;
-    int chunk_next = (chunk >= 0 && first + stride0 < cta_hi) ? first + stride0 : -1;
+    int chunk, chunk_next;
+    if (kLocal) {
+        chunk = __shfl_sync(kFull32, draw(), 0);
+        chunk_next = __shfl_sync(kFull32, chunk >= 0 ? draw() : -1, 0);
+    } else {
+        chunk = a.chunk_lo + gw;
+        chunk_next = chunk + wtotal;
+        if (chunk >= a.nchunks) chunk = -1;
+        if (chunk_next >= a.nchunks) chunk_next = -1;
+    }
     if (kStage && chunk >= 0) prefetch(chunk);
     while (chunk >= 0) {
-        const int fetch_ticket = (chunk_next >= 0) ? issue_fetch() : 0;   // warp-uniform condition
+        const int ticket = (kLocal && chunk_next >= 0) ? draw() : -1;   // the chunk after next; warp-uniform condition
         // kFull: the chunk is 32 consecutive valid slots; else lanes >= N of a group (and envs >= E) idle
         const int e = chunk * gpw + (lane / G);
         const bool valid = kFull ? true : ((e < E) && (ai < N));
@@ -337,8 +354,8 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             st.qx = stage[3 * 32 + lane]; st.qy = stage[4 * 32 + lane]; st.qz = stage[5 * 32 + lane];
             st.qw = stage[6 * 32 + lane];
             st.vx = stage[7 * 32 + lane]; st.vy = stage[8 * 32 + lane]; st.vz = stage[9 * 32 + lane];
-            st.wx = stage[10 * 32 + lane]; st.wy = stage[11 * 32 + lane]; st.wz = stage[12 * 32 + lane];
-            const float* cs = stage + 13 * 32 + lane;
+            st.wx = stage[10 * 32 + lane]; st.wy = stage[11 * 32 + lane]; st.wz = stage[4 * kP12Beg + lane];
+            const float* cs = stage + 4 * kCtlBeg + lane;
             if constexpr (ModeTraits<MODE>::io) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) k.io[i] = cs[i * 32];
@@ -354,7 +371,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                     k.dve[i] = cs[(9 + i) * 32]; k.ltv[i] = cs[(12 + i) * 32];
                 }
             }
-            const float* as = stage + (13 + kNC) * 32 + kA * lane;
+            const float* as = stage + 4 * kActBeg + kA * lane;
             if constexpr (kA == 4) act0 = *reinterpret_cast<const float4*>(as);
             if constexpr (kA == 3) act0 = make_float4(as[0], as[1], as[2], 0.f);
             __syncwarp();           // everyone has read its column before the stage is refilled
@@ -546,9 +563,12 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
 #ifdef MRS_TRACE
         stamp();
 #endif
-        const int chunk_next2 = resolve_fetch(fetch_ticket, chunk_next);
         chunk = chunk_next;
-        chunk_next = chunk_next2;
+        if (kLocal) {
+            chunk_next = __shfl_sync(kFull32, ticket, 0);
+        } else {
+            chunk_next = (chunk >= 0 && chunk + wtotal < a.nchunks) ? chunk + wtotal : -1;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1158,9 +1178,7 @@ static bool config_is_baked(const MrsConfig& c, const Derived& d) {
 template <int MODE, int GT, int WPB, bool BAKED>
 static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
                             bool pdl, cudaStream_t st) {
-    constexpr bool kStage = MRS_PREFETCH && GT != 0;
-    constexpr size_t smem = (size_t)WPB * 32 * 2 * sizeof(float4) +
-                            (kStage ? (size_t)WPB * mode_stage_floats<MODE>() * sizeof(float) : 16);
+    constexpr size_t smem = (size_t)WPB * group_warp_smem_bytes<MODE, GT>();
     static bool configured[64] = {};          // per device: the attribute belongs to the function ON a device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MRS_ERR_CUDA;
