@@ -120,7 +120,7 @@ def cpu_sample_sizes(wname):
     w = WORKLOADS[wname]
     if w['N'] >= 1024:
         return 1, 2          # one env of 4096 agents: ~N^2 pair arrays in numpy
-    return max(1, 4096 // w['N']), 8
+    return max(1, 4096 // w['N']), 800          # ~10 s of CPU work per process (oracle port: ~4.5e5 agent-steps/s/core)
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -347,8 +347,12 @@ def run_gpu(args):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {**workload_config(w, E, world),
                    'launch': ('CUDA graph of %d single-step launches, %d replays' if use_graph else '%d plain launches x %d') % (T, replays),
-                   'l2': 'no flush: per-step streamed bytes (actions+X+A) are distinct every step and exceed L2 over the '
-                         'region; state is re-read as the previous step left it; see l2_flushed'},
+                   'l2': 'inputs larger than L2: the timed region consumes %.0f MB of distinct action buffers and writes '
+                         '%.0f MB of distinct X/A tape slots (L2 = 126 MB); no buffer is re-read across iterations -- the '
+                         'state is loop-carried (written by step t, read by step t+1, as in any rollout).  l2_flushed '
+                         'reports the same step one launch at a time behind a 512 MB read-flush'
+                         % (T * E * N * max(M._abi.ACTION_DIMS[sw.cfg.action_type], 1) * 4 / 1e6,
+                            steps * E * N * (6 + (N if sw.A_tape is not None else 0)) * 4 / 1e6)},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': kernel, 'peak_source': peak_src,
                      'algorithmic_bytes_per_agent_step': w['B'], 'agent_steps_per_launch': E * N,
@@ -386,7 +390,7 @@ def run_reference(args):
     Ep, _ = cpu_sample_sizes(args.workload)
     steps, warmup = args.steps, args.warmup
     # bounded: each "step" here is one env.step of the sample batch (procs x Ep envs)
-    Tc = max(1, min(steps, 16))
+    Tc = max(1, min(steps, 200))
     v, wall, total = cpu_port_throughput(args.workload, procs, Ep, Tc)
     out = {
         'impl': 'reference', 'metric': 'agent-steps/sec', 'value': v, 'unit': 'agent-steps/s',
