@@ -25,8 +25,11 @@
  *                         host writes slot p-1 at each step (descending) so that slots
  *                         [p, p+K] are the reference's newest-first K_HOPS+1 window
  *                         (mrsgym/MRS.py:87-114) with no per-step copy.
- *   scratch float[7][S]   only for N > 32 (unconstrained velocities, pre-step positions,
- *                         contact-proximity flag between the wide-path kernels)
+ *   scratch float[P][S]   only for N > 32 (unconstrained velocities, pre-step positions,
+ *                         contact-proximity flag between the wide-path kernels; for N >= 1024
+ *                         also the per-slice partial sums of the pair pass).  P =
+ *                         mrs_scratch_planes(N): 7, or 7 + 2 * 32 for N >= 1024.  No initial
+ *                         contents required.
  */
 #ifndef MRS_B200_H
 #define MRS_B200_H
@@ -41,7 +44,8 @@ extern "C" {
 #define MRS_STATE_PLANES 13
 #define MRS_CTRL_PLANES 18
 #define MRS_STATS_SLOTS 8
-#define MRS_SCRATCH_PLANES 7
+#define MRS_SCRATCH_PLANES 7          /* N < 1024 */
+#define MRS_SCRATCH_PAIR_SPLITS 32    /* N >= 1024: + 2 * 32 planes of partial pair sums / flags */
 
 /* ACTION_TYPE strings of the reference are method names dispatched by getattr
  * (mrsgym/Environment.py:92 -> mrsgym/Quadcopter.py:26-65). */
@@ -132,7 +136,7 @@ typedef struct {
     float* rpm;                          /* [4][S] or NULL */
     float* X_tape;                       /* [L][E][N][D] or NULL */
     float* A_tape;                       /* [L][E][N][N] or NULL */
-    float* scratch;                      /* [7][S], needed iff N > 32 */
+    float* scratch;                      /* [mrs_scratch_planes(N)][S], needed iff N > 32 */
     unsigned int* status;                /* [1] */
     unsigned long long* stats;           /* [MRS_STATS_SLOTS] */
 } MrsBuffers;
@@ -144,6 +148,9 @@ const char* mrs_strerror(int err);
 int mrs_state_dim(int state_layout);
 /* ACTION_DIM of an action type. */
 int mrs_action_dim(int action_type);
+
+/* Planes of MrsBuffers.scratch a swarm of N agents per env needs (0 for N <= 32). */
+int mrs_scratch_planes(int N);
 
 /* sizeof(MrsConfig) / sizeof(MrsBuffers) as compiled: lets a foreign binding check its mirror. */
 size_t mrs_sizeof_config(void);

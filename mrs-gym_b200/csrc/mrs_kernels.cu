@@ -688,48 +688,123 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
             }
         }
     }
-    if constexpr (LPA <= 32) {
-        dw = group_sum<LPA>(dw);
-        const unsigned gmask = (LPA == 32) ? kFull32 : (((1u << (LPA & 31)) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
-        near = (__ballot_sync(kFull32, near) & gmask) != 0u;
-    } else {
-        // one CTA per agent (N >= 1024): warp sums in a fixed order through shared memory
-        __shared__ float part[kBlock / 32];
-        __shared__ int near_any;
-        if (threadIdx.x == 0) near_any = 0;
-        dw = group_sum<32>(dw);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = dw;
-        if (near) near_any = 1;
-        __syncthreads();
-        dw = 0.f;
+    static_assert(LPA <= 32, "N >= 1024 uses pair_tile_kernel");
+    dw = group_sum<LPA>(dw);
+    const unsigned gmask = (LPA == 32) ? kFull32 : (((1u << (LPA & 31)) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
+    near = (__ballot_sync(kFull32, near) & gmask) != 0u;
+    if (l != 0 || !valid) return;
+    agent_pre<MODE>(c, d, b, actions, S, s, dw, near && pair_contact);
+}
+
+// ------------------------------------------------------------------------------ pair pass for N >= 1024
+// n-body tiling.  A CTA owns 128 agents of one env (one per thread, own position in registers) and one
+// of `nsplit` slices of the partner range; partner positions go through shared memory in tiles of 128
+// and every thread reads the SAME partner (broadcast LDS.128), so a pair costs no global load, no index
+// arithmetic and no shuffle: ~16 instructions without the downwash term, which is skipped per warp when
+// none of its 32 agents can feel this partner (not above, dxy >= 10 m, or exp(-0.5 (dxy/beta)^2)
+// underflowing float32).  Partial sums of slice js go to scratch plane kPairPlane0 + js, the proximity
+// flag to plane kPairPlane0 + nsplit + js; agent_pre_kernel adds them in slice order (deterministic).
+// (The first version gave every agent a whole CTA that walked the partners from the L1-resident position
+// planes: 45 instructions per pair, 29.9 us at N = 4096.)
+constexpr int kPairPlane0 = MRS_SCRATCH_PLANES;      // first partial-sum plane
+constexpr int kPairMaxSplit = MRS_SCRATCH_PAIR_SPLITS;
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+pair_tile_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int jw,
+                 int nsplit) {
+    __shared__ float4 tile[kBlock];
+    const int N = c.N;
+    const unsigned S = (unsigned)c.E * (unsigned)N;
+    const int it = blockIdx.x / nsplit, js = blockIdx.x - it * nsplit;
+    const unsigned env0 = blockIdx.y * (unsigned)N;
+    const int i = it * kBlock + threadIdx.x;
+    const bool valid = i < N;
+    const float* __restrict__ px = b.state + 0 * (size_t)S + env0;
+    const float* __restrict__ py = b.state + 1 * (size_t)S + env0;
+    const float* __restrict__ pz = b.state + 2 * (size_t)S + env0;
+    // an idle lane sits far below everything: no partner is above-and-near, none is close
+    const float pix = valid ? px[i] : 0.f, piy = valid ? py[i] : 0.f, piz = valid ? pz[i] : 3.0e18f;
+    const bool pair_contact = c.phys.agent_contact && N > 1;
+    // 0 < d2 < lim2 as ONE unsigned compare of the float bits (d2 >= 0 or NaN): (bits - 1) < (bits(lim2) - 1);
+    // d2 == 0 is the agent itself (or a coincident partner, which the contact row ignores anyway)
+    const unsigned lim_m1 = __float_as_uint(d.lim2) - 1u;
+    float dw = 0.f;
+    bool near = false;
+    // Tile culling: a tile whose highest partner lies more than the contact range below the lowest agent of
+    // this warp can neither blow on any of them (dz <= 0) nor touch them: skipped as a whole (exact, not a
+    // cut-off).  It pays when the index order follows height; the C4 bench lattice has z as its fastest
+    // index, so no tile is skipped there and the test costs ~1 %.
+    __shared__ float tile_zmax[kBlock / 32];
+    float wz_min = valid ? piz : 3.0e38f;
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; ++w) dw += part[w];
-        near = near_any != 0;
-    }
-    if constexpr (LPA > 32) {
-        // N >= 1024: the per-agent part runs in its own thread-per-agent kernel (agent_pre_kernel); with
-        // one CTA per agent a single lane doing ~500 dependent instructions was the critical path
-        if (threadIdx.x == 0 && valid) {
-            b.scratch[0 * (size_t)S + s] = dw;
-            b.scratch[6 * (size_t)S + s] = (near && pair_contact) ? 1.f : 0.f;
+    for (int o = 16; o > 0; o >>= 1) wz_min = fminf(wz_min, __shfl_xor_sync(kFull32, wz_min, o));
+    const float z_skip = wz_min - sqrtf(d.lim2);
+    const int jbeg = js * jw, jend = min(jbeg + jw, N);
+    for (int j0 = jbeg; j0 < jend; j0 += kBlock) {
+        const int jj = j0 + threadIdx.x;
+        const float4 mine = (jj < jend) ? make_float4(px[jj], py[jj], pz[jj], 0.f) : make_float4(3.0e18f, 0.f, -3.0e18f, 0.f);
+        float zm = mine.z;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(kFull32, zm, o));
+        __syncthreads();
+        tile[threadIdx.x] = mine;
+        if ((threadIdx.x & 31) == 0) tile_zmax[threadIdx.x >> 5] = zm;
+        __syncthreads();
+        const float tz = fmaxf(fmaxf(tile_zmax[0], tile_zmax[1]), fmaxf(tile_zmax[2], tile_zmax[3]));
+        if (tz < z_skip) continue;          // warp-uniform
+#pragma unroll 2
+        for (int jl = 0; jl < kBlock; jl += 4) {
+            float dxy2[4], rz[4];
+            bool live[4], any_live = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 pj = tile[jl + u];
+                const float rx = pj.x - pix, ry = pj.y - piy;
+                rz[u] = pj.z - piz;
+                dxy2[u] = rx * rx + ry * ry;
+                const float d2 = dxy2[u] + rz[u] * rz[u];
+                near = near || (__float_as_uint(d2) - 1u < lim_m1);
+                const float beta = c.quad.dw2 * rz[u] + c.quad.dw3;
+                live[u] = MODE != MRS_NO_ACTION && rz[u] > 0.f && dxy2[u] < 100.f && !(dxy2[u] > 208.f * beta * beta);
+                any_live = any_live || live[u];
+            }
+            if (MODE != MRS_NO_ACTION && __any_sync(kFull32, any_live)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float f = downwash_pair(c.quad, d, dxy2[u], rz[u]);
+                    dw += live[u] ? f : 0.f;
+                }
+            }
         }
-        return;
-    } else {
-        if (l != 0 || !valid) return;
-        agent_pre<MODE>(c, d, b, actions, S, s, dw, near && pair_contact);
     }
+    if (!valid) return;
+    const unsigned s = env0 + (unsigned)i;
+    b.scratch[(size_t)(kPairPlane0 + js) * S + s] = dw;
+    b.scratch[(size_t)(kPairPlane0 + nsplit + js) * S + s] = (near && pair_contact) ? 1.f : 0.f;
 }
 
 // thread-per-agent half of the wide pre pass for N >= 1024 (dw and the proximity flag come from scratch)
 template <int MODE>
 __global__ void __launch_bounds__(kBlock)
 agent_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
-                 const float* __restrict__ actions) {
+                 const float* __restrict__ actions, int nsplit) {
     const unsigned S = (unsigned)c.E * (unsigned)c.N;
     const unsigned s = blockIdx.x * kBlock + threadIdx.x;
     if (s >= S) return;
-    agent_pre<MODE>(c, d, b, actions, S, s, b.scratch[0 * (size_t)S + s], b.scratch[6 * (size_t)S + s] != 0.f);
+    float dw = 0.f, fl = 0.f;
+    for (int j0 = 0; j0 < nsplit; j0 += 8) {       // fixed order: the sum does not depend on the launch shape
+        float pd[8], pf[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {              // independent loads in flight
+            const bool in = j0 + u < nsplit;
+            pd[u] = in ? b.scratch[(size_t)(kPairPlane0 + j0 + u) * S + s] : 0.f;
+            pf[u] = in ? b.scratch[(size_t)(kPairPlane0 + nsplit + j0 + u) * S + s] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { dw += pd[u]; fl += pf[u]; }
+    }
+    agent_pre<MODE>(c, d, b, actions, S, s, dw, fl != 0.f);
 }
 
 template <int LPA>
@@ -1275,6 +1350,21 @@ SideLane* side_lane() {
 }
 }  // namespace
 
+// partner slices of pair_tile_kernel: enough CTAs to fill the GPU, at most kPairMaxSplit partial planes
+static void pair_split(const MrsConfig& c, int* jw, int* nsplit) {
+    const int itiles = (c.N + kBlock - 1) / kBlock;
+    const long long want = 8LL * (sm_count() > 0 ? sm_count() : 148);            // ~8 CTAs per SM
+    long long ns = (want + (long long)itiles * c.E - 1) / ((long long)itiles * c.E);
+    const int max_ns = (c.N + kBlock - 1) / kBlock;                                 // at least one tile per slice
+    if (ns > kPairMaxSplit) ns = kPairMaxSplit;
+    if (ns > max_ns) ns = max_ns;
+    if (ns < 1) ns = 1;
+    int w = (int)((c.N + ns - 1) / ns);
+    w = (w + kBlock - 1) / kBlock * kBlock;                                         // whole tiles
+    *jw = w;
+    *nsplit = (c.N + w - 1) / w;
+}
+
 template <int MODE, int LPA, int LPB>
 static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     const size_t S = (size_t)c.E * c.N;
@@ -1282,10 +1372,17 @@ static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffer
     const unsigned blocks = (unsigned)((S * LPA + kBlock - 1) / kBlock);
     const unsigned blocks_post = (unsigned)((S * LPB + kBlock - 1) / kBlock);
     SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
+    int jw = 0, nsplit = 0;
+    if (LPA > 32) pair_split(c, &jw, &nsplit);
     for (int t = 0; t < a.T; ++t) {
         const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
-        step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
-        if (LPA > 32) agent_pre_kernel<MODE><<<(unsigned)((S + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, d, b, act_t);
+        if constexpr (LPA > 32) {
+            const int itiles = (c.N + kBlock - 1) / kBlock;
+            pair_tile_kernel<MODE><<<dim3((unsigned)(itiles * nsplit), (unsigned)c.E), kBlock, 0, st>>>(c, d, b, jw, nsplit);
+            agent_pre_kernel<MODE><<<(unsigned)((S + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, d, b, act_t, nsplit);
+        } else {
+            step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
+        }
         if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
         step_post_kernel<LPB><<<blocks_post, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
         if (b.A_tape) {
@@ -1308,10 +1405,11 @@ static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffer
 template <int MODE>
 static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     if (!b.scratch) return MRS_ERR_ARG;
-    if ((unsigned long long)c.E * c.N * 128ull >= 0x7fffffffull * (unsigned long long)kBlock) return MRS_ERR_UNSUPPORTED;
+    if ((unsigned long long)c.E * c.N * 32ull >= 0x7fffffffull * (unsigned long long)kBlock) return MRS_ERR_UNSUPPORTED;
+    if (c.N >= 1024 && c.E > 65535) return MRS_ERR_UNSUPPORTED;          // grid.y of pair_tile_kernel
     if (c.N <= 128) return launch_wide_lpa<MODE, 8, 8>(c, d, b, a, st);
     if (c.N < 1024) return launch_wide_lpa<MODE, 32, 32>(c, d, b, a, st);
-    return launch_wide_lpa<MODE, 128, 32>(c, d, b, a, st);     // a whole CTA walks the partners of one agent
+    return launch_wide_lpa<MODE, 128, 32>(c, d, b, a, st);     // n-body tiles (pair_tile_kernel) + agent_pre_kernel
 }
 
 static int pow2ceil(int n) {
@@ -1425,6 +1523,11 @@ int mrs_action_dim(int action_type) {
 }
 
 int mrs_state_dim(int state_layout) { return state_dim(state_layout); }
+
+int mrs_scratch_planes(int N) {
+    if (N <= 32) return 0;
+    return N >= 1024 ? MRS_SCRATCH_PLANES + 2 * MRS_SCRATCH_PAIR_SPLITS : MRS_SCRATCH_PLANES;
+}
 
 size_t mrs_sizeof_config(void) { return sizeof(MrsConfig); }
 size_t mrs_sizeof_buffers(void) { return sizeof(MrsBuffers); }
