@@ -1,10 +1,8 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 Q="--warmup 5 --no-cpu --clock-seconds 0 --e2e-steps 0"
-for w in c4; do
-python bench.py --steps 200 --workload $w $Q > gpurun_out/b60_$w.json 2>>gpurun_out/b60.err; python -c "
+for r in 0 2 3 4 5; do
+MRS_B200_PAIR_RES=$r python bench.py --steps 200 --workload c4 $Q > gpurun_out/b61_$r.json 2>>gpurun_out/b61.err; python -c "
 import json
-d=json.load(open('gpurun_out/b60_$w.json'))
-print('$w value %.3e ms/step %.4f frac %.3f | flushed ms %.4f frac %.3f | many %s'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median'],d['l2_flushed']['frac'],d['step_many'] and '%.3e'%d['step_many']['value']))"
+d=json.load(open('gpurun_out/b61_$r.json'))
+print('res $r value %.3e ms/step %.4f frac %.3f | flushed ms %.4f frac %.3f'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median'],d['l2_flushed']['frac']))"
 done
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/b60_launches_c4.csv python bench.py --workload c4 --steps 20 --warmup 3 --no-cpu --clock-seconds 0 --e2e-steps 2 > gpurun_out/b60_l.log 2>&1
-python tools/ncu_launch_summary.py gpurun_out/b60_launches_c4.csv > gpurun_out/b60_sum.txt; head -6 gpurun_out/b60_sum.txt
+tail -3 gpurun_out/b61.err
