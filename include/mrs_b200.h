@@ -26,10 +26,10 @@
  *                         [p, p+K] are the reference's newest-first K_HOPS+1 window
  *                         (mrsgym/MRS.py:87-114) with no per-step copy.
  *   scratch float[P][S]   only for N > 32 (unconstrained velocities, pre-step positions,
- *                         contact-proximity flag between the wide-path kernels; for N >= 1024
+ *                         contact-proximity flag between the wide-path kernels; for N > 128
  *                         also the per-slice partial sums of the pair pass).  P =
- *                         mrs_scratch_planes(N): 7, or 7 + 2 * 32 for N >= 1024.  No initial
- *                         contents required.
+ *                         mrs_scratch_planes(E, N): 7, or 7 + 2 * slices (<= 32 slices; 1 when
+ *                         E is large) for N > 128.  No initial contents required.
  */
 #ifndef MRS_B200_H
 #define MRS_B200_H
@@ -44,8 +44,8 @@ extern "C" {
 #define MRS_STATE_PLANES 13
 #define MRS_CTRL_PLANES 18
 #define MRS_STATS_SLOTS 8
-#define MRS_SCRATCH_PLANES 7          /* N < 1024 */
-#define MRS_SCRATCH_PAIR_SPLITS 32    /* N >= 1024: + 2 * 32 planes of partial pair sums / flags */
+#define MRS_SCRATCH_PLANES 7          /* N <= 128 */
+#define MRS_SCRATCH_PAIR_SPLITS 32    /* N > 128: + 2 planes (partial pair sum, flag) per partner slice, <= 32 slices */
 
 /* ACTION_TYPE strings of the reference are method names dispatched by getattr
  * (mrsgym/Environment.py:92 -> mrsgym/Quadcopter.py:26-65). */
@@ -136,7 +136,7 @@ typedef struct {
     float* rpm;                          /* [4][S] or NULL */
     float* X_tape;                       /* [L][E][N][D] or NULL */
     float* A_tape;                       /* [L][E][N][N] or NULL */
-    float* scratch;                      /* [mrs_scratch_planes(N)][S], needed iff N > 32 */
+    float* scratch;                      /* [mrs_scratch_planes(E, N)][S], needed iff N > 32 */
     unsigned int* status;                /* [1] */
     unsigned long long* stats;           /* [MRS_STATS_SLOTS] */
 } MrsBuffers;
@@ -149,8 +149,8 @@ int mrs_state_dim(int state_layout);
 /* ACTION_DIM of an action type. */
 int mrs_action_dim(int action_type);
 
-/* Planes of MrsBuffers.scratch a swarm of N agents per env needs (0 for N <= 32). */
-int mrs_scratch_planes(int N);
+/* Planes of MrsBuffers.scratch E envs of N agents need (0 for N <= 32). */
+int mrs_scratch_planes(int E, int N);
 
 /* sizeof(MrsConfig) / sizeof(MrsBuffers) as compiled: lets a foreign binding check its mirror. */
 size_t mrs_sizeof_config(void);

@@ -688,7 +688,7 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
             }
         }
     }
-    static_assert(LPA <= 32, "N >= 1024 uses pair_tile_kernel");
+    static_assert(LPA <= 32, "N > 128 uses pair_tile_kernel");
     dw = group_sum<LPA>(dw);
     const unsigned gmask = (LPA == 32) ? kFull32 : (((1u << (LPA & 31)) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
     near = (__ballot_sync(kFull32, near) & gmask) != 0u;
@@ -696,7 +696,7 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
     agent_pre<MODE>(c, d, b, actions, S, s, dw, near && pair_contact);
 }
 
-// ------------------------------------------------------------------------------ pair pass for N >= 1024
+// ------------------------------------------------------------------------------ pair pass for N > 128
 // n-body tiling.  A CTA owns 128 agents of one env (one per thread, own position in registers) and one
 // of `nsplit` slices of the partner range; partner positions go through shared memory in tiles of 128
 // and every thread reads the SAME partner (broadcast LDS.128), so a pair costs no global load, no index
@@ -716,8 +716,11 @@ pair_tile_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ De
     __shared__ float4 tile[kBlock];
     const int N = c.N;
     const unsigned S = (unsigned)c.E * (unsigned)N;
-    const int it = blockIdx.x / nsplit, js = blockIdx.x - it * nsplit;
-    const unsigned env0 = blockIdx.y * (unsigned)N;
+    const int itiles = (N + kBlock - 1) / kBlock;
+    const unsigned per_env = (unsigned)(itiles * nsplit);
+    const unsigned env = blockIdx.x / per_env, rem = blockIdx.x - env * per_env;
+    const int it = (int)(rem / (unsigned)nsplit), js = (int)(rem - (unsigned)it * (unsigned)nsplit);
+    const unsigned env0 = env * (unsigned)N;
     const int i = it * kBlock + threadIdx.x;
     const bool valid = i < N;
     const float* __restrict__ px = b.state + 0 * (size_t)S + env0;
@@ -1350,19 +1353,19 @@ SideLane* side_lane() {
 }
 }  // namespace
 
-// partner slices of pair_tile_kernel: enough CTAs to fill the GPU, at most kPairMaxSplit partial planes
-static void pair_split(const MrsConfig& c, int* jw, int* nsplit) {
-    const int itiles = (c.N + kBlock - 1) / kBlock;
-    const long long want = 8LL * (sm_count() > 0 ? sm_count() : 148);            // ~8 CTAs per SM
-    long long ns = (want + (long long)itiles * c.E - 1) / ((long long)itiles * c.E);
-    const int max_ns = (c.N + kBlock - 1) / kBlock;                                 // at least one tile per slice
+// partner slices of pair_tile_kernel: ~8 CTAs per SM of a B200, at most kPairMaxSplit partial planes, whole
+// tiles per slice.  A pure function of (E, N): mrs_scratch_planes sizes the caller's scratch from it.
+static void pair_split(int E, int N, int* jw, int* nsplit) {
+    const long long itiles = (N + kBlock - 1) / kBlock;
+    const long long want = 8LL * 148;
+    long long ns = (want + itiles * E - 1) / (itiles * E);
     if (ns > kPairMaxSplit) ns = kPairMaxSplit;
-    if (ns > max_ns) ns = max_ns;
+    if (ns > itiles) ns = itiles;                                                    // at least one tile per slice
     if (ns < 1) ns = 1;
-    int w = (int)((c.N + ns - 1) / ns);
-    w = (w + kBlock - 1) / kBlock * kBlock;                                         // whole tiles
+    int w = (int)((N + ns - 1) / ns);
+    w = (w + kBlock - 1) / kBlock * kBlock;
     *jw = w;
-    *nsplit = (c.N + w - 1) / w;
+    *nsplit = (N + w - 1) / w;
 }
 
 template <int MODE, int LPA, int LPB>
@@ -1373,12 +1376,12 @@ static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffer
     const unsigned blocks_post = (unsigned)((S * LPB + kBlock - 1) / kBlock);
     SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
     int jw = 0, nsplit = 0;
-    if (LPA > 32) pair_split(c, &jw, &nsplit);
+    if (LPA > 32) pair_split(c.E, c.N, &jw, &nsplit);
     for (int t = 0; t < a.T; ++t) {
         const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
         if constexpr (LPA > 32) {
             const int itiles = (c.N + kBlock - 1) / kBlock;
-            pair_tile_kernel<MODE><<<dim3((unsigned)(itiles * nsplit), (unsigned)c.E), kBlock, 0, st>>>(c, d, b, jw, nsplit);
+            pair_tile_kernel<MODE><<<(unsigned)((long long)itiles * nsplit * c.E), kBlock, 0, st>>>(c, d, b, jw, nsplit);
             agent_pre_kernel<MODE><<<(unsigned)((S + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, d, b, act_t, nsplit);
         } else {
             step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
@@ -1406,9 +1409,7 @@ template <int MODE>
 static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     if (!b.scratch) return MRS_ERR_ARG;
     if ((unsigned long long)c.E * c.N * 32ull >= 0x7fffffffull * (unsigned long long)kBlock) return MRS_ERR_UNSUPPORTED;
-    if (c.N >= 1024 && c.E > 65535) return MRS_ERR_UNSUPPORTED;          // grid.y of pair_tile_kernel
     if (c.N <= 128) return launch_wide_lpa<MODE, 8, 8>(c, d, b, a, st);
-    if (c.N < 1024) return launch_wide_lpa<MODE, 32, 32>(c, d, b, a, st);
     return launch_wide_lpa<MODE, 128, 32>(c, d, b, a, st);     // n-body tiles (pair_tile_kernel) + agent_pre_kernel
 }
 
@@ -1524,9 +1525,12 @@ int mrs_action_dim(int action_type) {
 
 int mrs_state_dim(int state_layout) { return state_dim(state_layout); }
 
-int mrs_scratch_planes(int N) {
-    if (N <= 32) return 0;
-    return N >= 1024 ? MRS_SCRATCH_PLANES + 2 * MRS_SCRATCH_PAIR_SPLITS : MRS_SCRATCH_PLANES;
+int mrs_scratch_planes(int E, int N) {
+    if (N <= 32 || E <= 0) return 0;
+    if (N <= 128) return MRS_SCRATCH_PLANES;
+    int jw = 0, nsplit = 0;
+    pair_split(E, N, &jw, &nsplit);
+    return MRS_SCRATCH_PLANES + 2 * nsplit;
 }
 
 size_t mrs_sizeof_config(void) { return sizeof(MrsConfig); }

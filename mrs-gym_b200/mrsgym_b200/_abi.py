@@ -82,7 +82,7 @@ _SIGNATURES = {
     'mrs_strerror': (C.c_char_p, [C.c_int]),
     'mrs_state_dim': (C.c_int, [C.c_int]),
     'mrs_action_dim': (C.c_int, [C.c_int]),
-    'mrs_scratch_planes': (C.c_int, [C.c_int]),
+    'mrs_scratch_planes': (C.c_int, [C.c_int, C.c_int]),
     'mrs_sizeof_config': (C.c_size_t, []),
     'mrs_sizeof_buffers': (C.c_size_t, []),
     'mrs_default_config': (C.c_int, [C.POINTER(MrsConfig)]),

@@ -70,7 +70,7 @@ class Swarm:
         self.rpm = torch.zeros(4, self.S, **z) if keep_rpm else None
         self.X_tape = torch.zeros(self.L, self.E, self.N, max(self.D, 1), **z) if self.D > 0 else None
         self.A_tape = torch.zeros(self.L, self.E, self.N, self.N, **z) if want_A else None
-        self.scratch = torch.zeros(self.lib.mrs_scratch_planes(self.N), self.S, **z) if self.N > 32 else None
+        self.scratch = torch.zeros(self.lib.mrs_scratch_planes(self.E, self.N), self.S, **z) if self.N > 32 else None
         self.status = torch.zeros(1, device=dev, dtype=torch.int32)
         self.stats = torch.zeros(_abi.STATS_SLOTS, device=dev, dtype=torch.int64)
         self.bufs = _abi.MrsBuffers()

@@ -542,3 +542,29 @@ def test_baked_kernels_agree_with_generic_kernels(mode, E, N):
     for k in ('pos', 'vel'):
         np.testing.assert_allclose(ga[k], gb[k], rtol=1e-4, atol=1e-4, err_msg='%s %s after %d steps' % (mode, k, T))
     assert a.read_status() == 0 and b.read_status() == 0
+
+
+@pytest.mark.parametrize('E,N,mode', [(2, 1100, 'set_target_vel'), (1, 1024, 'set_control'), (3, 1025, 'set_speeds')])
+def test_tiled_pair_path_ragged(E, N, mode):
+    """N >= 1024 (pair_tile_kernel + agent_pre_kernel): agent tiles and partner slices that do not divide N,
+    several envs per launch, contact regime (spacing 0.55 < 2 * AGENT_RADIUS + margin) -- one step against the
+    oracle, then the same step again from the same state must reproduce bit for bit (fixed-order partial sums)."""
+    rng = np.random.default_rng(97 + N)
+    st = H.random_state(rng, E, N, spacing=0.55, jitter=0.05)
+    act = H.random_actions(rng, mode, 1, E, N, start_pos=st['pos'])
+    sw = _swarm(E, N, mode, 1, 1.5)
+    H.upload_state(sw, st)
+    sw.step(_dev(act[0]))
+    ref = H.make_spec(E, N, mode, 1, 1.5, st)
+    ref.step(act[0])
+    g1, r1 = H.read_state(sw), H.spec_state(ref)
+    # contact rows switch on thresholds (dist < margin, rhs > 0): allow a float32-sized band
+    for k, tol in (('vel', 2e-4), ('pos', 2e-6), ('angvel', 1e-4)):
+        assert np.max(np.abs(g1[k] - r1[k])) <= tol, k
+    X = sw.X_window()[0].cpu().numpy()
+    np.testing.assert_array_equal(sw.A_window()[0].cpu().numpy(), spec.adjacency(X[..., :3], 1.5))
+    assert sw.read_stats()['agent_contact_rows'] > 0        # sphere contact rows fired
+    sw2 = _swarm(E, N, mode, 1, 1.5)
+    H.upload_state(sw2, st)
+    sw2.step(_dev(act[0]))
+    assert torch.equal(sw.state, sw2.state)

@@ -1,8 +1,10 @@
+python -m pytest tests -x -q -m gpu 2>&1 | tail -5
 Q="--warmup 5 --no-cpu --clock-seconds 0 --e2e-steps 0"
-for r in 0 2 3 4 5; do
-MRS_B200_PAIR_RES=$r python bench.py --steps 200 --workload c4 $Q > gpurun_out/b61_$r.json 2>>gpurun_out/b61.err; python -c "
+for v in base minb6 minb8; do
+  if [ $v = base ]; then L=""; else L="MRS_B200_LIB=$PWD/build_variants/lib_$v.so"; fi
+  env $L python bench.py --steps 200 $Q > gpurun_out/b62_$v.json 2>>gpurun_out/b62.err; python -c "
 import json
-d=json.load(open('gpurun_out/b61_$r.json'))
-print('res $r value %.3e ms/step %.4f frac %.3f | flushed ms %.4f frac %.3f'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median'],d['l2_flushed']['frac']))"
+d=json.load(open('gpurun_out/b62_$v.json'))
+print('$v value %.3e ms/step %.4f frac %.3f | flushed ms %.4f frac %.3f | many %s'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median'],d['l2_flushed']['frac'],d['step_many'] and '%.3e'%d['step_many']['value']))"
 done
-tail -3 gpurun_out/b61.err
+tail -2 gpurun_out/b62.err
