@@ -201,6 +201,16 @@ class Swarm:
         elif actions.device != self.device:
             raise ValueError('actions live on %s, the swarm on %s' % (actions.device, self.device))
 
+    def _step_launches(self, n=1, fused=False):
+        """Kernels the library launches for n steps (bench: gpu_launches).  N <= 32: one fused kernel per step
+        (per call when `fused`: mrs_step_many), plus one for a ragged last warp-chunk when N is 8, 16 or 32 and E
+        is not a multiple of 32 / N.  N > 32: pre (+ per-agent kernel for N > 128), post, adjacency per step."""
+        if self.N <= 32:
+            gpw = 32 // self.N if self.N in (8, 16, 32) else 0
+            per = 1 + (1 if gpw and self.E % gpw and self.E >= gpw else 0)
+            return per if fused else per * n
+        return n * ((3 if self.N > 128 else 2) + (1 if self.A_tape is not None else 0))
+
     def step(self, actions):
         """One env.step for all envs.  actions: device float32 [E,N,A] contiguous, or None."""
         self._check_actions(actions)
@@ -208,7 +218,7 @@ class Swarm:
         ha = self._make_room(2) - 1 if self.A_tape is not None else 0
         _abi.check(self.lib.mrs_step(C.byref(self.cfg), C.byref(self.bufs), _ptr(actions), hx, ha, self._stream()),
                    'mrs_step')
-        self.launches += 1 if self.N <= 32 else (3 if self.A_tape is not None else 2)
+        self.launches += self._step_launches()
         if self.X_tape is not None:
             self.hx = hx
         if self.A_tape is not None:
@@ -226,7 +236,7 @@ class Swarm:
             a = actions[done:done + n] if actions is not None else None
             _abi.check(self.lib.mrs_step_many(C.byref(self.cfg), C.byref(self.bufs), _ptr(a), n, hx - 1, ha - 1,
                                               self._stream()), 'mrs_step_many')
-            self.launches += 1 if self.N <= 32 else n * (3 if self.A_tape is not None else 2)
+            self.launches += self._step_launches(n, fused=True)
             if self.X_tape is not None:
                 self.hx = hx - n
             if self.A_tape is not None:
@@ -270,7 +280,7 @@ class Swarm:
         ha = self._make_room(2) - 1 if self.A_tape is not None else 0
         _abi.check(self.lib.mrs_step_host(C.byref(self.cfg), C.byref(self.bufs), _ptr(actions_host), _ptr(dev_actions),
                                           _ptr(X_host), _ptr(A_host), hx, ha, self._stream()), 'mrs_step_host')
-        self.launches += 1 if self.N <= 32 else (3 if self.A_tape is not None else 2)
+        self.launches += self._step_launches()
         if self.X_tape is not None:
             self.hx = hx
         if self.A_tape is not None:
@@ -293,7 +303,7 @@ class Swarm:
                 _ptr(X_host[done:done + n]) if X_host is not None else C.c_void_p(0),
                 _ptr(A_host[done:done + n]) if A_host is not None else C.c_void_p(0),
                 n, hx - 1, ha - 1, self._stream()), 'mrs_rollout_host')
-            self.launches += n if self.N <= 32 else n * (3 if self.A_tape is not None else 2)
+            self.launches += self._step_launches(n)
             if self.X_tape is not None:
                 self.hx = hx - n
             if self.A_tape is not None:
