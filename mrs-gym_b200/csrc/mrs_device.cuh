@@ -169,7 +169,7 @@ __device__ __forceinline__ void euler_to_mat(float roll, float pitch, float yaw,
 
 // nnlsRPM (Quadcopter.py:172-208).  The 4x4 NNLS is solved by enumerating the 16 active
 // sets: the optimum is the primal-feasible subset solution of least residual.
-__device__ __noinline__ void nnls_enumerate(const MrsQuadParams& q, const float* B, float* sq) {
+static __device__ __noinline__ void nnls_enumerate(const MrsQuadParams& q, const float* B, float* sq) {
     float best = INFINITY;
     for (int m = 0; m < 16; ++m) {
         float x[4];

@@ -1,889 +1,12 @@
-// mrs_kernels.cu -- sm_100a kernels + C ABI of the B200-native mrs-gym step path.
-//
-// Two execution shapes, chosen per call from N (agents per env):
-//
-//  * N <= 32  "group" path: one lane per agent, an env is a group of G = pow2ceil(N) lanes of one
-//    warp (N=8: 4 envs per warp).  Everything of MRS.step that touches the simulator is ONE kernel:
-//    action -> cascaded PID / mixer -> rotor wrench + ground effect + drag + downwash ->
-//    Bullet velocity update -> sphere / ground contact -> position + quaternion integration ->
-//    newest X slice + newest A slice.  The three intra-env pair passes (downwash on pre-step
-//    positions, contact on unconstrained velocities, adjacency on post-step positions) go through a
-//    per-warp shared-memory tile read with 128-bit LDS.  With T > 1 (mrs_step_many) the state stays
-//    in registers across steps, only actions stream in and X/A stream out.
-//
-//  * N > 32   "tiled" path: an env spans many CTAs, so the step is three kernels with the pair
-//    passes tiled n-body style through shared memory:  pre (forces -> v*, w*; copies pre-step
-//    positions to scratch), post (contact, integration, X), adjacency (row tile x column tile,
-//    coalesced 128-bit stores; this is a pure streaming store at N=4096).
+// mrs_kernels.cu -- ABI unit of libmrs_b200.so: the C entry points (include/mrs_b200.h), the kernels that
+// do not depend on the action mode (adjacency, observe, set_state, spawn, sensors, tape maintenance) and the
+// dispatch to the per-mode step units (mrs_step.cuh, one object per mode from mrs_step_mode.cu).
 //
 // Reference behaviour: /root/reference/mrsgym/MRS.py:240-277 and callees (see mrs_device.cuh);
 // Bullet step restated in oracle/bullet_model.py.  No CPU fallback exists in this library.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include "mrs_b200.h"
-#include "mrs_device.cuh"
-#include "mrs_baked.cuh"
+#include "mrs_common.cuh"
 
 namespace mrs {
-
-constexpr int kBlock = 128;
-constexpr unsigned kFull32 = 0xffffffffu;
-
-struct StepArgs {
-    const float* actions;  // [T][E][N][A]
-    int T;
-    int slot_x, slot_a;    // step t writes X tape slot slot_x - t and A tape slot slot_a - t
-    // group path: the same as pointers, resolved once on the host (NULL = that tape is not written):
-    // step t writes X to X0 - t * xstride and A to A0 - t * astride (strides in floats)
-    float* X0;
-    float* A0;
-    long long xstride, astride;
-    int G;                 // group width (power of two >= N), group path only
-    int chunk_lo, nchunks; // this launch walks the warp-sized work items [chunk_lo, nchunks), group path only
-};
-
-// ------------------------------------------------------------------------------ state planes
-__device__ __forceinline__ void load_agent(const float* __restrict__ st, unsigned S, unsigned s, Agent& a) {
-    a.px = st[0 * S + s]; a.py = st[1 * S + s]; a.pz = st[2 * S + s];
-    a.qx = st[3 * S + s]; a.qy = st[4 * S + s]; a.qz = st[5 * S + s]; a.qw = st[6 * S + s];
-    a.vx = st[7 * S + s]; a.vy = st[8 * S + s]; a.vz = st[9 * S + s];
-    a.wx = st[10 * S + s]; a.wy = st[11 * S + s]; a.wz = st[12 * S + s];
-}
-
-__device__ __forceinline__ void store_agent(float* __restrict__ st, unsigned S, unsigned s, const Agent& a) {
-    st[0 * S + s] = a.px; st[1 * S + s] = a.py; st[2 * S + s] = a.pz;
-    st[3 * S + s] = a.qx; st[4 * S + s] = a.qy; st[5 * S + s] = a.qz; st[6 * S + s] = a.qw;
-    st[7 * S + s] = a.vx; st[8 * S + s] = a.vy; st[9 * S + s] = a.vz;
-    st[10 * S + s] = a.wx; st[11 * S + s] = a.wy; st[12 * S + s] = a.wz;
-}
-
-__device__ __forceinline__ void dummy_agent(Agent& a) {
-    a.px = a.py = 0.f; a.pz = 1.0e3f;
-    a.qx = a.qy = a.qz = 0.f; a.qw = 1.f;
-    a.vx = a.vy = a.vz = 0.f;
-    a.wx = a.wy = a.wz = 0.f;
-}
-
-template <int MODE>
-__device__ __forceinline__ void load_ctrl(const float* __restrict__ ct, unsigned S, unsigned s, Ctrl& k) {
-    using MT = ModeTraits<MODE>;
-    if constexpr (MT::io) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) k.io[i] = ct[(0 + i) * S + s];
-    }
-    if constexpr (MT::ip) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) k.ip[i] = ct[(3 + i) * S + s];
-    }
-    if constexpr (MT::vel) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            k.iv[i] = ct[(6 + i) * S + s];
-            k.lve[i] = ct[(9 + i) * S + s];
-            k.dve[i] = ct[(12 + i) * S + s];
-            k.ltv[i] = ct[(15 + i) * S + s];
-        }
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ void store_ctrl(float* __restrict__ ct, unsigned S, unsigned s, const Ctrl& k) {
-    using MT = ModeTraits<MODE>;
-    if constexpr (MT::io) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) ct[(0 + i) * S + s] = k.io[i];
-    }
-    if constexpr (MT::ip) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) ct[(3 + i) * S + s] = k.ip[i];
-    }
-    if constexpr (MT::vel) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            ct[(6 + i) * S + s] = k.iv[i];
-            ct[(9 + i) * S + s] = k.lve[i];
-            ct[(12 + i) * S + s] = k.dve[i];
-            ct[(15 + i) * S + s] = k.ltv[i];
-        }
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ bool load_action(const float* __restrict__ actions, size_t idx, float* act) {
-    constexpr int A = ModeTraits<MODE>::A;
-    if constexpr (A == 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(actions) + idx);
-        act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
-        return isnan(v.x) || isnan(v.y) || isnan(v.z) || isnan(v.w);
-    } else if constexpr (A == 3) {
-        const float* p = actions + idx * 3;
-        act[0] = __ldg(p); act[1] = __ldg(p + 1); act[2] = __ldg(p + 2); act[3] = 0.f;
-        return isnan(act[0]) || isnan(act[1]) || isnan(act[2]);
-    } else {
-        act[0] = act[1] = act[2] = act[3] = 0.f;
-        return false;
-    }
-}
-
-// tape stores are write-once streams (nobody on the device re-reads a slot soon): streaming hint
-#ifndef MRS_TAPE_STREAMING
-#define MRS_TAPE_STREAMING 1
-#endif
-#if MRS_TAPE_STREAMING
-#define MRS_TAPE_ST(ptr, val) __stcs((ptr), (val))
-#else
-#define MRS_TAPE_ST(ptr, val) (*(ptr) = (val))
-#endif
-
-// newest X slice of one agent (Environment.get_X with the built-in state_fn layouts)
-__device__ __forceinline__ void write_X(float* __restrict__ Xs, int layout, unsigned s, const Agent& a) {
-    if (layout == MRS_X_POS_VEL) {
-        float2* p = reinterpret_cast<float2*>(Xs + (size_t)s * 6);
-        MRS_TAPE_ST(p + 0, make_float2(a.px, a.py));
-        MRS_TAPE_ST(p + 1, make_float2(a.pz, a.vx));
-        MRS_TAPE_ST(p + 2, make_float2(a.vy, a.vz));
-    } else if (layout == MRS_X_FULL) {
-        float* p = Xs + (size_t)s * 13;
-        p[0] = a.px; p[1] = a.py; p[2] = a.pz;
-        p[3] = a.qx; p[4] = a.qy; p[5] = a.qz; p[6] = a.qw;
-        p[7] = a.vx; p[8] = a.vy; p[9] = a.vz;
-        p[10] = a.wx; p[11] = a.wy; p[12] = a.wz;
-    }
-}
-
-// ------------------------------------------------------------------------------ async staging
-// The group kernel walks several warp-chunks per warp.  While chunk c is being computed, the 13
-// state planes (+ the first action) of chunk c+1 are already in flight to a per-warp shared-memory
-// stage through cp.async (LDGSTS): the load latency of a chunk is hidden behind the arithmetic of
-// the previous one without holding a second register copy of the state.  Stage layout per warp
-// (floats): 13 state planes x 32 | the mode's PID planes x 32 | 32 actions x ACTION_DIM; everything is
-// moved as 16-byte pieces (a plane's share of a chunk is 128 contiguous bytes = 8 pieces).
-#ifndef MRS_PREFETCH
-#define MRS_PREFETCH 1
-#endif
-
-__device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// ------------------------------------------------------------------------------ group path
-// GT > 0: compile-time group width with N == GT (8, 16, 32: pair loops unrolled) and FULL chunks only:
-//         every chunk is 32 consecutive valid agent slots, so the kernel carries no bounds logic at
-//         all; a ragged last chunk (E not a multiple of 32/N) is a second, one-chunk launch of the
-//         GT == 0 kernel (dispatch_step).
-// GT == 0: run-time width a.G >= N (any N <= 32), lanes >= N of a group idle.
-// WPB = warps per CTA.  WPB = 4: many small CTAs, chunks handed out grid-stride (small jobs).
-// WPB = 4 * minb (one CTA owns a whole SM): the CTA takes a contiguous share of the chunks and its
-// warps pull them from a shared-memory counter.  Per-warp timestamps at C5 (tools/trace_c5.py)
-// showed that with a static split the warps of one launch finish between 12 and 21 us after the
-// start -- the hardware warp scheduler is not fair -- and the kernel lasts as long as its slowest
-// warp; the SM-local dynamic hand-out keeps all warps of an SM busy until its share is done
-// (first / last warp end 14.7 / 20.2 us).  A device-wide atomic counter was tried first: 12k
-// same-address L2 atomics per launch serialise and cost +40 %.
-//
-// BAKED: the model constants (cf2x.urdf, QuadControl gains, Bullet defaults, DT, GRAVITY and what the
-// host derives from them) are compile-time values taken from the generated mrs_baked.cuh instead of
-// kernel parameters.  sm_100a has no constant-bank operands on its FP instructions: every parameter a
-// chunk uses costs an LDC/LDCU issue slot (~10 % of the generic kernel's instructions), immediates cost
-// nothing and fold.  The host picks the baked kernel only when the caller's MrsConfig carries exactly
-// those values (config_is_baked: bitwise compare); anything else runs the generic kernel.
-
-// plane `pl` of an SoA buffer given the pointer to the agent's slot in plane 0: one IMAD.WIDE.U32
-__device__ __forceinline__ float* plane_ptr(float* p0, unsigned S, int pl) {
-    return reinterpret_cast<float*>(reinterpret_cast<char*>(p0) + (unsigned long long)S * (unsigned)(pl * 4));
-}
-__device__ __forceinline__ const float* plane_ptr(const float* p0, unsigned S, int pl) {
-    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p0) + (unsigned long long)S * (unsigned)(pl * 4));
-}
-
-// dynamic shared memory of one warp of the group kernel: pair tile (+ prefetch stage for full chunks)
-template <int MODE, int GT> __host__ __device__ constexpr int group_warp_smem_bytes() {
-    return 1024 + ((MRS_PREFETCH && GT != 0) ? mode_stage_floats<MODE>() * 4 : 0);
-}
-
-template <int MODE, int GT, int WPB, bool BAKED>
-__global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : 1)
-step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant__ Derived d_in, const MrsBuffers b,
-                  const StepArgs a) {
-    MrsConfig c_bk;
-    Derived d_bk;
-    if constexpr (BAKED) baked_fill(c_bk, d_bk, c_in, d_in);
-    const MrsConfig& c = BAKED ? c_bk : c_in;
-    const Derived& d = BAKED ? d_bk : d_in;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr bool kFull = GT != 0;
-    constexpr bool kStage = MRS_PREFETCH && kFull;
-    // shared memory, one contiguous region per warp so that every address is one per-warp base plus an
-    // immediate: [32 positions | 32 velocities] (the pair tile, 1 KB) [prefetch stage]
-    constexpr int kWarpBytes = group_warp_smem_bytes<MODE, GT>();
-    __shared__ int sh_counter, sh_hi;
-    __shared__ unsigned sh_events[5];       // CTA-level status word + the four statistics counters
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char* wbase = smem_raw + wib * kWarpBytes;
-    float4* wpos = reinterpret_cast<float4*>(wbase);
-    float4* wvel = wpos + 32;
-    float* stage = reinterpret_cast<float*>(wbase + 1024);
-    const int G = GT ? GT : a.G;
-    const int N = GT ? GT : c.N;
-    const int E = c.E;
-    const int gpw = 32 / G;
-    const int ai = lane & (G - 1);
-    const int gb = lane - ai;
-    const unsigned S = (unsigned)E * (unsigned)N;
-    const int wtotal = gridDim.x * WPB;
-    const MrsPhysicsParams& ph = c.phys;
-    const bool pair_contact = ph.agent_contact && N > 1;
-
-    // Work distribution (see the comment above the kernel) over the chunks [a.chunk_lo, a.nchunks).
-    // kLocal: the CTA owns the contiguous share [cta_lo, cta_hi) and its warps draw chunk indices from
-    // a shared-memory counter; a warp always knows its next chunk (the stage prefetch needs it) and
-    // draws the one after next at the top of an iteration, so the atomic's latency is never waited for.
-    constexpr bool kLocal = WPB > 4;
-    const int gw = blockIdx.x * WPB + wib;
-    if (threadIdx.x < 5) sh_events[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) {
-        const int nwork = a.nchunks - a.chunk_lo;
-        sh_counter = a.chunk_lo + (int)(((long long)blockIdx.x * nwork) / gridDim.x);
-        sh_hi = a.chunk_lo + (int)(((long long)(blockIdx.x + 1) * nwork) / gridDim.x);
-    }
-    __syncthreads();
-    // lane 0 draws a chunk index (-1 when the share is used up); the others get it by shuffle later
-    auto draw = [&]() -> int {
-        int v = -1;
-        if (lane == 0) {
-            // .inc with the maximal bound == add 1; ptxas wraps an .add of a constant in its warp-aggregation
-            // sequence (vote, popc, ltmask, shuffle: 14 instructions) although only one lane is active here
-            // (ptxas wraps this in its warp-aggregation sequence -- vote, popc, ltmask, shuffle -- although one
-            // lane is active; .inc, a run-time addend and an addend read from shared memory all end up the same)
-            asm volatile("atom.shared.add.u32 %0, [%1], 1;"
-                         : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(&sh_counter)) : "memory");
-            v = (v < sh_hi) ? v : -1;
-        }
-        return v;
-    };
-    // chunk = 32 consecutive agent slots (kFull).  The stage is filled in 16-byte pieces, piece q at float
-    // offset 4 q, lane l moves pieces l, l + 32, ...:  [0, 96) state planes 0-11 (plane q >> 3, sub-piece
-    // q & 7: a lane's plane advances by 4 per round, so its element index is lane part + round part +
-    // chunk part), then the chunk's actions (32 * ACTION_DIM contiguous floats: one whole round for
-    // ACTION_DIM 4), then plane 12, then 8 pieces per PID plane.
-    constexpr int kNC = mode_nctrl<MODE>();
-    constexpr int kA = ModeTraits<MODE>::A;
-    constexpr int kActBeg = 96, kActEnd = kActBeg + 8 * kA;       // piece ranges
-    constexpr int kP12Beg = kActEnd, kP12End = kP12Beg + 8;
-    constexpr int kCtlBeg = kP12End, kCtlEnd = kCtlBeg + 8 * kNC;
-    constexpr int kPieces = kCtlEnd;
-    static_assert(kPieces * 4 == mode_stage_floats<MODE>(), "stage layout");
-    const unsigned lane_el = (unsigned)(lane >> 3) * S + (unsigned)(lane & 7) * 4u;   // plane (l>>3), sub-piece (l&7)
-    auto prefetch = [&](int chunk) {
-        const unsigned s0 = (unsigned)chunk * 32u;
-#pragma unroll
-        for (int i = 0; i < (kPieces + 31) / 32; ++i) {
-            const int q = lane + 32 * i;
-            const int lo = 32 * i, hi = 32 * i + 31;       // compile-time after unrolling: the tests below fold
-            if (hi < kActBeg) {
-                cp_async16(stage + 4 * q, b.state + (lane_el + s0 + (unsigned)(4 * i) * S));
-            } else {
-                if (lo < kActEnd && hi >= kActBeg && (lo >= kActBeg || q >= kActBeg) && (hi < kActEnd || q < kActEnd))
-                    cp_async16(stage + 4 * q, a.actions + (s0 * (unsigned)kA + (unsigned)(q - kActBeg) * 4u));
-                if (lo < kP12End && hi >= kP12Beg && (lo >= kP12Beg || q >= kP12Beg) && (hi < kP12End || q < kP12End))
-                    cp_async16(stage + 4 * q, b.state + (12u * S + s0 + (unsigned)(q - kP12Beg) * 4u));
-                if (kNC > 0 && lo < kCtlEnd && hi >= kCtlBeg && (lo >= kCtlBeg || q >= kCtlBeg) && (hi < kCtlEnd || q < kCtlEnd)) {
-                    const int cq = q - kCtlBeg;
-                    cp_async16(stage + 4 * q, b.ctrl + ((unsigned)mode_ctrl_plane<MODE>(cq >> 3) * S + s0 + (unsigned)(cq & 7) * 4u));
-                }
-            }
-        }
-        cp_async_commit();
-    };
-#ifdef MRS_TRACE
-    // debug build (tools/trace_c5.py): per-warp timeline (globaltimer ns) into bufs.scratch seen as
-    // u64[warps][8], plus per-step aggregates [min start, max wait release, max end, min end]
-    unsigned long long* trace = reinterpret_cast<unsigned long long*>(b.scratch) + (size_t)gw * 8;
-    unsigned long long* agg = reinterpret_cast<unsigned long long*>(b.scratch) + (size_t)8192 * 8 + (size_t)a.slot_x * 4;
-    int trace_i = 0;
-    auto stamp = [&]() {
-        unsigned long long tns;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-        if (lane == 0 && trace_i < 8) trace[trace_i] = tns;
-        if (lane == 0 && trace_i == 0) atomicMin(agg + 0, tns);
-        if (lane == 0 && trace_i == 1) atomicMax(agg + 1, tns);
-        ++trace_i;
-    };
-    auto stamp_end = [&]() {
-        unsigned long long tns;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-        if (lane == 0) { atomicMax(agg + 2, tns); atomicMin(agg + 3, tns); }
-    };
-    stamp();
-#endif
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#ifdef MRS_TRACE
-    stamp();
-#endif
-    int chunk, chunk_next;
-    if (kLocal) {
-        chunk = __shfl_sync(kFull32, draw(), 0);
-        chunk_next = __shfl_sync(kFull32, chunk >= 0 ? draw() : -1, 0);
-    } else {
-        chunk = a.chunk_lo + gw;
-        chunk_next = chunk + wtotal;
-        if (chunk >= a.nchunks) chunk = -1;
-        if (chunk_next >= a.nchunks) chunk_next = -1;
-    }
-    if (kStage && chunk >= 0) prefetch(chunk);
-    while (chunk >= 0) {
-        const int ticket = (kLocal && chunk_next >= 0) ? draw() : -1;   // the chunk after next; warp-uniform condition
-        // kFull: the chunk is 32 consecutive valid slots; else lanes >= N of a group (and envs >= E) idle
-        const int e = chunk * gpw + (lane / G);
-        const bool valid = kFull ? true : ((e < E) && (ai < N));
-        const unsigned s = kFull ? (unsigned)chunk * 32u + (unsigned)lane
-                                 : (valid ? (unsigned)e * (unsigned)N + (unsigned)ai : 0u);
-        Agent st;
-        Ctrl k;
-        float4 act0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (kStage) {
-            cp_async_wait_all();
-            __syncwarp();           // pieces were fetched by other lanes
-            st.px = stage[0 * 32 + lane]; st.py = stage[1 * 32 + lane]; st.pz = stage[2 * 32 + lane];
-            st.qx = stage[3 * 32 + lane]; st.qy = stage[4 * 32 + lane]; st.qz = stage[5 * 32 + lane];
-            st.qw = stage[6 * 32 + lane];
-            st.vx = stage[7 * 32 + lane]; st.vy = stage[8 * 32 + lane]; st.vz = stage[9 * 32 + lane];
-            st.wx = stage[10 * 32 + lane]; st.wy = stage[11 * 32 + lane]; st.wz = stage[4 * kP12Beg + lane];
-            const float* cs = stage + 4 * kCtlBeg + lane;
-            if constexpr (ModeTraits<MODE>::io) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) k.io[i] = cs[i * 32];
-            }
-            if constexpr (ModeTraits<MODE>::ip) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) k.ip[i] = cs[(3 + i) * 32];
-            }
-            if constexpr (ModeTraits<MODE>::vel) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    k.iv[i] = cs[(3 + i) * 32]; k.lve[i] = cs[(6 + i) * 32];
-                    k.dve[i] = cs[(9 + i) * 32]; k.ltv[i] = cs[(12 + i) * 32];
-                }
-            }
-            const float* as = stage + 4 * kActBeg + kA * lane;
-            if constexpr (kA == 4) act0 = *reinterpret_cast<const float4*>(as);
-            if constexpr (kA == 3) act0 = make_float4(as[0], as[1], as[2], 0.f);
-            __syncwarp();           // everyone has read its column before the stage is refilled
-            if (chunk_next >= 0) prefetch(chunk_next);
-        } else if (valid) {
-            load_agent(b.state, S, s, st);
-            load_ctrl<MODE>(b.ctrl, S, s, k);
-        } else {
-            dummy_agent(st);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) k.io[i] = k.ip[i] = k.iv[i] = k.lve[i] = k.dve[i] = k.ltv[i] = 0.f;
-        }
-        float* Xs = a.X0;       // tape slots of step t (they move down one slot per step)
-        float* As = a.A0;
-        for (int t = 0; t < a.T; ++t, Xs -= a.xstride, As -= a.astride) {
-            // per-step event word: the registers behind it live only as long as the step needs them
-            unsigned status = 0;
-            unsigned n_agent_rows = 0, n_ground = 0;
-            float rpm[4];
-            float act[4];
-            bool nan_act = false;
-            if (kStage && t == 0) {
-                act[0] = act0.x; act[1] = act0.y; act[2] = act0.z; act[3] = act0.w;
-                nan_act = kA > 0 && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || isnan(act0.w));
-            } else if (valid) {
-                nan_act = load_action<MODE>(a.actions, (size_t)t * S + s, act);
-            } else {
-                act[0] = act[1] = act[2] = act[3] = 0.f;
-            }
-            if (nan_act) status |= MRS_STATUS_NAN_ACTION;
-
-#ifdef MRS_EXP_COPYONLY      // experiment (profiles/README.md): memory movement of a step only, no physics
-            st.px += act[0] * 1e-12f;
-            if (false) {
-#else
-            {
-#endif
-            float R[9];
-            quat_to_mat(st, R);
-            action_to_rpm<MODE>(c, c_in.quad, d, st, R, act, k, rpm);
-            if (b.rpm && MODE != MRS_NO_ACTION && valid) {       // optional Quadcopter.speeds mirror
-#pragma unroll
-                for (int i = 0; i < 4; ++i) *plane_ptr(b.rpm + s, S, i) = rpm[i];
-            }
-
-            // ---- pair pass 1: downwash + contact proximity on the pre-step positions
-            __syncwarp();
-            wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
-            __syncwarp();
-            float dw = 0.f;
-            bool near = false;
-            if (MODE != MRS_NO_ACTION || pair_contact) {
-#pragma unroll 8
-                for (int r = 1; r < G; ++r) {
-                    const int j = ai ^ r;
-                    if (GT || j < N) {
-                        const float4 pj = wpos[gb + j];
-                        const float rx = pj.x - st.px, ry = pj.y - st.py, rz = pj.z - st.pz;
-                        const float dxy2 = rx * rx + ry * ry;
-                        if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, d, dxy2, rz);
-                        near = near || (dxy2 + rz * rz < d.lim2);
-                    }
-                }
-            }
-            apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
-
-            // ---- pair pass 2 (rare): sphere-sphere contact on the unconstrained velocities
-            if (pair_contact && __any_sync(kFull32, near && valid)) {
-                wvel[lane] = make_float4(st.vx, st.vy, st.vz, 0.f);
-                __syncwarp();
-                if (near) {
-                    // st.p still is the pre-step position (integrate comes later)
-                    const float p0x = st.px, p0y = st.py, p0z = st.pz;
-                    float acc[3] = {0.f, 0.f, 0.f};
-                    for (int r = 1; r < G; ++r) {
-                        const int j = ai ^ r;
-                        if (GT || j < N) {
-                            const float4 pj = wpos[gb + j];
-                            const float4 vj = wvel[gb + j];
-                            if (agent_contact_pair(ph, d, p0x - pj.x, p0y - pj.y, p0z - pj.z, st.vx - vj.x,
-                                                   st.vy - vj.y, st.vz - vj.z, acc))
-                                ++n_agent_rows;
-                        }
-                    }
-                    st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
-                }
-            }
-            if (ph.ground_contact && ground_contact(ph, d, st)) ++n_ground;
-            integrate(c, d, st);
-            if (!agent_finite(st)) status |= MRS_STATUS_NONFINITE;
-
-            }
-            // ---- observation: newest X slice and newest A slice into their tape slots
-            // (X rows staged through shared memory and written as whole 16-byte pieces were measured: neutral
-            // at C5, 18.4 vs 18.1 us -- unlike the A rows below, the float2 stores are not the limiter)
-            if (a.X0 && valid) write_X(Xs, c.state_layout, s, st);
-            if (a.A0) {
-                float* Arow = As + (size_t)s * N;
-                if (d.comm_inf) {
-                    if (valid)
-                        for (int j = 0; j < N; ++j) Arow[j] = (j == ai) ? 0.f : 1.f;
-                } else {
-                    __syncwarp();
-                    wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
-                    __syncwarp();
-                    if constexpr (GT != 0) {
-                        // Lane pair (2k, 2k+1) shares the two rows 2k, 2k+1 of A: the even lane computes the
-                        // even column quads of BOTH rows, the odd lane the odd quads.  One STG.128 of the pair
-                        // then covers 32 contiguous bytes, i.e. whole 32-byte sectors (a lane writing its own
-                        // row alone sends every sector twice, half filled), and every column position read
-                        // from shared memory serves two rows.
-                        const int h = lane & 1;
-                        const float4 r0 = wpos[lane & ~1], r1 = wpos[lane | 1];
-                        float* Arow0 = As + (size_t)(s & ~1u) * GT;
-                        const int d0 = (ai & ~1) - 4 * h;          // column of row 0's diagonal relative to quad h
-#pragma unroll
-                        for (int qq = 0; qq < GT / 8; ++qq) {       // this lane's quads: h, h + 2, ...
-                            const int col = 8 * qq + 4 * h;
-                            float4 pj[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) pj[u] = wpos[gb + col + u];
-                            float v0[4], v1[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float h0 = adjacency_pair(r0.x, r0.y, r0.z, pj[u].x, pj[u].y, pj[u].z, d.s_max);
-                                const float h1 = adjacency_pair(r1.x, r1.y, r1.z, pj[u].x, pj[u].y, pj[u].z, d.s_max);
-                                v0[u] = (8 * qq + u == d0) ? 0.f : h0;
-                                v1[u] = (8 * qq + u == d0 + 1) ? 0.f : h1;
-                            }
-                            MRS_TAPE_ST(reinterpret_cast<float4*>(Arow0 + col), make_float4(v0[0], v0[1], v0[2], v0[3]));
-                            MRS_TAPE_ST(reinterpret_cast<float4*>(Arow0 + GT + col), make_float4(v1[0], v1[1], v1[2], v1[3]));
-                        }
-                    } else if (valid) {
-                        if ((N & 3) == 0) {
-#pragma unroll 2
-                            for (int j = 0; j < N; j += 4) {
-                                // loads and arithmetic unconditional, the diagonal is a select afterwards: a
-                                // conditional around the shared-memory load compiles to one divergent
-                                // BSSY/BRA/BSYNC block per element (no overlap between the pairs)
-                                float4 pj[4];
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) pj[u] = wpos[gb + j + u];
-                                float v[4];
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const float hit = adjacency_pair(st.px, st.py, st.pz, pj[u].x, pj[u].y, pj[u].z, d.s_max);
-                                    v[u] = (j + u == ai) ? 0.f : hit;
-                                }
-                                MRS_TAPE_ST(reinterpret_cast<float4*>(Arow + j), make_float4(v[0], v[1], v[2], v[3]));
-                            }
-                        } else {
-                            for (int j = 0; j < N; ++j) {
-                                const float4 pj = wpos[gb + j];
-                                const float hit = adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
-                                Arow[j] = (j == ai) ? 0.f : hit;
-                            }
-                        }
-                    }
-                }
-            }
-            // status / statistics: warp-reduce, then CTA-level shared-memory counters; the global atomics
-            // happen once per CTA at the end.  (A swarm resting on the ground reports a ground contact per
-            // agent per step: with one global atomic per warp-chunk that was 10 k same-address L2 atomics
-            // per launch at C5 and cost ~15 % of the step.)
-            if (!valid) { status = 0; n_agent_rows = 0; n_ground = 0; }
-            if (__reduce_or_sync(kFull32, status | n_agent_rows | n_ground)) {      // rare in free flight
-                const unsigned any_status = __reduce_or_sync(kFull32, status);
-                const unsigned sum_rows = __reduce_add_sync(kFull32, n_agent_rows);
-                const unsigned sum_gnd = __reduce_add_sync(kFull32, n_ground);
-                if (lane == 0) {
-                    if (any_status) atomicOr(&sh_events[0], any_status);
-                    if (sum_rows) atomicAdd(&sh_events[1], sum_rows);
-                    if (sum_gnd) atomicAdd(&sh_events[2], sum_gnd);
-                    if (any_status & MRS_STATUS_NONFINITE) atomicAdd(&sh_events[3], 1u);
-                    if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(&sh_events[4], 1u);
-                }
-            }
-        }
-
-        if (valid) {
-            float* p0 = b.state + s;
-            *plane_ptr(p0, S, 0) = st.px; *plane_ptr(p0, S, 1) = st.py; *plane_ptr(p0, S, 2) = st.pz;
-            *plane_ptr(p0, S, 3) = st.qx; *plane_ptr(p0, S, 4) = st.qy; *plane_ptr(p0, S, 5) = st.qz;
-            *plane_ptr(p0, S, 6) = st.qw;
-            *plane_ptr(p0, S, 7) = st.vx; *plane_ptr(p0, S, 8) = st.vy; *plane_ptr(p0, S, 9) = st.vz;
-            *plane_ptr(p0, S, 10) = st.wx; *plane_ptr(p0, S, 11) = st.wy; *plane_ptr(p0, S, 12) = st.wz;
-            store_ctrl<MODE>(b.ctrl, S, s, k);
-        }
-#ifdef MRS_TRACE
-        stamp();
-#endif
-        chunk = chunk_next;
-        if (kLocal) {
-            chunk_next = __shfl_sync(kFull32, ticket, 0);
-        } else {
-            chunk_next = (chunk >= 0 && chunk + wtotal < a.nchunks) ? chunk + wtotal : -1;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (sh_events[0] && b.status) atomicOr(b.status, sh_events[0]);
-        if (b.stats) {
-            if (sh_events[1]) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)sh_events[1]);
-            if (sh_events[2]) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)sh_events[2]);
-            if (sh_events[3]) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)sh_events[3]);
-            if (sh_events[4]) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, (unsigned long long)sh_events[4]);
-        }
-    }
-#ifdef MRS_TRACE
-    stamp_end();
-#endif
-}
-
-// ------------------------------------------------------------------------------ wide path (N > 32)
-// An env no longer fits a warp, so the pair passes are spread over LPA lanes PER AGENT (LPA = 8 for
-// N <= 128, else 32): every lane walks the partners j = l, l + LPA, ... of its agent straight from
-// the L1/L2-resident position planes, the partial sums are combined with a fixed-order xor-shuffle
-// tree (deterministic), and the group's lane 0 runs the per-agent part.  One env of 4096 agents
-// therefore fills the GPU with 4096 warps instead of 32 CTAs.
-// scratch planes: 0-2 unconstrained velocity, 3-5 pre-step position, 6 contact-proximity flag.
-template <int LPA>
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-    for (int o = LPA / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull32, v, o);
-    return v;
-}
-
-// per-agent part of the wide pre pass: controller -> rotor wrench + aero (dw = downwash sum) ->
-// unconstrained velocities; stashes v*, the pre-step position and the proximity flag in scratch
-template <int MODE>
-__device__ __forceinline__ void agent_pre(const MrsConfig& c, const Derived& d, const MrsBuffers& b,
-                                          const float* __restrict__ actions, unsigned S, unsigned s, float dw, bool near) {
-    Agent st;
-    Ctrl k;
-    load_agent(b.state, S, s, st);
-    load_ctrl<MODE>(b.ctrl, S, s, k);
-    const float pix = st.px, piy = st.py, piz = st.pz;
-    float act[4];
-    unsigned status = 0;
-    if (load_action<MODE>(actions, s, act)) status |= MRS_STATUS_NAN_ACTION;
-    float R[9], rpm[4];
-    quat_to_mat(st, R);
-    action_to_rpm<MODE>(c, c.quad, d, st, R, act, k, rpm);
-    apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
-    float* sc = b.scratch;
-    sc[0 * (size_t)S + s] = st.vx; sc[1 * (size_t)S + s] = st.vy; sc[2 * (size_t)S + s] = st.vz;
-    sc[3 * (size_t)S + s] = pix; sc[4 * (size_t)S + s] = piy; sc[5 * (size_t)S + s] = piz;
-    sc[6 * (size_t)S + s] = near ? 1.f : 0.f;
-    b.state[10 * (size_t)S + s] = st.wx; b.state[11 * (size_t)S + s] = st.wy; b.state[12 * (size_t)S + s] = st.wz;
-    store_ctrl<MODE>(b.ctrl, S, s, k);
-    if (b.rpm && MODE != MRS_NO_ACTION) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) b.rpm[i * (size_t)S + s] = rpm[i];
-    }
-    if (status && b.status) {
-        atomicOr(b.status, status);
-        if (b.stats) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, 1ull);
-    }
-}
-
-template <int MODE, int LPA>
-__global__ void __launch_bounds__(kBlock)
-step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
-                const float* __restrict__ actions) {
-    const int N = c.N;
-    const unsigned S = (unsigned)c.E * (unsigned)N;
-    const unsigned gid = (blockIdx.x * kBlock + threadIdx.x) / LPA;      // agent slot of this lane group
-    const int l = threadIdx.x & (LPA - 1);
-    const bool valid = gid < S;
-    const unsigned s = valid ? gid : 0u;
-    const unsigned env0 = (s / (unsigned)N) * (unsigned)N;
-    const int ai = (int)(s - env0);
-    const float* __restrict__ px = b.state + 0 * (size_t)S + env0;
-    const float* __restrict__ py = b.state + 1 * (size_t)S + env0;
-    const float* __restrict__ pz = b.state + 2 * (size_t)S + env0;
-    const float pix = px[ai], piy = py[ai], piz = pz[ai];
-    float dw = 0.f;
-    bool near = false;
-    const bool pair_contact = c.phys.agent_contact && N > 1;
-    if (MODE != MRS_NO_ACTION || pair_contact) {
-        // Uniform trip count for the whole warp (the vote below needs every lane).  The SFU part of the
-        // downwash is skipped for a whole warp when none of its 32 pairs can contribute: partner not
-        // above (rz <= 0), dxy >= 10, or exp(-0.5 (dxy/beta)^2) underflowing float32 (0.5 q^2 > 104).
-        // Consecutive partners share a height layer in a lattice-like swarm, so the vote is mostly uniform.
-        // four partners per lane and iteration: independent loads in flight, one vote per four pairs
-        for (int j0 = 0; j0 < N; j0 += 4 * LPA) {
-            float dxy2[4], rz[4];
-            bool live[4], any_live = false;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u * LPA + l;
-                const bool in = j < N;
-                const int jj = in ? j : ai;
-                const float rx = px[jj] - pix, ry = py[jj] - piy;
-                rz[u] = pz[jj] - piz;
-                dxy2[u] = rx * rx + ry * ry;
-                const bool other = in && j != ai;
-                const float beta = c.quad.dw2 * rz[u] + c.quad.dw3;
-                live[u] = MODE != MRS_NO_ACTION && other && rz[u] > 0.f && dxy2[u] < 100.f &&
-                          !(dxy2[u] > 208.f * beta * beta);
-                any_live = any_live || live[u];
-                near = near || (other && dxy2[u] + rz[u] * rz[u] < d.lim2);
-            }
-            if (MODE != MRS_NO_ACTION && __any_sync(kFull32, any_live)) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float f = downwash_pair(c.quad, d, dxy2[u], rz[u]);
-                    dw += live[u] ? f : 0.f;
-                }
-            }
-        }
-    }
-    static_assert(LPA <= 32, "N > 128 uses pair_tile_kernel");
-    dw = group_sum<LPA>(dw);
-    const unsigned gmask = (LPA == 32) ? kFull32 : (((1u << (LPA & 31)) - 1u) << ((threadIdx.x & 31) & ~(LPA - 1)));
-    near = (__ballot_sync(kFull32, near) & gmask) != 0u;
-    if (l != 0 || !valid) return;
-    agent_pre<MODE>(c, d, b, actions, S, s, dw, near && pair_contact);
-}
-
-// ------------------------------------------------------------------------------ pair pass for N > 128
-// n-body tiling.  A CTA owns 128 agents of one env (one per thread, own position in registers) and one
-// of `nsplit` slices of the partner range; partner positions go through shared memory in tiles of 128
-// and every thread reads the SAME partner (broadcast LDS.128), so a pair costs no global load, no index
-// arithmetic and no shuffle: ~16 instructions without the downwash term, which is skipped per warp when
-// none of its 32 agents can feel this partner (not above, dxy >= 10 m, or exp(-0.5 (dxy/beta)^2)
-// underflowing float32).  Partial sums of slice js go to scratch plane kPairPlane0 + js, the proximity
-// flag to plane kPairPlane0 + nsplit + js; agent_pre_kernel adds them in slice order (deterministic).
-// (The first version gave every agent a whole CTA that walked the partners from the L1-resident position
-// planes: 45 instructions per pair, 29.9 us at N = 4096.)
-constexpr int kPairPlane0 = MRS_SCRATCH_PLANES;      // first partial-sum plane
-constexpr int kPairMaxSplit = MRS_SCRATCH_PAIR_SPLITS;
-
-template <int MODE>
-__global__ void __launch_bounds__(kBlock)
-pair_tile_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int jw,
-                 int nsplit) {
-    __shared__ float4 tile[kBlock];
-    const int N = c.N;
-    const unsigned S = (unsigned)c.E * (unsigned)N;
-    const int itiles = (N + kBlock - 1) / kBlock;
-    const unsigned per_env = (unsigned)(itiles * nsplit);
-    const unsigned env = blockIdx.x / per_env, rem = blockIdx.x - env * per_env;
-    const int it = (int)(rem / (unsigned)nsplit), js = (int)(rem - (unsigned)it * (unsigned)nsplit);
-    const unsigned env0 = env * (unsigned)N;
-    const int i = it * kBlock + threadIdx.x;
-    const bool valid = i < N;
-    const float* __restrict__ px = b.state + 0 * (size_t)S + env0;
-    const float* __restrict__ py = b.state + 1 * (size_t)S + env0;
-    const float* __restrict__ pz = b.state + 2 * (size_t)S + env0;
-    // an idle lane sits far below everything: no partner is above-and-near, none is close
-    const float pix = valid ? px[i] : 0.f, piy = valid ? py[i] : 0.f, piz = valid ? pz[i] : 3.0e18f;
-    const bool pair_contact = c.phys.agent_contact && N > 1;
-    // 0 < d2 < lim2 as ONE unsigned compare of the float bits (d2 >= 0 or NaN): (bits - 1) < (bits(lim2) - 1);
-    // d2 == 0 is the agent itself (or a coincident partner, which the contact row ignores anyway)
-    const unsigned lim_m1 = __float_as_uint(d.lim2) - 1u;
-    float dw = 0.f;
-    bool near = false;
-    // Tile culling: a tile whose highest partner lies more than the contact range below the lowest agent of
-    // this warp can neither blow on any of them (dz <= 0) nor touch them: skipped as a whole (exact, not a
-    // cut-off).  It pays when the index order follows height; the C4 bench lattice has z as its fastest
-    // index, so no tile is skipped there and the test costs ~1 %.
-    __shared__ float tile_zmax[kBlock / 32];
-    float wz_min = valid ? piz : 3.0e38f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wz_min = fminf(wz_min, __shfl_xor_sync(kFull32, wz_min, o));
-    const float z_skip = wz_min - sqrtf(d.lim2);
-    const int jbeg = js * jw, jend = min(jbeg + jw, N);
-    for (int j0 = jbeg; j0 < jend; j0 += kBlock) {
-        const int jj = j0 + threadIdx.x;
-        const float4 mine = (jj < jend) ? make_float4(px[jj], py[jj], pz[jj], 0.f) : make_float4(3.0e18f, 0.f, -3.0e18f, 0.f);
-        float zm = mine.z;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(kFull32, zm, o));
-        __syncthreads();
-        tile[threadIdx.x] = mine;
-        if ((threadIdx.x & 31) == 0) tile_zmax[threadIdx.x >> 5] = zm;
-        __syncthreads();
-        const float tz = fmaxf(fmaxf(tile_zmax[0], tile_zmax[1]), fmaxf(tile_zmax[2], tile_zmax[3]));
-        if (tz < z_skip) continue;          // warp-uniform
-#pragma unroll 2
-        for (int jl = 0; jl < kBlock; jl += 4) {
-            float dxy2[4], rz[4];
-            bool live[4], any_live = false;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 pj = tile[jl + u];
-                const float rx = pj.x - pix, ry = pj.y - piy;
-                rz[u] = pj.z - piz;
-                dxy2[u] = rx * rx + ry * ry;
-                const float d2 = dxy2[u] + rz[u] * rz[u];
-                near = near || (__float_as_uint(d2) - 1u < lim_m1);
-                const float beta = c.quad.dw2 * rz[u] + c.quad.dw3;
-                live[u] = MODE != MRS_NO_ACTION && rz[u] > 0.f && dxy2[u] < 100.f && !(dxy2[u] > 208.f * beta * beta);
-                any_live = any_live || live[u];
-            }
-            if (MODE != MRS_NO_ACTION && __any_sync(kFull32, any_live)) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float f = downwash_pair(c.quad, d, dxy2[u], rz[u]);
-                    dw += live[u] ? f : 0.f;
-                }
-            }
-        }
-    }
-    if (!valid) return;
-    const unsigned s = env0 + (unsigned)i;
-    b.scratch[(size_t)(kPairPlane0 + js) * S + s] = dw;
-    b.scratch[(size_t)(kPairPlane0 + nsplit + js) * S + s] = (near && pair_contact) ? 1.f : 0.f;
-}
-
-// thread-per-agent half of the wide pre pass for N >= 1024 (dw and the proximity flag come from scratch)
-template <int MODE>
-__global__ void __launch_bounds__(kBlock)
-agent_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
-                 const float* __restrict__ actions, int nsplit) {
-    const unsigned S = (unsigned)c.E * (unsigned)c.N;
-    const unsigned s = blockIdx.x * kBlock + threadIdx.x;
-    if (s >= S) return;
-    float dw = 0.f, fl = 0.f;
-    for (int j0 = 0; j0 < nsplit; j0 += 8) {       // fixed order: the sum does not depend on the launch shape
-        float pd[8], pf[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {              // independent loads in flight
-            const bool in = j0 + u < nsplit;
-            pd[u] = in ? b.scratch[(size_t)(kPairPlane0 + j0 + u) * S + s] : 0.f;
-            pf[u] = in ? b.scratch[(size_t)(kPairPlane0 + nsplit + j0 + u) * S + s] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { dw += pd[u]; fl += pf[u]; }
-    }
-    agent_pre<MODE>(c, d, b, actions, S, s, dw, fl != 0.f);
-}
-
-template <int LPA>
-__global__ void __launch_bounds__(kBlock)
-step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int slot) {
-    const int N = c.N;
-    const unsigned S = (unsigned)c.E * (unsigned)N;
-    const unsigned gid = (blockIdx.x * kBlock + threadIdx.x) / LPA;
-    const int l = threadIdx.x & (LPA - 1);
-    const bool valid = gid < S;
-    const unsigned s = valid ? gid : 0u;
-    const unsigned env0 = (s / (unsigned)N) * (unsigned)N;
-    const int ai = (int)(s - env0);
-    const MrsPhysicsParams& ph = c.phys;
-    const float* __restrict__ sc = b.scratch;
-    Agent st;
-    st.px = sc[3 * (size_t)S + s]; st.py = sc[4 * (size_t)S + s]; st.pz = sc[5 * (size_t)S + s];
-    st.vx = sc[0 * (size_t)S + s]; st.vy = sc[1 * (size_t)S + s]; st.vz = sc[2 * (size_t)S + s];
-    const bool near = valid && sc[6 * (size_t)S + s] != 0.f;       // uniform over the lane group
-    float acc[3] = {0.f, 0.f, 0.f};
-    unsigned rows = 0;
-    if (near) {
-        const float* __restrict__ qx = sc + 3 * (size_t)S + env0;
-        const float* __restrict__ qy = sc + 4 * (size_t)S + env0;
-        const float* __restrict__ qz = sc + 5 * (size_t)S + env0;
-        for (int j0 = l; j0 < N; j0 += 4 * LPA) {     // 4 independent partner loads in flight per lane
-            float dx[4], dy[4], dz[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u * LPA;
-                const bool ok = j < N && j != ai;
-                const int jj = ok ? j : ai;
-                dx[u] = st.px - qx[jj]; dy[u] = st.py - qy[jj]; dz[u] = st.pz - qz[jj];
-                if (!ok) dx[u] = 1.0e18f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u] < d.lim2) {
-                    const int j = j0 + u * LPA;
-                    const float vjx = sc[0 * (size_t)S + env0 + j], vjy = sc[1 * (size_t)S + env0 + j],
-                                vjz = sc[2 * (size_t)S + env0 + j];
-                    if (agent_contact_pair(ph, d, dx[u], dy[u], dz[u], st.vx - vjx, st.vy - vjy, st.vz - vjz, acc)) ++rows;
-                }
-            }
-        }
-    }
-    // every lane of the warp takes part in the shuffles (groups without contact add zeros)
-    acc[0] = group_sum<LPA>(acc[0]); acc[1] = group_sum<LPA>(acc[1]); acc[2] = group_sum<LPA>(acc[2]);
-    rows = (unsigned)group_sum<LPA>((float)rows);
-    const bool lead = (l == 0) && valid;
-    unsigned gnd = 0, bad = 0;
-    if (lead) {
-        st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
-        st.qx = b.state[3 * (size_t)S + s]; st.qy = b.state[4 * (size_t)S + s]; st.qz = b.state[5 * (size_t)S + s];
-        st.qw = b.state[6 * (size_t)S + s];
-        st.wx = b.state[10 * (size_t)S + s]; st.wy = b.state[11 * (size_t)S + s]; st.wz = b.state[12 * (size_t)S + s];
-        if (ph.ground_contact && ground_contact(ph, d, st)) gnd = 1;
-        integrate(c, d, st);
-        store_agent(b.state, S, s, st);
-        if (b.X_tape && c.state_layout != MRS_X_NONE)
-            write_X(b.X_tape + (size_t)slot * S * state_dim(c.state_layout), c.state_layout, s, st);
-        bad = agent_finite(st) ? 0u : 1u;
-    }
-    // statistics: one warp reduction, then at most three global atomics per warp (not per agent)
-    const unsigned w_rows = __reduce_add_sync(kFull32, lead ? rows : 0u);
-    const unsigned w_gnd = __reduce_add_sync(kFull32, gnd);
-    const unsigned w_bad = __reduce_add_sync(kFull32, bad);
-    if ((threadIdx.x & 31) == 0) {
-        if (w_bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
-        if (b.stats) {
-            if (w_rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)w_rows);
-            if (w_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)w_gnd);
-            if (w_bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)w_bad);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------ adjacency
 // Flat version, any N and any position layout: one thread per output element.
@@ -1178,141 +301,7 @@ tape_fill_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t 
 }
 
 // ------------------------------------------------------------------------------ host side
-static int g_sm_count = 0;
-
-static int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-        g_sm_count = n;
-    }
-    return g_sm_count;
-}
-
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
-// largest float s with sqrt_rn(s) <= r  (see adjacency_pair)
-static float adjacency_threshold(float r) {
-    if (!(r >= 0.f)) return -1.f;          // negative or NaN range: nothing is adjacent
-    if (isinf(r)) return INFINITY;
-    float s = r * r;
-    if (isinf(s)) return 3.402823466e+38f;  // every finite squared distance qualifies
-    while (sqrtf(s) > r) s = nextafterf(s, -INFINITY);
-    for (;;) {
-        const float up = nextafterf(s, INFINITY);
-        if (isinf(up) || sqrtf(up) > r) break;
-        s = up;
-    }
-    return s;
-}
-
-static int check_cfg(const MrsConfig* cfg) {
-    if (!cfg) return MRS_ERR_ARG;
-    if (cfg->E <= 0 || cfg->N <= 0 || cfg->K < 0) return MRS_ERR_ARG;
-    if (cfg->action_type < 0 || cfg->action_type > MRS_NO_ACTION) return MRS_ERR_ARG;
-    if (cfg->state_layout < 0 || cfg->state_layout > MRS_X_FULL) return MRS_ERR_ARG;
-    return MRS_OK;
-}
-
-static int last_error() { return cudaGetLastError() == cudaSuccess ? MRS_OK : MRS_ERR_CUDA; }
-
-static Derived make_derived(const MrsConfig& c) {
-    Derived d;
-    const MrsQuadParams& q = c.quad;
-    const MrsPhysicsParams& p = c.phys;
-    d.inv_mass = (float)(1.0 / (double)p.mass);
-    for (int i = 0; i < 3; ++i) d.inv_I[i] = (float)(1.0 / (double)p.inertia[i]);
-    const double pr4 = (double)q.prop_radius / 4.0;
-    d.gnd_c = (float)((double)q.kf * (double)q.gnd_eff_coeff * pr4 * pr4);
-    d.dw_c = (float)((double)q.dw1 * pr4 * pr4);
-    d.rpm2rad = (float)(2.0 * 3.14159265358979323846 / 60.0);
-    d.q_x2 = (float)(0.25 * (double)c.dt * (double)c.dt);
-    d.cap_w2 = (float)(((double)p.ang_motion_threshold / (double)c.dt) * ((double)p.ang_motion_threshold / (double)c.dt));
-    const double cap_ang = 0.5 * 1.57079632679489661923 / (double)c.dt;      // Bullet: 0.5 * SIMD_HALF_PI / dt
-    d.cap_k = (float)(sin(0.5 * cap_ang * (double)c.dt) / cap_ang);
-    d.cap_c = (float)cos(0.5 * cap_ang * (double)c.dt);
-    const float lim = 2.f * p.agent_radius + p.contact_margin;
-    d.lim2 = lim * lim;
-    d.gnd_skip_z = p.ground_z + p.contact_margin + p.col_radius + p.col_halfheight + p.col_margin + 1e-3f;
-    d.inv_dt = (float)(1.0 / (double)c.dt);
-    d.erp_dt = (float)((double)p.erp2 / (double)c.dt);
-    d.comm_inf = isinf(c.comm_range) && c.comm_range > 0.f;
-    d.s_max = adjacency_threshold(c.comm_range);
-    d.inv_ctrl_dt = (float)(1.0 / (double)q.ctrl_dt);
-    d.inv_4kf = (float)(1.0 / (4.0 * (double)q.kf));
-    d.inv_pwm_a = (float)(1.0 / (double)q.pwm2rpm_a);
-    d.inv_qmass = (float)(1.0 / (double)q.mass);
-    return d;
-}
-
-// true iff the caller's configuration carries exactly the constants mrs_baked.cuh was generated from
-static bool config_is_baked(const MrsConfig& c, const Derived& d) {
-    MrsConfig cc = c;
-    Derived dd = d;
-    baked_constants(cc, dd);
-    return memcmp(&cc, &c, sizeof(MrsConfig)) == 0 && memcmp(&dd, &d, sizeof(Derived)) == 0;
-}
-
-template <int MODE, int GT, int WPB, bool BAKED>
-static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
-                            bool pdl, cudaStream_t st) {
-    constexpr size_t smem = (size_t)WPB * group_warp_smem_bytes<MODE, GT>();
-    static bool configured[64] = {};          // per device: the attribute belongs to the function ON a device
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MRS_ERR_CUDA;
-    if (!configured[dev]) {
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB, BAKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-                cudaSuccess)
-            return MRS_ERR_CUDA;
-        configured[dev] = true;
-    }
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3((unsigned)blocks);
-    lc.blockDim = dim3(WPB * 32);
-    lc.dynamicSmemBytes = smem;
-    lc.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = attr;
-    lc.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&lc, step_group_kernel<MODE, GT, WPB, BAKED>, c, d, b, a) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return MRS_ERR_CUDA;
-    }
-    return last_error();
-}
-
-template <int MODE, int GT>
-static int launch_group(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
-    constexpr int kBig = 4 * ModeTraits<MODE>::minb;            // warps of a CTA that owns a whole SM
-    const int sms = sm_count();
-    if (sms <= 0) return MRS_ERR_CUDA;
-    static const int use_pdl = env_int("MRS_B200_PDL", 1);
-    static const int use_big = env_int("MRS_B200_BIGCTA", 1);
-    // large jobs (every warp of the GPU gets more than two chunks): one SM-sized CTA per SM with the
-    // shared-memory hand-out.  Programmatic dependent launch pays off for full waves (measured
-    // -2.3 % at C5); partial waves are faster with plain stream order (C3: +11 % with PDL).
-    static const int use_baked = env_int("MRS_B200_BAKED", 1);
-    const bool baked = use_baked && config_is_baked(c, d);
-    const int nwork = a.nchunks - a.chunk_lo;
-    if (use_big && nwork > 2 * sms * kBig)
-        return baked ? launch_group_wpb<MODE, GT, kBig, true>(c, d, b, a, sms, use_pdl != 0, st)
-                     : launch_group_wpb<MODE, GT, kBig, false>(c, d, b, a, sms, use_pdl != 0, st);
-    const long long need = ((long long)nwork + 3) / 4;
-    const long long cap = (long long)sms * ModeTraits<MODE>::minb;
-    const long long blocks = need < cap ? need : cap;
-    const bool pdl = use_pdl && need >= cap;
-    return baked ? launch_group_wpb<MODE, GT, 4, true>(c, d, b, a, blocks, pdl, st)
-                 : launch_group_wpb<MODE, GT, 4, false>(c, d, b, a, blocks, pdl, st);
-}
-
-static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, int N, float s_max, int comm_inf,
+int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, int N, float s_max, int comm_inf,
                             cudaStream_t st) {
     if (N >= 128 && (N & 3) == 0) {
         const int col_tiles = (N + 4 * kBlock - 1) / (4 * kBlock);
@@ -1332,13 +321,7 @@ static int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, in
 // Side stream of the wide path: the adjacency kernel of step t (a pure streaming store that only
 // reads the new positions) runs next to the compute-bound pair kernel of step t+1; it has to be done
 // before post(t+1) overwrites the positions.  Fork / join through events, so it is capturable.
-namespace {
-struct SideLane {
-    cudaStream_t s = nullptr;
-    cudaEvent_t posted = nullptr, adj_done = nullptr;
-    bool ok = false;
-};
-SideLane g_side[64];
+static SideLane g_side[64];
 SideLane* side_lane() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
@@ -1351,110 +334,19 @@ SideLane* side_lane() {
     }
     return &L;
 }
-}  // namespace
 
-// partner slices of pair_tile_kernel: ~8 CTAs per SM of a B200, at most kPairMaxSplit partial planes, whole
-// tiles per slice.  A pure function of (E, N): mrs_scratch_planes sizes the caller's scratch from it.
-static void pair_split(int E, int N, int* jw, int* nsplit) {
-    const long long itiles = (N + kBlock - 1) / kBlock;
-    const long long want = 8LL * 148;
-    long long ns = (want + itiles * E - 1) / (itiles * E);
-    if (ns > kPairMaxSplit) ns = kPairMaxSplit;
-    if (ns > itiles) ns = itiles;                                                    // at least one tile per slice
-    if (ns < 1) ns = 1;
-    int w = (int)((N + ns - 1) / ns);
-    w = (w + kBlock - 1) / kBlock * kBlock;
-    *jw = w;
-    *nsplit = (N + w - 1) / w;
-}
-
-template <int MODE, int LPA, int LPB>
-static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
-    const size_t S = (size_t)c.E * c.N;
-    constexpr int A = ModeTraits<MODE>::A;
-    const unsigned blocks = (unsigned)((S * LPA + kBlock - 1) / kBlock);
-    const unsigned blocks_post = (unsigned)((S * LPB + kBlock - 1) / kBlock);
-    SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
-    int jw = 0, nsplit = 0;
-    if (LPA > 32) pair_split(c.E, c.N, &jw, &nsplit);
-    for (int t = 0; t < a.T; ++t) {
-        const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
-        if constexpr (LPA > 32) {
-            const int itiles = (c.N + kBlock - 1) / kBlock;
-            pair_tile_kernel<MODE><<<(unsigned)((long long)itiles * nsplit * c.E), kBlock, 0, st>>>(c, d, b, jw, nsplit);
-            agent_pre_kernel<MODE><<<(unsigned)((S + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, d, b, act_t, nsplit);
-        } else {
-            step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
-        }
-        if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
-        step_post_kernel<LPB><<<blocks_post, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
-        if (b.A_tape) {
-            cudaStream_t as = st;
-            if (L) {
-                if (cudaEventRecord(L->posted, st) != cudaSuccess) return MRS_ERR_CUDA;
-                if (cudaStreamWaitEvent(L->s, L->posted, 0) != cudaSuccess) return MRS_ERR_CUDA;
-                as = L->s;
-            }
-            const int rc = launch_adjacency(b.state, S, 1, b.A_tape + (size_t)(a.slot_a - t) * S * c.N, c.E, c.N, d.s_max,
-                                            d.comm_inf, as);
-            if (rc) return rc;
-            if (L && cudaEventRecord(L->adj_done, L->s) != cudaSuccess) return MRS_ERR_CUDA;
-        }
-    }
-    if (L && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
-    return last_error();
-}
-
-template <int MODE>
-static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
-    if (!b.scratch) return MRS_ERR_ARG;
-    if ((unsigned long long)c.E * c.N * 32ull >= 0x7fffffffull * (unsigned long long)kBlock) return MRS_ERR_UNSUPPORTED;
-    if (c.N <= 128) return launch_wide_lpa<MODE, 8, 8>(c, d, b, a, st);
-    return launch_wide_lpa<MODE, 128, 32>(c, d, b, a, st);     // n-body tiles (pair_tile_kernel) + agent_pre_kernel
-}
-
-static int pow2ceil(int n) {
-    int g = 1;
-    while (g < n) g <<= 1;
-    return g;
-}
-
-template <int MODE>
-static int dispatch_step(const MrsConfig& c, const MrsBuffers& b, StepArgs a, cudaStream_t st) {
-    const Derived d = make_derived(c);
-    if (c.N <= 32) {
-        a.G = pow2ceil(c.N);
-        const size_t S = (size_t)c.E * c.N;
-        a.xstride = (long long)(S * (size_t)state_dim(c.state_layout));
-        a.astride = (long long)(S * (size_t)c.N);
-        a.X0 = (b.X_tape && c.state_layout != MRS_X_NONE) ? b.X_tape + (size_t)a.slot_x * (size_t)a.xstride : nullptr;
-        a.A0 = b.A_tape ? b.A_tape + (size_t)a.slot_a * (size_t)a.astride : nullptr;
-        const int gpw = 32 / a.G;
-        const int nchunks = (c.E + gpw - 1) / gpw;
-        a.chunk_lo = 0;
-        a.nchunks = nchunks;
-        if (c.N != 8 && c.N != 16 && c.N != 32) return launch_group<MODE, 0>(c, d, b, a, st);
-        // power-of-two swarms: unrolled pair loops over FULL chunks (32 valid slots); a ragged last chunk
-        // (E not a multiple of 32/N) goes to the run-time-width kernel as a one-chunk launch
-        const int nfull = c.E / gpw;
-        int rc = MRS_OK;
-        if (nfull > 0) {
-            a.nchunks = nfull;
-            switch (c.N) {
-                case 8:  rc = launch_group<MODE, 8>(c, d, b, a, st); break;
-                case 16: rc = launch_group<MODE, 16>(c, d, b, a, st); break;
-                default: rc = launch_group<MODE, 32>(c, d, b, a, st); break;
-            }
-        }
-        if (rc == MRS_OK && nfull < nchunks) {
-            a.chunk_lo = nfull;
-            a.nchunks = nchunks;
-            rc = launch_group<MODE, 0>(c, d, b, a, st);
-        }
-        return rc;
-    }
-    return launch_tiled<MODE>(c, d, b, a, st);
-}
+#ifdef MRS_DEV_ONLY_MODE
+extern template int dispatch_step<MRS_DEV_ONLY_MODE>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+#else
+extern template int dispatch_step<MRS_SET_TARGET_VEL>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+extern template int dispatch_step<MRS_SET_TARGET_POS>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+extern template int dispatch_step<MRS_SET_TARGET_ACCEL>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+extern template int dispatch_step<MRS_SET_FORCE>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+extern template int dispatch_step<MRS_SET_TARGET_ORI>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+extern template int dispatch_step<MRS_SET_CONTROL>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+extern template int dispatch_step<MRS_SET_SPEEDS>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+extern template int dispatch_step<MRS_NO_ACTION>(const MrsConfig&, const MrsBuffers&, StepArgs, cudaStream_t);
+#endif
 
 static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T, int slot_x, int slot_a,
                      void* stream) {
