@@ -47,8 +47,9 @@ WORKLOADS = {
                desc='65536 envs x 8 agents per GPU, set_speeds, K_HOPS=3, RETURN_A COMM_RANGE=2.0 (BASELINE configs[4])'),
     'c2': dict(E=256, N=32, mode='set_target_pos', K=3, R=2.0, spacing=1.0, z0=2.5, B=316,
                desc='256 envs x 32 agents, set_target_pos, K_HOPS=3, RETURN_A COMM_RANGE=2.0 (BASELINE configs[1])'),
-    'c3': dict(E=4096, N=16, mode='set_control', K=0, R=float('inf'), spacing=0.7, z0=1.0, B=144,
-               desc='4096 envs x 16 agents, set_control, ground + agent contact (BASELINE configs[2])'),
+    'c3': dict(E=4096, N=16, mode='set_control', K=0, R=float('inf'), spacing=0.7, z0=1.0, B=144, A=False,
+               desc='4096 envs x 16 agents, set_control, ground + agent contact, RETURN_A off (BASELINE configs[2]; '
+                    'SURVEY.md 8d counts no A bytes for it)'),
     # not BASELINE configs: the C5 shape with the PID action modes (profiling the controller path)
     'c5v': dict(E=65536, N=8, mode='set_target_vel', K=3, R=2.0, spacing=1.0, z0=2.5, B=296,
                 desc='65536 envs x 8 agents per GPU, set_target_vel, K_HOPS=3, RETURN_A COMM_RANGE=2.0'),
@@ -210,7 +211,7 @@ def run_gpu(args):
     st, act_np = make_inputs(w, E, T, seed=1234 + 4 + rank)
     use_graph = T >= K + 1
     sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T if use_graph else 2 * K + 2, ring=use_graph,
-                 want_A=not os.environ.get('MRS_EXP_NO_A'))
+                 want_A=w.get('A', True) and not os.environ.get('MRS_EXP_NO_A'))
     H.upload_state(sw, st)
     actions = torch.from_numpy(act_np).to(dev)
     if use_graph:
@@ -288,13 +289,13 @@ def run_gpu(args):
     adim = M._abi.ACTION_DIMS[sw.cfg.action_type]
     n_e = min(steps, args.e2e_steps)
     h2d = E * N * adim * 4
-    d2h = E * N * (6 + N) * 4
+    d2h = E * N * (6 + (N if sw.A_tape is not None else 0)) * 4
     e2e_value = e2e_pipe_value = None
     if n_e > 0:
         host_act = [torch.from_numpy(act_np[i % T]).pin_memory() for i in range(min(n_e, T))]
         dev_act = torch.empty(E, N, max(adim, 1), device=dev)
         Xh = torch.empty(E, N, 6).pin_memory()
-        Ah = torch.empty(E, N, N).pin_memory()
+        Ah = torch.empty(E, N, N).pin_memory() if sw.A_tape is not None else None
         for i in range(3):
             sw.step_host(host_act[i % len(host_act)], dev_act, Xh, Ah)
         barrier()
@@ -310,7 +311,7 @@ def run_gpu(args):
         n_p = min(n_e, T)
         ah = torch.from_numpy(act_np[:n_p]).pin_memory()
         Xhh = torch.empty(n_p, E, N, 6).pin_memory()
-        Ahh = torch.empty(n_p, E, N, N).pin_memory()
+        Ahh = torch.empty(n_p, E, N, N).pin_memory() if sw.A_tape is not None else None
         dev2 = torch.empty(2, E, N, max(adim, 1), device=dev)
         sw.rollout_host(ah, dev2, Xhh, Ahh)
         barrier()

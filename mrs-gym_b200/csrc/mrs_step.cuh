@@ -324,8 +324,27 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             if (a.A0) {
                 float* Arow = As + (size_t)s * N;
                 if (d.comm_inf) {
-                    if (valid)
+                    // COMM_RANGE = inf: ones - eye (MRS.py:119-121), written with the same lane-pair row sharing
+                    // as below (whole-sector STG.128) where the width is a compile-time constant
+                    if constexpr (GT != 0) {
+                        const int h = lane & 1;
+                        float* Arow0 = As + (size_t)(s & ~1u) * GT;
+                        const int d0 = (ai & ~1) - 4 * h;
+#pragma unroll
+                        for (int qq = 0; qq < GT / 8; ++qq) {
+                            const int col = 8 * qq + 4 * h;
+                            float v0[4], v1[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                v0[u] = (8 * qq + u == d0) ? 0.f : 1.f;
+                                v1[u] = (8 * qq + u == d0 + 1) ? 0.f : 1.f;
+                            }
+                            MRS_TAPE_ST(reinterpret_cast<float4*>(Arow0 + col), make_float4(v0[0], v0[1], v0[2], v0[3]));
+                            MRS_TAPE_ST(reinterpret_cast<float4*>(Arow0 + GT + col), make_float4(v1[0], v1[1], v1[2], v1[3]));
+                        }
+                    } else if (valid) {
                         for (int j = 0; j < N; ++j) Arow[j] = (j == ai) ? 0.f : 1.f;
+                    }
                 } else {
                     __syncwarp();
                     wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
