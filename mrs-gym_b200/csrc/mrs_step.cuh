@@ -239,22 +239,27 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
         }
         float* Xs = a.X0;       // tape slots of step t (they move down one slot per step)
         float* As = a.A0;
+        // the action of step t + 1 is loaded while step t is computed (mrs_step_many: a load at the top of
+        // every step had its whole latency exposed, 20 % of that kernel's stall samples); act0 holds the
+        // action of the coming step
+        if (!kStage) {
+            float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+            if (valid) (void)load_action<MODE>(a.actions, (size_t)s, tmp);
+            act0 = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
         for (int t = 0; t < a.T; ++t, Xs -= a.xstride, As -= a.astride) {
             // per-step event word: the registers behind it live only as long as the step needs them
             unsigned status = 0;
             unsigned n_agent_rows = 0, n_ground = 0;
             float rpm[4];
-            float act[4];
-            bool nan_act = false;
-            if (kStage && t == 0) {
-                act[0] = act0.x; act[1] = act0.y; act[2] = act0.z; act[3] = act0.w;
-                nan_act = kA > 0 && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || isnan(act0.w));
-            } else if (valid) {
-                nan_act = load_action<MODE>(a.actions, (size_t)t * S + s, act);
-            } else {
-                act[0] = act[1] = act[2] = act[3] = 0.f;
+            float act[4] = {act0.x, act0.y, act0.z, act0.w};
+            if (kA > 0 && valid && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || (kA == 4 && isnan(act0.w))))
+                status |= MRS_STATUS_NAN_ACTION;
+            if (t + 1 < a.T && valid) {
+                float tmp[4];
+                (void)load_action<MODE>(a.actions, (size_t)(t + 1) * S + s, tmp);
+                act0 = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
             }
-            if (nan_act) status |= MRS_STATUS_NAN_ACTION;
 
 #ifdef MRS_EXP_COPYONLY      // experiment (profiles/README.md): memory movement of a step only, no physics
             st.px += act[0] * 1e-12f;
