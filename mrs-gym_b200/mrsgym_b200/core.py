@@ -252,7 +252,7 @@ class Swarm:
     def capture_rollout(self, actions, T: int):
         """CUDA-graph a T-step rollout (launch-bound loops belong in graphs): returns a
         GraphRollout whose replay() advances all envs by T steps reading actions[t] from the
-        given device buffer (refill it between replays).  The swarm switches to ring mode (tape heads
+        given device buffer (refill it between replays).  Capturing itself leaves the swarm where it was.  The swarm switches to ring mode (tape heads
         wrap around, no slots are moved); T must be a multiple of the tape size, so every replay
         ends on the slots it started from (pass tape_slots=T to the constructor)."""
         return GraphRollout(self, actions, T)
@@ -439,7 +439,18 @@ class GraphRollout:
         side = torch.cuda.Stream(device=sw.device)
         side.wait_stream(torch.cuda.current_stream(sw.device))
         with torch.cuda.stream(side):
-            self._body()            # warm-up outside capture (lazy module load, occupancy query)
+            # warm-up outside capture (lazy module load, per-function attributes): it advances the swarm by T
+            # steps, so everything a later step can read is put back afterwards -- state, PID planes, counters
+            # and the K+1 observation windows (the rest of the tapes is history nobody can reach any more)
+            keep = [(t, t.clone()) for t in (sw.state, sw.ctrl, sw.status, sw.stats, sw.rpm) if t is not None]
+            for tape, which in ((sw.X_tape, 1), (sw.A_tape, 2)):
+                if tape is not None:
+                    keep += [(tape[sl], tape[sl].clone()) for sl in sw.window_slots(which)]
+            heads = (sw.hx, sw.ha, sw.a_empty, sw.launches)
+            self._body()
+            for dst, src in keep:
+                dst.copy_(src)
+            sw.hx, sw.ha, sw.a_empty, sw.launches = heads
             torch.cuda.synchronize(sw.device)
             with torch.cuda.graph(self.graph, stream=side):
                 before = sw.launches

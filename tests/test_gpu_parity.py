@@ -568,3 +568,27 @@ def test_tiled_pair_path_ragged(E, N, mode):
     H.upload_state(sw2, st)
     sw2.step(_dev(act[0]))
     assert torch.equal(sw.state, sw2.state)
+
+
+def test_capture_rollout_leaves_the_swarm_untouched():
+    """capture_rollout warms the launch path up outside the capture; that must not advance the swarm: a captured
+    twin replayed once equals T plain steps from the same start, windows included."""
+    E, N, K, T = 37, 8, 2, 12
+    rng = np.random.default_rng(123)
+    st = H.random_state(rng, E, N)
+    act = _dev(H.random_actions(rng, 'set_target_vel', T, E, N))
+    a = _swarm(E, N, 'set_target_vel', K, 1.5, tape_slots=T, ring=True)
+    b = _swarm(E, N, 'set_target_vel', K, 1.5, tape_slots=T, ring=True)
+    for sw in (a, b):
+        H.upload_state(sw, st)
+        sw.step(act[0])                     # some history in the windows
+    before = (a.state.clone(), a.ctrl.clone().nan_to_num(nan=-7.0), a.X_window().clone(), a.A_window().clone())
+    roll = a.capture_rollout(act, T)
+    assert torch.equal(a.state, before[0]) and torch.equal(a.ctrl.nan_to_num(nan=-7.0), before[1])
+    assert torch.equal(a.X_window(), before[2]) and torch.equal(a.A_window(), before[3])
+    roll.replay()
+    for t in range(T):
+        b.step(act[t])
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(a.X_window(), b.X_window()) and torch.equal(a.A_window(), b.A_window())
+    assert a.read_stats() == b.read_stats()
