@@ -22,6 +22,12 @@ import torch
 from . import _abi
 
 
+# torch.cuda.current_stream() builds a Stream object (~7 us per call, a tenth of a small env.step); the raw
+# handle is all the C ABI needs
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None) or (
+    lambda idx: torch.cuda.current_stream(idx).cuda_stream)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -94,7 +100,7 @@ class Swarm:
     def _stream(self):
         if torch.cuda.current_device() != self.device.index:
             raise _abi.MrsError('current CUDA device changed to %d; the swarm lives on %s' % (torch.cuda.current_device(), self.device))
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(_raw_stream(self.device.index))
 
     def set_action_type(self, action_type):
         if action_type is None:

@@ -1,9 +1,1 @@
-Q="--warmup 5 --no-cpu --clock-seconds 0 --e2e-steps 0"
-for v in base cta2 cta4 base cta2; do
-  if [ $v = base ]; then L=""; else L="MRS_B200_LIB=$PWD/build_variants/lib_$v.so"; fi
-  env $L python bench.py --steps 400 $Q > gpurun_out/b69_$v.json 2>>gpurun_out/b69.err; python -c "
-import json
-d=json.load(open('gpurun_out/b69_$v.json'))
-print('$v value %.3e ms/step %.4f frac %.3f | flushed ms %.4f frac %.3f | many %s'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median'],d['l2_flushed']['frac'],d['step_many'] and '%.3e'%d['step_many']['value']))"
-done
-tail -2 gpurun_out/b69.err
+python tools/_prof_host.py 2>&1 | tail -50
