@@ -80,12 +80,15 @@ class Swarm:
         self.status = torch.zeros(1, device=dev, dtype=torch.int32)
         self.stats = torch.zeros(_abi.STATS_SLOTS, device=dev, dtype=torch.int64)
         self.bufs = _abi.MrsBuffers()
+        self._cfg_ref, self._bufs_ref = C.byref(self.cfg), C.byref(self.bufs)     # reused by the per-step calls
+        self._mrs_step = self.lib.mrs_step
         self._bind()
         self.hx = self.L - self.K - 1
         self.ha = self.L - self.K - 1
         self.ring = bool(ring)     # True: heads wrap around the tape, nothing is ever moved (graph rollouts)
         self.a_empty = True        # no A slice pushed since the last full reset (MRS.py:186)
         self.launches = 0          # kernel launches issued through the ABI (bench: gpu_launches)
+        self._launches_per_step = self._step_launches()
 
     # ------------------------------------------------------------------ plumbing
     def _bind(self):
@@ -222,9 +225,10 @@ class Swarm:
         self._check_actions(actions)
         hx = self._make_room(1) - 1 if self.X_tape is not None else 0
         ha = self._make_room(2) - 1 if self.A_tape is not None else 0
-        _abi.check(self.lib.mrs_step(C.byref(self.cfg), C.byref(self.bufs), _ptr(actions), hx, ha, self._stream()),
-                   'mrs_step')
-        self.launches += self._step_launches()
+        rc = self._mrs_step(self._cfg_ref, self._bufs_ref, _ptr(actions), hx, ha, self._stream())
+        if rc:
+            _abi.check(rc, 'mrs_step')
+        self.launches += self._launches_per_step
         if self.X_tape is not None:
             self.hx = hx
         if self.A_tape is not None:

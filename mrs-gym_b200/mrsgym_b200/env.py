@@ -392,6 +392,12 @@ class MRS:
     # ------------------------------------------------------------------ step
     def _prep_actions(self, actions):
         adim = self.swarm.action_dim
+        sw = self.swarm
+        # fast path of a training loop: a float32 device tensor of the right size needs no conversion at all
+        if (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.float32
+                and actions.is_contiguous() and actions.numel() == sw.S * adim and actions.device == sw.device
+                and not actions.requires_grad and self.CHECK_NAN is not True):
+            return actions.view(self.N_ENVS, self.N_AGENTS, adim)
         host = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
         actions = torch.as_tensor(actions).detach()
         if actions.dtype != torch.float32:

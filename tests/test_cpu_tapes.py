@@ -70,6 +70,9 @@ def make_swarm(K, L, ring=False):
     sw.a_empty = True
     sw.lib = FakeLib(sw)
     sw._stream = lambda: None
+    sw._mrs_step = sw.lib.mrs_step                      # what Swarm.__init__ caches for the per-step call
+    sw._cfg_ref, sw._bufs_ref = ctypes.byref(sw.cfg), ctypes.byref(sw.bufs)
+    sw._launches_per_step = 1
     return sw
 
 

@@ -1,15 +1,19 @@
-"""Wall-clock latency of MRS.step for the README example (C1: one env, 3 agents) and small batches."""
+"""Wall-clock latency of MRS.step (closed loop: one Python call and one launch per step, nothing overlapped by a
+graph) for the README example (C1: one env, 3 agents), small batches and the C5 shape."""
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', 'mrs-gym_b200'))
 import mrsgym_b200 as mrsgym
-for E, N, mode in ((1, 3, 'set_target_vel'), (1, 32, 'set_target_pos'), (256, 32, 'set_target_pos'), (4096, 16, 'set_control')):
-    env = mrsgym.make('mrs-v0', N_ENVS=E, N_AGENTS=N, K_HOPS=3 if N == 32 else 0, COMM_RANGE=2.0, ACTION_TYPE=mode,
+for E, N, mode in ((1, 3, 'set_target_vel'), (1, 32, 'set_target_pos'), (256, 32, 'set_target_pos'), (4096, 16, 'set_control'),
+                   (65536, 8, 'set_speeds')):
+    env = mrsgym.make('mrs-v0', N_ENVS=E, N_AGENTS=N, K_HOPS=3 if N in (8, 32) else 0, COMM_RANGE=2.0, ACTION_TYPE=mode,
                       START_POS=torch.rand(N, 3) * 4 + torch.tensor([0., 0, 2]), START_ORI=torch.zeros(N, 3))
     adim = env.swarm.action_dim
     a_host = torch.zeros(E, N, adim) if E > 1 else torch.zeros(N, adim)
     if mode == 'set_control':
         a_host[..., 0] = 9.81
+    if mode == 'set_speeds':
+        a_host[...] = 14475.8
     a_dev = a_host.cuda()
     for name, a in (('host actions', a_host), ('device actions', a_dev)):
         for _ in range(20):
