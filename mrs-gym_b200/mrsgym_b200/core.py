@@ -63,7 +63,15 @@ class Swarm:
         self.cfg.dt, self.cfg.gravity = float(dt), float(gravity)
         self.cfg.phys.agent_radius = float(agent_radius)
         self.D = _abi.STATE_DIMS[state_layout] if state_layout != _abi.X_NONE else int(custom_D)
-        self.L = int(tape_slots) if tape_slots else max(2 * self.K + 2, 16)
+        if tape_slots:
+            self.L = int(tape_slots)
+        else:
+            # default history depth: when a head reaches slot 0 the K newest slots move to the top (K copies of
+            # a whole slice), so the move is amortised over L - K steps; deep tapes make it negligible.  Up to
+            # 256 slots within a ~2 GB budget for X and A together (C5: 29 MB per slot -> 68 slots).
+            D_ = _abi.STATE_DIMS[state_layout] if state_layout != _abi.X_NONE else int(custom_D)
+            slot_bytes = 4 * self.S * (max(D_, 0) + (self.N if want_A else 0))
+            self.L = max(2 * self.K + 2, 16, min(256, int(2e9 // max(slot_bytes, 1))))
         if self.L < (self.K + 1 if ring else 2 * self.K + 2):
             raise ValueError('tape_slots must be >= 2*K_HOPS+2 (K_HOPS+1 in ring mode)')
         self.cfg.L = self.L

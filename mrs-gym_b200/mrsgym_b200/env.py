@@ -178,6 +178,7 @@ class MRS:
             self.START_ORI = self.START_ORI.expand(self.N_AGENTS, -1)
         self._batched = (self.N_ENVS > 1) if self.BATCHED is None else bool(self.BATCHED)
         self._copy = (not self._batched) if self.COPY_OBS is None else bool(self.COPY_OBS)
+        self._views = {}
         # state_fn: None / 'pos_vel' / 'full' -> fused in the step kernel; callable -> python
         if state_fn is None:
             state_fn = 'pos_vel'
@@ -244,11 +245,28 @@ class MRS:
             w = w[:, 0]
         return w.clone() if self._copy else w
 
+    def _window(self, which):
+        """Newest-first K+1 window of tape `which` in the reference's layout.  The window of a given head slot
+        is always the same view of the (static) tape, so views are built once per head position: a training
+        loop pays a dict lookup instead of slicing + permuting two tensors per step."""
+        sw = self.swarm
+        head = sw.hx if which == 1 else sw.ha
+        tape = sw.X_tape if which == 1 else sw.A_tape
+        if tape is None or self._copy or (sw.ring and head + sw.K + 1 > sw.L):     # copies / wrapped windows are fresh
+            return self._shape(sw.X_window() if which == 1 else sw.A_window())
+        key = (which, head, tape.data_ptr())
+        v = self._views.get(key)
+        if v is None:
+            if len(self._views) > 4 * sw.L + 8:
+                self._views.clear()
+            v = self._views[key] = self._shape(sw.X_window() if which == 1 else sw.A_window())
+        return v
+
     def get_Xk(self):
-        return self._shape(self.swarm.X_window())
+        return self._window(1)
 
     def get_Ak(self):
-        return self._shape(self.swarm.A_window())
+        return self._window(2)
 
     def calc_Xk(self):
         """MRS.calc_Xk (MRS.py:87-95): push X of the current state."""

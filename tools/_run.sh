@@ -1,6 +1,6 @@
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 python tools/latency_c1.py 2>&1 | tail -8
-python - <<'PY'
+python - <<"PY"
 import os, sys, time, torch
 sys.path.insert(0, 'mrs-gym_b200')
 import mrsgym_b200 as mrsgym
