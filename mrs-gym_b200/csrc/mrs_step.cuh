@@ -163,14 +163,16 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
         unsigned long long tns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
         if (lane == 0 && trace_i < 8) trace[trace_i] = tns;
-        if (lane == 0 && trace_i == 0) atomicMin(agg + 0, tns);
-        if (lane == 0 && trace_i == 1) atomicMax(agg + 1, tns);
+        // aggregates: one atomic per CTA (per-warp atomics on one address -- 8 k per launch -- stretched the
+        // kernel boundary by ~6 us and showed up as a gap that the production build does not have)
+        if (threadIdx.x == 0 && trace_i == 0) atomicMin(agg + 0, tns);
+        if (threadIdx.x == 0 && trace_i == 1) atomicMax(agg + 1, tns);
         ++trace_i;
     };
-    auto stamp_end = [&]() {
+    auto stamp_end = [&]() {            // called after the CTA's final barrier: the CTA's end
         unsigned long long tns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-        if (lane == 0) { atomicMax(agg + 2, tns); atomicMin(agg + 3, tns); }
+        if (threadIdx.x == 0) { atomicMax(agg + 2, tns); atomicMin(agg + 3, tns); }
     };
     stamp();
 #endif

@@ -1,15 +1,10 @@
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python tools/latency_c1.py 2>&1 | tail -8
-python - <<"PY"
-import os, sys, time, torch
-sys.path.insert(0, 'mrs-gym_b200')
-import mrsgym_b200 as mrsgym
-env = mrsgym.make('mrs-v0', N_ENVS=65536, N_AGENTS=8, K_HOPS=3, COMM_RANGE=2.0, ACTION_TYPE='set_speeds')
-env.reset()
-a = torch.full((65536, 8, 4), 14475.8, device='cuda')
-for _ in range(50): env.step(a)
-torch.cuda.synchronize(); t0 = time.perf_counter(); n = 2000
-for _ in range(n): X, r, d, info = env.step(a)
-torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n
-print('closed-loop MRS.step at C5, device actions: %.1f us per env.step (%.3g agent-steps/s)' % (dt * 1e6, 65536 * 8 / dt))
-PY
+Q="--warmup 5 --no-cpu --clock-seconds 0 --e2e-steps 0"
+for pd in 0 16 8 32 16; do
+MRS_B200_POOL_DIV=$pd python bench.py --steps 400 $Q > gpurun_out/b71_$pd.json 2>>gpurun_out/b71.err; python -c "
+import json
+d=json.load(open('gpurun_out/b71_$pd.json'))
+print('pool 1/$pd value %.3e ms/step %.4f frac %.3f | flushed ms %.4f frac %.3f | many %s'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median'],d['l2_flushed']['frac'],d['step_many'] and '%.3e'%d['step_many']['value']))"
+done
+tail -2 gpurun_out/b71.err
+timeout 200 python tools/soak.py c5 5000 2>&1 | tail -1

@@ -10,7 +10,7 @@ w = bench.WORKLOADS['c5']
 E, N, K = w['E'], w['N'], w['K']
 T = 8
 st, act = bench.make_inputs(w, E, T, 1)
-sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T + 2 * K + 2)
+sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T, ring=True)
 sw.scratch = torch.zeros(max(7, sw.lib.mrs_scratch_planes(sw.E, sw.N)), sw.S, device='cuda')
 sw._bind()
 H.upload_state(sw, st)
