@@ -283,6 +283,37 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             __syncwarp();
             float dw = 0.f;
             bool near = false;
+#ifndef MRS_PAIR_ONCE
+#define MRS_PAIR_ONCE 1
+#endif
+            if constexpr (MRS_PAIR_ONCE && GT != 0) {
+                // Every unordered pair is evaluated ONCE: in round k lane a handles the pair (a, a + k mod N), so
+                // rounds 1 .. N/2 - 1 cover each pair exactly once and round N/2 covers its pairs from both ends.
+                // The downwash acts on whichever of the two flies lower (dz > 0 seen from below), so one evaluation
+                // with |dz| serves both; the partner's share and the squared distance travel by shuffle.
+                if (MODE != MRS_NO_ACTION || pair_contact) {
+                    float dmin = 3.0e38f;
+#pragma unroll
+                    for (int k = 1; k <= GT / 2; ++k) {
+                        const float4 pj = wpos[gb + ((ai + k) & (GT - 1))];
+                        const float rx = pj.x - st.px, ry = pj.y - st.py, rz = pj.z - st.pz;
+                        const float dxy2 = rx * rx + ry * ry;
+                        const float d2 = dxy2 + rz * rz;
+                        float f = 0.f;
+                        if (MODE != MRS_NO_ACTION) f = downwash_pair(c.quad, d, dxy2, fabsf(rz));   // 0 when dz == 0
+                        dw += (rz > 0.f) ? f : 0.f;
+                        dmin = fminf(dmin, d2);
+                        if (k < GT / 2) {
+                            const int src = gb + ((ai - k) & (GT - 1));       // the lane whose round-k partner I am
+                            const float got = __shfl_sync(kFull32, (rz < 0.f) ? f : 0.f, src);
+                            const float gd2 = __shfl_sync(kFull32, d2, src);
+                            if (MODE != MRS_NO_ACTION) dw += got;
+                            dmin = fminf(dmin, gd2);
+                        }
+                    }
+                    near = dmin < d.lim2;
+                }
+            } else
             if (MODE != MRS_NO_ACTION || pair_contact) {
 #pragma unroll 8
                 for (int r = 1; r < G; ++r) {
