@@ -9,8 +9,9 @@ GPU): 65536 envs x 8 agents PER GPU (weak scaling), ACTION_TYPE set_speeds, K_HO
 (RETURN_A), built-in state_fn cat(pos, vel).  A "step" is one env.step of all envs = ONE launch of
 step_group_kernel that reads and writes the whole state in HBM.
 
-Timed region: `steps` steps issued as CUDA-graph replays of T-step rollouts (Swarm.capture_rollout;
-actions of every step are distinct device buffers), bracketed by barrier + synchronize, CUDA events
+Timed region: `steps` steps issued as CUDA-graph replays of T-step rollouts (T = min(steps, 100);
+Swarm.capture_rollout; actions of every step are distinct device buffers) plus steps % T plain
+launches, bracketed by barrier + synchronize, CUDA events
 on the launching stream, max over ranks.  L2: no flush in the headline loop -- per step the kernel
 streams actions + X + A (38 MB at c5) that are distinct every step, while the 27 MB state is
 re-read from wherever the previous step left it (that is the real access pattern of a rollout);
@@ -205,8 +206,9 @@ def run_gpu(args):
     E = E0 if args.scaling == 'weak' else max(1, E0 // world)
     N, K = w['N'], w['K']
     steps, warmup = args.steps, max(args.warmup, 3)
-    T = max(d for d in range(1, min(steps, args.graph_steps) + 1) if steps % d == 0)
-    replays = steps // T
+    # the timed region is `replays` replays of a T-step graph plus `rem` plain single-step launches at its end
+    T = min(steps, args.graph_steps)
+    replays, rem = steps // T, steps % T
 
     st, act_np = make_inputs(w, E, T, seed=1234 + 4 + rank)
     use_graph = T >= K + 1
@@ -222,6 +224,7 @@ def run_gpu(args):
 
             def replay(self):
                 sw.step_many_single(actions, T)
+        _Plain.launches_per_replay = T * sw._step_launches()
         roll = _Plain()
 
     def barrier():
@@ -239,6 +242,8 @@ def run_gpu(args):
         e0.record()
         for _ in range(replays):
             roll.replay()
+        for t in range(rem):                      # only when `steps` is not a multiple of the graph length
+            sw.step(actions[t])
         if world > 1:
             stats = sw.allreduce_stats()          # the per-rollout statistics reduction (NCCL)
         e1.record()
@@ -250,7 +255,7 @@ def run_gpu(args):
             for _ in range(max(1, 2000 // T)):
                 roll.replay()
             torch.cuda.synchronize(dev)
-    gpu_launches = replays * roll.launches_per_replay
+    gpu_launches = replays * roll.launches_per_replay + rem * sw._step_launches()
     ms = D.max_over_ranks(ms, dev)
     agent_steps = float(E) * N * steps * world
     value = agent_steps / (ms * 1e-3)
@@ -347,7 +352,8 @@ def run_gpu(args):
         'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {**workload_config(w, E, world),
-                   'launch': ('CUDA graph of %d single-step launches, %d replays' if use_graph else '%d plain launches x %d') % (T, replays),
+                   'launch': (('CUDA graph of %d single-step launches, %d replays' if use_graph else '%d plain launches x %d') % (T, replays))
+                             + (' + %d plain launches' % rem if rem else ''),
                    'l2': 'inputs larger than L2: the timed region consumes %.0f MB of distinct action buffers and writes '
                          '%.0f MB of distinct X/A tape slots (L2 = 126 MB); no buffer is re-read across iterations -- the '
                          'state is loop-carried (written by step t, read by step t+1, as in any rollout).  l2_flushed '

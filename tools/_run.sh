@@ -1,9 +1,7 @@
-Q="--warmup 5 --no-cpu --clock-seconds 0 --e2e-steps 0"
-for v in base NOSTATESTORE NOXA; do
-  if [ $v = base ]; then L=""; else L="MRS_B200_LIB=$PWD/build_variants/lib_$v.so"; fi
-  env $L python bench.py --steps 400 $Q > gpurun_out/b73_$v.json 2>>gpurun_out/b73.err; python -c "
+for args in "--steps 7 --warmup 2" "--steps 3 --warmup 1" "--steps 101 --warmup 3" "--steps 250 --warmup 5" "--steps 200 --warmup 5"; do
+python bench.py $args --no-cpu > gpurun_out/b74.json 2>gpurun_out/b74.err || { echo FAIL $args; tail -5 gpurun_out/b74.err; }
+python -c "
 import json
-d=json.load(open('gpurun_out/b73_$v.json'))
-print('$v value %.3e ms/step %.4f frac %.3f | flushed ms %.4f | many %s'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median'],d['step_many'] and '%.3e'%d['step_many']['value']))"
+d=json.load(open('gpurun_out/b74.json'))
+print('$args', 'value %.3e ms/step %.4f steps %d warmup %d launches %d e2e %s launch %s'%(d['value'],d['ms_per_step'],d['steps'],d['warmup'],d['gpu_launches'],d['e2e']['value'], d['config']['launch']))"
 done
-tail -2 gpurun_out/b73.err
