@@ -56,6 +56,9 @@ WORKLOADS = {
                 desc='65536 envs x 8 agents per GPU, set_target_vel, K_HOPS=3, RETURN_A COMM_RANGE=2.0'),
     'c5p': dict(E=65536, N=8, mode='set_target_pos', K=3, R=2.0, spacing=1.0, z0=2.5, B=220,
                 desc='65536 envs x 8 agents per GPU, set_target_pos, K_HOPS=3, RETURN_A COMM_RANGE=2.0'),
+    # not a BASELINE config: a mid-size swarm at scale (thread-per-agent kernels of the 32 < N <= 128 range)
+    'm64': dict(E=1024, N=64, mode='set_target_vel', K=1, R=2.0, spacing=1.0, z0=2.5, B=104 + 12 + 120 + 24 + 256,
+                desc='1024 envs x 64 agents, set_target_vel, K_HOPS=1, RETURN_A COMM_RANGE=2.0'),
     'c4': dict(E=1, N=4096, mode='set_force', K=0, R=2.0, spacing=1.0, z0=2.0, B=16548,
                desc='1 env x 4096 agents, set_force, adjacency dominated (BASELINE configs[3])'),
 }

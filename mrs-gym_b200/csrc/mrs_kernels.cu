@@ -31,6 +31,45 @@ adjacency_flat_kernel(const float* __restrict__ pos, size_t cs, size_t as, float
     }
 }
 
+// Quad version for N < 128, N % 4 == 0 (swarms of 36 .. 124 agents, many envs): one thread per row and column
+// quad, lanes along the columns, so a warp's STG.128 writes whole rows (N = 64: two rows = 512 contiguous
+// bytes).  The positions of the few envs a CTA touches are staged in shared memory once: no per-element
+// div / mod, no scattered position loads (the flat kernel needs 6 loads and ~25 instructions per element).
+constexpr int kQuadTile = 3 * 128;
+__global__ void __launch_bounds__(kBlock)
+adjacency_quad_kernel(const float* __restrict__ pos, size_t cs, size_t as, float* __restrict__ A, int E, int N,
+                      float s_max, int comm_inf) {
+    __shared__ float4 tile[kQuadTile];
+    const unsigned Q = (unsigned)N / 4u;
+    const size_t nquads = (size_t)E * N * Q;
+    const size_t g0 = (size_t)blockIdx.x * kBlock;
+    const size_t gl = (g0 + kBlock < nquads ? g0 + kBlock : nquads) - 1;
+    const size_t e_first = (g0 / Q) / (unsigned)N, e_last = (gl / Q) / (unsigned)N;      // envs of the CTA's rows
+    const size_t t0 = e_first * (unsigned)N;
+    const unsigned count = (unsigned)((e_last + 1) * (unsigned)N - t0);                   // <= 3 N
+    for (unsigned idx = threadIdx.x; idx < count; idx += kBlock) {
+        const size_t sj = (t0 + idx) * as;
+        tile[idx] = make_float4(pos[sj], pos[cs + sj], pos[2 * cs + sj], 0.f);
+    }
+    __syncthreads();
+    const size_t g = g0 + threadIdx.x;
+    if (g >= nquads) return;
+    const size_t row = g / Q;                       // agent slot of the row
+    const unsigned q = (unsigned)(g - row * Q);
+    const unsigned env_base = (unsigned)((row / (unsigned)N) * (unsigned)N - t0);
+    const unsigned i = (unsigned)(row - (row / (unsigned)N) * (unsigned)N);
+    const float4 pi = tile[(unsigned)(row - t0)];
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned j = 4u * q + (unsigned)u;
+        const float4 pj = tile[env_base + j];
+        const float hit = comm_inf ? 1.f : adjacency_pair(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, s_max);
+        v[u] = (j == i) ? 0.f : hit;
+    }
+    __stcs(reinterpret_cast<float4*>(A + row * (unsigned)N + 4u * q), make_float4(v[0], v[1], v[2], v[3]));
+}
+
 // Tiled version for N >= 128, N % 4 == 0.  CTA = kRowTile rows x 512 columns of one env; each
 // lane keeps its 4 column positions in registers, row positions are broadcast from shared
 // memory, each warp store is 512 contiguous bytes of one A row.
@@ -308,6 +347,10 @@ int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, in
         const int row_tiles = (N + kRowTile - 1) / kRowTile;
         dim3 grid((unsigned)(col_tiles * row_tiles), (unsigned)E);
         adjacency_tiled_kernel<<<grid, kBlock, 0, st>>>(pos, cs, as, A, E, N, s_max, comm_inf);
+    } else if (N > 32 && (N & 3) == 0 && (size_t)E * N * (N / 4) < 0x7fffffffull * (size_t)kBlock) {
+        const size_t nquads = (size_t)E * N * (N / 4);
+        adjacency_quad_kernel<<<(unsigned)((nquads + kBlock - 1) / kBlock), kBlock, 0, st>>>(pos, cs, as, A, E, N, s_max,
+                                                                                             comm_inf);
     } else {
         const size_t total = (size_t)E * N * N;
         const size_t blocks = (total + 255) / 256;

@@ -602,6 +602,68 @@ step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Der
     agent_pre<MODE>(c, d, b, actions, S, s, dw, near && pair_contact);
 }
 
+// ------------------------------------------------------------------------------ pre pass, 32 < N <= 128, many agents
+// One THREAD per agent.  A CTA covers 128 consecutive agent slots (they may span several envs); the positions
+// of all envs it touches go to shared memory once (<= 128 + 2 (N - 1) slots) and every thread walks the N
+// partners of its own env there with the pair loop of pair_tile_kernel (17 instructions per pair without the
+// downwash term, warp vote around it, `0 < d2 < lim2` on the float bits so that the agent itself needs no
+// special case), then runs the per-agent part itself.  With 8 lanes per agent (step_pre_kernel) seven of the
+// eight lanes idle through the ~500 instructions of the per-agent part and a pair costs 45 instructions;
+// this shape needs a quarter of the lane-instructions once there are enough agents to fill the GPU.
+constexpr int kMidTile = kBlock + 2 * (128 - 1);
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+step_mid_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
+                    const float* __restrict__ actions) {
+    __shared__ float4 tile[kMidTile];
+    const int N = c.N;
+    const unsigned S = (unsigned)c.E * (unsigned)N;
+    const unsigned s0 = blockIdx.x * (unsigned)kBlock;
+    const unsigned sl = min(s0 + (unsigned)kBlock, S) - 1u;            // last slot of this CTA
+    const unsigned e_first = s0 / (unsigned)N, e_last = sl / (unsigned)N;
+    const unsigned t0 = e_first * (unsigned)N;                          // first slot in the tile
+    const unsigned count = (e_last + 1u) * (unsigned)N - t0;
+    for (unsigned idx = threadIdx.x; idx < count; idx += kBlock)
+        tile[idx] = make_float4(b.state[t0 + idx], b.state[(size_t)S + t0 + idx], b.state[2 * (size_t)S + t0 + idx], 0.f);
+    __syncthreads();
+    const unsigned s = s0 + threadIdx.x;
+    const bool valid = s < S;
+    const unsigned sv = valid ? s : sl;
+    const unsigned base = (sv / (unsigned)N) * (unsigned)N - t0;       // my env's first entry in the tile
+    const float4 me = tile[sv - t0];
+    const bool pair_contact = c.phys.agent_contact && N > 1;
+    const unsigned lim_m1 = __float_as_uint(d.lim2) - 1u;
+    float dw = 0.f;
+    bool near = false;
+    for (int j0 = 0; j0 < N; j0 += 4) {
+        float dxy2[4], rz[4];
+        bool live[4], any_live = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = min(j0 + u, N - 1);                           // the tail repeats the last partner ...
+            const bool in = j0 + u < N;                                 // ... without counting it
+            const float4 pj = tile[base + j];
+            const float rx = pj.x - me.x, ry = pj.y - me.y;
+            rz[u] = pj.z - me.z;
+            dxy2[u] = rx * rx + ry * ry;
+            const float d2 = dxy2[u] + rz[u] * rz[u];
+            near = near || (in && __float_as_uint(d2) - 1u < lim_m1);
+            const float beta = c.quad.dw2 * rz[u] + c.quad.dw3;
+            live[u] = MODE != MRS_NO_ACTION && in && rz[u] > 0.f && dxy2[u] < 100.f && !(dxy2[u] > 208.f * beta * beta);
+            any_live = any_live || live[u];
+        }
+        if (MODE != MRS_NO_ACTION && __any_sync(kFull32, any_live)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float f = downwash_pair(c.quad, d, dxy2[u], rz[u]);
+                dw += live[u] ? f : 0.f;
+            }
+        }
+    }
+    if (valid) agent_pre<MODE>(c, d, b, actions, S, s, dw, near && pair_contact);
+}
+
 // ------------------------------------------------------------------------------ pair pass for N > 128
 // n-body tiling.  A CTA owns 128 agents of one env (one per thread, own position in registers) and one
 // of `nsplit` slices of the partner range; partner positions go through shared memory in tiles of 128
@@ -882,10 +944,43 @@ static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffer
     return last_error();
 }
 
+// 32 < N <= 128 with enough agents to fill the GPU: one thread per agent in both passes
+template <int MODE>
+static int launch_mid(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
+    const size_t S = (size_t)c.E * c.N;
+    constexpr int A = ModeTraits<MODE>::A;
+    const unsigned blocks = (unsigned)((S + kBlock - 1) / kBlock);
+    SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
+    for (int t = 0; t < a.T; ++t) {
+        const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
+        step_mid_pre_kernel<MODE><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
+        if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
+        step_post_kernel<1><<<blocks, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
+        if (b.A_tape) {
+            cudaStream_t as = st;
+            if (L) {
+                if (cudaEventRecord(L->posted, st) != cudaSuccess) return MRS_ERR_CUDA;
+                if (cudaStreamWaitEvent(L->s, L->posted, 0) != cudaSuccess) return MRS_ERR_CUDA;
+                as = L->s;
+            }
+            const int rc = launch_adjacency(b.state, S, 1, b.A_tape + (size_t)(a.slot_a - t) * S * c.N, c.E, c.N, d.s_max,
+                                            d.comm_inf, as);
+            if (rc) return rc;
+            if (L && cudaEventRecord(L->adj_done, L->s) != cudaSuccess) return MRS_ERR_CUDA;
+        }
+    }
+    if (L && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
+    return last_error();
+}
+
 template <int MODE>
 static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     if (!b.scratch) return MRS_ERR_ARG;
     if ((unsigned long long)c.E * c.N * 32ull >= 0x7fffffffull * (unsigned long long)kBlock) return MRS_ERR_UNSUPPORTED;
+    // lanes-per-agent kernels fill the GPU with few agents (latency); thread-per-agent kernels do a quarter of
+    // the work once there are enough of them
+    static const long long mid_min = env_int("MRS_B200_MID_MIN_AGENTS", 32768);
+    if (c.N <= 128 && (long long)c.E * c.N >= mid_min) return launch_mid<MODE>(c, d, b, a, st);
     if (c.N <= 128) return launch_wide_lpa<MODE, 8, 8>(c, d, b, a, st);
     return launch_wide_lpa<MODE, 128, 32>(c, d, b, a, st);     // n-body tiles (pair_tile_kernel) + agent_pre_kernel
 }

@@ -58,7 +58,8 @@ def _check_delta(tag, s0, g1, r1):
 
 
 # ------------------------------------------------------------------------------ adjacency
-@pytest.mark.parametrize('E,N,R', [(1, 3, 1.5), (64, 8, 2.0), (16, 32, 2.0), (7, 5, 0.9), (3, 33, 1.7),
+@pytest.mark.parametrize('E,N,R', [(1, 3, 1.5), (64, 8, 2.0), (16, 32, 2.0), (7, 5, 0.9), (3, 33, 1.7), (5, 64, 2.0),
+                                   (9, 36, 1.2), (3, 100, float('inf')), (700, 64, 2.0), (2, 124, 1.6),
                                    (2, 128, 2.0), (1, 500, 3.0), (1, 4096, 2.0), (4, 16, float('inf')),
                                    (1, 256, float('inf'))])
 def test_adjacency_bit_exact_vs_torch_cpu(E, N, R):
@@ -592,3 +593,34 @@ def test_capture_rollout_leaves_the_swarm_untouched():
     assert torch.equal(a.state, b.state)
     assert torch.equal(a.X_window(), b.X_window()) and torch.equal(a.A_window(), b.A_window())
     assert a.read_stats() == b.read_stats()
+
+
+@pytest.mark.parametrize('E,N,mode', [(512, 64, 'set_target_vel'), (400, 100, 'set_control'), (1000, 33, 'set_speeds'),
+                                      (260, 128, 'set_target_pos')])
+def test_thread_per_agent_mid_path(E, N, mode):
+    """32 < N <= 128 with >= 32768 agents: step_mid_pre_kernel + step_post_kernel<1> (one thread per agent, the
+    CTA's 128 slots span several envs).  One step in the contact regime against the oracle, A bit-exact, and a
+    3-step mrs_step_many equal to three single steps."""
+    rng = np.random.default_rng(11 + N)
+    st = H.random_state(rng, E, N, spacing=0.55, jitter=0.05)
+    act = H.random_actions(rng, mode, 3, E, N, start_pos=st['pos'])
+    sw = _swarm(E, N, mode, 1, 1.5)
+    H.upload_state(sw, st)
+    sw.step(_dev(act[0]))
+    ref = H.make_spec(E, N, mode, 1, 1.5, st)
+    ref.step(act[0])
+    g1, r1 = H.read_state(sw), H.spec_state(ref)
+    # contact rows switch on thresholds (dist < margin, rhs > 0): among tens of thousands of agents a few sit
+    # within float32 rounding of one, so the band of the small contact test holds for all but a handful
+    for k, tol in (('vel', 2e-4), ('pos', 2e-6), ('angvel', 1e-4)):
+        err = np.abs(g1[k] - r1[k]).max(axis=-1)
+        assert np.mean(err > tol) < 1e-3 and err.max() <= 50 * tol, (k, float(err.max()), float(np.mean(err > tol)))
+    X = sw.X_window()[0].cpu().numpy()
+    np.testing.assert_array_equal(sw.A_window()[0].cpu().numpy(), spec.adjacency(X[..., :3], 1.5))
+    assert sw.read_stats()['agent_contact_rows'] > 0
+    sw.step(_dev(act[1]))
+    sw.step(_dev(act[2]))
+    sw2 = _swarm(E, N, mode, 1, 1.5)
+    H.upload_state(sw2, st)
+    sw2.step_many(_dev(act), 3)
+    assert torch.equal(sw.state, sw2.state) and torch.equal(sw.A_window(), sw2.A_window())

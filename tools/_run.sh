@@ -1,7 +1,7 @@
-for args in "--steps 7 --warmup 2" "--steps 3 --warmup 1" "--steps 101 --warmup 3" "--steps 250 --warmup 5" "--steps 200 --warmup 5"; do
-python bench.py $args --no-cpu > gpurun_out/b74.json 2>gpurun_out/b74.err || { echo FAIL $args; tail -5 gpurun_out/b74.err; }
-python -c "
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+Q="--warmup 5 --no-cpu --clock-seconds 0 --e2e-steps 0"
+python bench.py --steps 200 --workload m64 $Q > gpurun_out/b77.json 2>>gpurun_out/b77.err; python -c "
 import json
-d=json.load(open('gpurun_out/b74.json'))
-print('$args', 'value %.3e ms/step %.4f steps %d warmup %d launches %d e2e %s launch %s'%(d['value'],d['ms_per_step'],d['steps'],d['warmup'],d['gpu_launches'],d['e2e']['value'], d['config']['launch']))"
-done
+d=json.load(open('gpurun_out/b77.json'))
+print('m64 value %.3e ms/step %.4f frac %.3f | flushed ms %.4f'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median']))"
+tail -2 gpurun_out/b77.err
