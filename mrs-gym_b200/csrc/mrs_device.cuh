@@ -34,12 +34,21 @@ struct Ctrl {
     float ltv[3];  // last_target_vel
 };
 
+#ifndef MRS_MINB_VEL
+#define MRS_MINB_VEL 5
+#endif
+#ifndef MRS_MINB_POS
+#define MRS_MINB_POS 6
+#endif
+#ifndef MRS_MINB_ACC
+#define MRS_MINB_ACC 6
+#endif
 template <int MODE> struct ModeTraits;
-template <> struct ModeTraits<MRS_SET_TARGET_VEL>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = true;  static constexpr int minb = 5; };
-template <> struct ModeTraits<MRS_SET_TARGET_POS>   { static constexpr int A = 3; static constexpr bool io = true,  ip = true,  vel = false;  static constexpr int minb = 6; };
-template <> struct ModeTraits<MRS_SET_TARGET_ACCEL> { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = 6; };
-template <> struct ModeTraits<MRS_SET_FORCE>        { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = 6; };
-template <> struct ModeTraits<MRS_SET_TARGET_ORI>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = 6; };
+template <> struct ModeTraits<MRS_SET_TARGET_VEL>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = true;  static constexpr int minb = MRS_MINB_VEL; };
+template <> struct ModeTraits<MRS_SET_TARGET_POS>   { static constexpr int A = 3; static constexpr bool io = true,  ip = true,  vel = false;  static constexpr int minb = MRS_MINB_POS; };
+template <> struct ModeTraits<MRS_SET_TARGET_ACCEL> { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = MRS_MINB_ACC; };
+template <> struct ModeTraits<MRS_SET_FORCE>        { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = MRS_MINB_ACC; };
+template <> struct ModeTraits<MRS_SET_TARGET_ORI>   { static constexpr int A = 3; static constexpr bool io = true,  ip = false, vel = false;  static constexpr int minb = MRS_MINB_ACC; };
 template <> struct ModeTraits<MRS_SET_CONTROL>      { static constexpr int A = 4; static constexpr bool io = false, ip = false, vel = false;  static constexpr int minb = 7; };
 #ifndef MRS_MINB_SPEEDS
 #define MRS_MINB_SPEEDS 7

@@ -1,12 +1,10 @@
-# scratch command file for `gpurun -- 'bash tools/_run.sh'` (overwritten freely during development);
-# this version is the round-end check: GPU tests, smoke, the default bench line and the reference arm
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python __graft_entry__.py smoke 2>&1 | tail -2
-python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; tail -2 gpurun_out/final_bench.err
-python -c "
+Q="--warmup 5 --no-cpu --clock-seconds 0 --e2e-steps 0"
+for w in c5v c5p; do
+for v in base v6p7 v7p7; do
+  if [ $v = base ]; then L=""; else L="MRS_B200_LIB=$PWD/build_variants/lib_$v.so"; fi
+  env $L python bench.py --steps 400 --workload $w $Q > gpurun_out/b78_${w}_$v.json 2>>gpurun_out/b78.err; python -c "
 import json
-d=json.load(open('gpurun_out/final_bench.json'))
-print('value %.3e ms/step %.4f frac %.3f traffic %s | flushed %.4f | many %.3e | e2e %.3e | cpu %.3e (%s cores) | launches %d | clocks %s'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['roofline']['traffic'],d['l2_flushed']['ms_per_step_median'],d['step_many']['value'],d['e2e']['value'],d['cpu_baseline']['value'],d['cpu_baseline']['cores'],d['gpu_launches'],d['clocks']))"
-python bench.py --impl reference --steps 20 --warmup 1 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('reference arm value %.3e cores %s'%(d['value'], d['cpu_baseline']['cores']))"
+d=json.load(open('gpurun_out/b78_${w}_$v.json'))
+print('$w $v value %.3e ms/step %.4f frac %.3f | flushed ms %.4f | many %s'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['l2_flushed']['ms_per_step_median'],d['step_many'] and '%.3e'%d['step_many']['value']))"
+done; done
+tail -2 gpurun_out/b78.err
