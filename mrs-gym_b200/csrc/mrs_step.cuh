@@ -109,10 +109,9 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     auto draw = [&]() -> int {
         int v = -1;
         if (lane == 0) {
-            // .inc with the maximal bound == add 1; ptxas wraps an .add of a constant in its warp-aggregation
-            // sequence (vote, popc, ltmask, shuffle: 14 instructions) although only one lane is active here
-            // (ptxas wraps this in its warp-aggregation sequence -- vote, popc, ltmask, shuffle -- although one
-            // lane is active; .inc, a run-time addend and an addend read from shared memory all end up the same)
+            // (ptxas wraps this atomic in its warp-aggregation sequence -- vote, popc, ltmask, shuffle: 14
+            // instructions -- although one lane is active; .inc with the maximal bound, a run-time addend and an
+            // addend read from shared memory all end up the same)
             asm volatile("atom.shared.add.u32 %0, [%1], 1;"
                          : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(&sh_counter)) : "memory");
             v = (v < sh_hi) ? v : -1;

@@ -86,6 +86,27 @@ def test_baked_constants_match_the_library_defaults():
     assert lib.mrs_config_is_baked(ctypes.byref(c5)) == 1
 
 
+def test_scratch_planes_follow_the_pair_slices():
+    """mrs_scratch_planes(E, N): nothing for the one-warp envs, 7 planes for the lanes-per-agent / thread-per-agent
+    kernels (N <= 128), 7 + 2 per partner slice for the tiled pair pass -- at most 32 slices, at most one per 128
+    partners, fewer as the env count alone fills the GPU."""
+    lib = _lib().lib()
+    assert lib.mrs_scratch_planes(10, 8) == 0 and lib.mrs_scratch_planes(1, 32) == 0
+    for N in (33, 64, 128):
+        assert lib.mrs_scratch_planes(1, N) == 7 and lib.mrs_scratch_planes(5000, N) == 7
+    assert lib.mrs_scratch_planes(1, 4096) == 7 + 2 * 32
+    assert lib.mrs_scratch_planes(1, 129) == 7 + 2 * 2          # two tiles of 128: two slices at most
+    assert lib.mrs_scratch_planes(1, 1024) == 7 + 2 * 8
+    last = None
+    for E in (1, 2, 8, 64, 1000, 100000):
+        p = lib.mrs_scratch_planes(E, 2048)
+        assert 9 <= p <= 7 + 2 * 16 and (p - 7) % 2 == 0
+        assert last is None or p <= last                         # more envs never need more slices
+        last = p
+    assert lib.mrs_scratch_planes(100000, 2048) == 9
+    assert lib.mrs_scratch_planes(0, 64) == 0
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
 def test_no_cpu_fallback():
     import mrsgym_b200 as M
