@@ -167,3 +167,43 @@ def test_stats_allreduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all('ok' in o for o in outs)
+
+
+def test_header_is_plain_c():
+    """include/mrs_b200.h is the drop-in boundary for non-Python callers (cgo / JNI / N-API): it must compile as
+    C99 and as C++ without any CUDA or torch type."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    for cmd in (['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only', '-x', 'c', HEADER],
+                ['g++', '-std=c++11', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c++', HEADER]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(HEADER).read()
+    assert '#include <cuda' not in text and '#include <torch' not in text and 'at::Tensor' not in text
+
+
+def test_reference_arm_prints_the_bench_contract():
+    """bench.py --impl reference runs on the CPU alone (oracle port on all host cores, a bounded sample) and prints
+    ONE JSON line on stdout with the contract's keys; under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '1'],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['metric'] == 'agent-steps/sec' and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2')
+    r1 = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2'],
+                        capture_output=True, text=True, timeout=120, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ''
