@@ -207,3 +207,23 @@ def test_reference_arm_prints_the_bench_contract():
     r1 = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2'],
                         capture_output=True, text=True, timeout=120, env=env)
     assert r1.returncode == 0 and r1.stdout.strip() == ''
+
+
+def test_plain_c_caller_links_and_runs(tmp_path):
+    """examples/c_abi_smoke.c: a C99 program with no CUDA headers links against libmrs_b200.so and uses the
+    configuration / validation entry points (the part of the ABI that needs no device)."""
+    import shutil
+    import subprocess
+    _abi = _lib()
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_abi.LIB_PATH)
+    exe = str(tmp_path / 'c_abi_smoke')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(root, 'include'),
+                        os.path.join(root, 'examples', 'c_abi_smoke.c'), '-o', exe, '-L', libdir, '-lmrs_b200',
+                        '-Wl,-rpath,' + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'baked 1' in r.stdout and 'action dim 4' in r.stdout
