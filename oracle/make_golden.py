@@ -25,9 +25,14 @@ ANCHOR_STATE = dict(pos=[[1.0, 2.0, 3.0]], rpy=[0.1, -0.2, 0.3], vel=[[0.3, -0.1
                     angvel=[[0.5, -0.4, 0.2]])
 
 
+ONLY = None          # --only a,b: write just these files (the random stream of main() is consumed all the same)
+
+
 def rollout(mrsgym, fake, name, N, mode, T, K, comm_range, start, actions, agent_radius=0.3, dt=0.01, gravity=9.81,
             none_steps=()):
     import torch
+    if ONLY is not None and name not in ONLY:
+        return
     env = ref_runner.make_env(mrsgym, fake, N, mode, K=K, comm_range=comm_range,
                               agent_radius=agent_radius, dt=dt, GRAVITY=gravity)
     ref_runner.write_state64(env, fake, **start)
@@ -139,6 +144,17 @@ def main():
                   rng.uniform(-1, 1, (T, N))], axis=-1)
     rollout(mrsgym, fake, 'contact_control', N, 'set_control', T, 1, 2.0, st, a.astype(np.float32))
 
+    # --- larger swarms: N = 16 (two envs per warp in the group kernel, half-round pair schedule) and N = 40
+    # (first size of the wide path), K_HOPS 3 / 1, finite COMM_RANGE
+    st = rand_start(rng, 16, spacing=0.9)
+    a = (rng.normal(0, 0.5, (1, 16, 3)).repeat(40, 0) + rng.normal(0, 0.05, (40, 16, 3))).astype(np.float32)
+    rollout(mrsgym, fake, 'traj_vel_n16', 16, 'set_target_vel', 40, 3, 1.5, st, a)
+    st = rand_start(rng, 40, spacing=1.0)
+    a = (st['pos'] + rng.normal(0, 0.4, (40, 3)))[None].repeat(30, 0).astype(np.float32)
+    rollout(mrsgym, fake, 'traj_pos_n40', 40, 'set_target_pos', 30, 1, 1.8, st, a)
+
 
 if __name__ == '__main__':
+    if len(sys.argv) > 2 and sys.argv[1] == '--only':
+        ONLY = set(sys.argv[2].split(','))
     main()
