@@ -152,6 +152,16 @@ def main():
     st = rand_start(rng, 40, spacing=1.0)
     a = (st['pos'] + rng.normal(0, 0.4, (40, 3)))[None].repeat(30, 0).astype(np.float32)
     rollout(mrsgym, fake, 'traj_pos_n40', 40, 'set_target_pos', 30, 1, 1.8, st, a)
+    # --- the shapes of BASELINE configs[1] / configs[2] as single envs: 32 agents set_target_pos K_HOPS 3
+    # COMM_RANGE 2.0 (one env = one warp of the group kernel), 16 agents set_control in the contact regime
+    st = rand_start(rng, 32, spacing=1.0, z0=3.0)
+    a = (st['pos'] + rng.normal(0, 0.5, (32, 3)))[None].repeat(25, 0).astype(np.float32)
+    rollout(mrsgym, fake, 'traj_pos_n32_c2', 32, 'set_target_pos', 25, 3, 2.0, st, a)
+    st = rand_start(rng, 16, spacing=0.7, z0=0.95, jitter=0.03, tilt=0.05, vel=0.2, angvel=0.2)
+    st['vel'][:, 2] -= 0.8
+    a = np.stack([9.81 + rng.uniform(-1, 1, (40, 16)), rng.uniform(-1, 1, (40, 16)), rng.uniform(-1, 1, (40, 16)),
+                  rng.uniform(-1, 1, (40, 16))], axis=-1).astype(np.float32)
+    rollout(mrsgym, fake, 'contact_control_n16_c3', 16, 'set_control', 40, 0, float('inf'), st, a)
 
 
 if __name__ == '__main__':
