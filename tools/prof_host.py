@@ -1,3 +1,5 @@
+"""cProfile of the Python side of MRS.step for the README example (one env, three agents): where the per-call
+host time goes.  python tools/prof_host.py (on a GPU box)."""
 import cProfile, pstats, os, sys, io
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', 'mrs-gym_b200'))
