@@ -96,27 +96,28 @@ def make_inputs(w, E, T, seed):
 
 # ------------------------------------------------------------------------------ CPU arm (oracle port)
 def _cpu_worker(args):
-    wname, E, T, seed = args
+    wname, E, T, seed, W = args
     os.environ.setdefault('OMP_NUM_THREADS', '1')
     import numpy as np
     import helpers as H
     w = WORKLOADS[wname]
-    st, act = make_inputs(w, E, T + 1, seed)
+    st, act = make_inputs(w, E, T + W, seed)
     env = H.make_spec(E, w['N'], w['mode'], w['K'], w['R'], st)
-    env.step(act[0])                       # warm-up (imports, scipy caches)
+    for t in range(W):                     # untimed warm-up steps (imports, scipy caches)
+        env.step(act[t])
     t0 = time.perf_counter()
     for t in range(T):
-        env.step(act[1 + t])
+        env.step(act[W + t])
     return time.perf_counter() - t0
 
 
-def cpu_port_throughput(wname, procs, E_per_proc, T, seed=4321):
+def cpu_port_throughput(wname, procs, E_per_proc, T, seed=4321, warmup=1):
     """agent-steps/s of the oracle port on `procs` host processes (slowest worker's wall time)."""
     w = WORKLOADS[wname]
     ctx = mp.get_context('spawn')
     t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        walls = pool.map(_cpu_worker, [(wname, E_per_proc, T, seed + i) for i in range(procs)])
+        walls = pool.map(_cpu_worker, [(wname, E_per_proc, T, seed + i, max(1, warmup)) for i in range(procs)])
     total = procs * E_per_proc * w['N'] * T
     return total / max(walls), max(walls), time.perf_counter() - t0
 
@@ -219,8 +220,19 @@ def run_gpu(args):
                  want_A=w.get('A', True) and not os.environ.get('MRS_EXP_NO_A'))
     H.upload_state(sw, st)
     actions = torch.from_numpy(act_np).to(dev)
+    # the one exchange of the path: the per-rollout statistics reduction, as the library's peer-memory kernel
+    # (mrs_stats_allreduce) at the end of every graph replay; torch.distributed / NCCL stays the plumbing
+    comm, comm_note = None, 'single GPU: no exchange'
+    if world > 1:
+        try:
+            comm = D.PeerComm()
+            comm_note = ('mrs_stats_allreduce: peer-memory kernel (NVLink P2P stores into the peers\' mailboxes, 64 B per '
+                         'rank, one 32-thread launch per GPU) as the last node of every rollout graph; NCCL only for '
+                         'rendezvous, handle exchange and the max over ranks of the timings')
+        except Exception as exc:                       # no peer access on this box: NCCL does the reduction
+            comm, comm_note = None, 'NCCL all-reduce after the rollout (PeerComm unavailable: %s)' % exc
     if use_graph:
-        roll = sw.capture_rollout(actions, T)
+        roll = sw.capture_rollout(actions, T, stats_comm=comm)
     else:                                   # fewer steps than the observation window: plain launches
         class _Plain:
             launches_per_replay = T
@@ -240,15 +252,31 @@ def run_gpu(args):
         roll.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(physical_gpu_index(local))
+    tiny = torch.zeros(1, device=dev)
+    in_graph = use_graph and comm is not None
+
+    def reduce_stats():
+        return sw.allreduce_stats(comm) if (comm is not None or world == 1) else sw.allreduce_stats()
+
     barrier()
     with sampler:
+        if world > 1:
+            # The region starts ON THE DEVICE: the stream first spins ~0.5 ms (the host enqueues the whole region
+            # behind it), then passes a device-side barrier across the ranks, then records e0 -- so every rank's
+            # clock starts when the last rank arrives, not when its host thread happened to wake up from the
+            # host barrier.  The statistics reduction at the end of the rollout aligns the ends the same way.
+            torch.cuda._sleep(int(0.5e-3 * 1.9e9))
+            if comm is not None:
+                comm.barrier()
+            else:
+                torch.distributed.all_reduce(tiny)
         e0.record()
         for _ in range(replays):
             roll.replay()
         for t in range(rem):                      # only when `steps` is not a multiple of the graph length
             sw.step(actions[t])
-        if world > 1:
-            stats = sw.allreduce_stats()          # the per-rollout statistics reduction (NCCL)
+        if world > 1 and (rem or not in_graph):
+            reduce_stats()                        # (inside the graph otherwise)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -258,6 +286,13 @@ def run_gpu(args):
             for _ in range(max(1, 2000 // T)):
                 roll.replay()
             torch.cuda.synchronize(dev)
+    stats_check = None
+    if world > 1:
+        # the peer-memory reduction against NCCL on the same counters (outside the timed region)
+        mine = reduce_stats().clone()
+        ref = sw.stats.clone()
+        torch.distributed.all_reduce(ref)
+        stats_check = 'ok' if bool((mine == ref).all()) else 'MISMATCH %s vs %s' % (mine.tolist(), ref.tolist())
     gpu_launches = replays * roll.launches_per_replay + rem * sw._step_launches()
     ms = D.max_over_ranks(ms, dev)
     agent_steps = float(E) * N * steps * world
@@ -354,15 +389,18 @@ def run_gpu(args):
         'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': steps,
         'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {**workload_config(w, E, world),
-                   'launch': (('CUDA graph of %d single-step launches, %d replays' if use_graph else '%d plain launches x %d') % (T, replays))
-                             + (' + %d plain launches' % rem if rem else ''),
-                   'l2': 'inputs larger than L2: the timed region consumes %.0f MB of distinct action buffers and writes '
-                         '%.0f MB of distinct X/A tape slots (L2 = 126 MB); no buffer is re-read across iterations -- the '
-                         'state is loop-carried (written by step t, read by step t+1, as in any rollout).  l2_flushed '
-                         'reports the same step one launch at a time behind a 512 MB read-flush'
-                         % (T * E * N * max(M._abi.ACTION_DIMS[sw.cfg.action_type], 1) * 4 / 1e6,
-                            steps * E * N * (6 + (N if sw.A_tape is not None else 0)) * 4 / 1e6)},
+        'config': workload_config(w, E, world),
+        'notes': {'launch': (('CUDA graph of %d single-step launches, %d replays' if use_graph else '%d plain launches x %d') % (T, replays))
+                            + (' + %d plain launches' % rem if rem else ''),
+                  'l2': 'inputs larger than L2: the timed region consumes %.0f MB of distinct action buffers and writes '
+                        '%.0f MB of distinct X/A tape slots (L2 = 126 MB); no buffer is re-read across iterations -- the '
+                        'state is loop-carried (written by step t, read by step t+1, as in any rollout).  l2_flushed '
+                        'reports the same step one launch at a time behind a 512 MB read-flush'
+                        % (T * E * N * max(M._abi.ACTION_DIMS[sw.cfg.action_type], 1) * 4 / 1e6,
+                           steps * E * N * (6 + (N if sw.A_tape is not None else 0)) * 4 / 1e6),
+                  'timed_region': ('device-aligned: spin + device barrier across ranks, e0, %d steps, statistics reduction, e1; '
+                                   'max over ranks' % steps) if world > 1 else 'e0, %d steps, e1 (CUDA events on the launch stream)' % steps,
+                  'collective': comm_note, 'stats_allreduce_check': stats_check},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': kernel, 'peak_source': peak_src,
                      'algorithmic_bytes_per_agent_step': w['B'], 'agent_steps_per_launch': E * N,
@@ -398,17 +436,17 @@ def run_reference(args):
     w = WORKLOADS[args.workload]
     procs = min(os.cpu_count() or 1, 64)
     Ep, _ = cpu_sample_sizes(args.workload)
-    steps, warmup = args.steps, args.warmup
+    steps, warmup = args.steps, max(args.warmup, 3)      # the same floor as the GPU arm
     # bounded: each "step" here is one env.step of the sample batch (procs x Ep envs)
     Tc = max(1, min(steps, 200))
-    v, wall, total = cpu_port_throughput(args.workload, procs, Ep, Tc)
+    v, wall, total = cpu_port_throughput(args.workload, procs, Ep, Tc, warmup=min(warmup, 20))
     out = {
         'impl': 'reference', 'metric': 'agent-steps/sec', 'value': v, 'unit': 'agent-steps/s',
-        'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': Tc, 'warmup': 1,
+        'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': Tc, 'warmup': warmup,
         'ms_per_step': wall / Tc * 1e3, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {**workload_config(w, args.envs or w['E'], int(os.environ.get('WORLD_SIZE', '1'))),
-                   'cpu_sample': 'bounded sample of the workload: %d processes x %d envs per step' % (procs, Ep)},
+        'config': workload_config(w, args.envs or w['E'], int(os.environ.get('WORLD_SIZE', '1'))),
+        'notes': {'cpu_sample': 'bounded sample of the workload: %d processes x %d envs per step' % (procs, Ep)},
         'cpu_baseline': {'value': v, 'unit': 'agent-steps/s', 'cores': procs, 'kind': 'port',
                          'sample': '%d processes x %d envs x %d agents x %d steps (oracle/spec.py numpy port of the '
                                    'reference step + restated Bullet; PyBullet itself is not installable here)'

@@ -46,6 +46,8 @@ extern "C" {
 #define MRS_STATS_SLOTS 8
 #define MRS_SCRATCH_PLANES 7          /* N <= 128 */
 #define MRS_SCRATCH_PAIR_SPLITS 32    /* N > 128: + 2 planes (partial pair sum, flag) per partner slice, <= 32 slices */
+#define MRS_COMM_MAX_WORLD 16         /* GPUs of one node a peer communicator spans */
+#define MRS_COMM_HANDLE_BYTES 64      /* size of the opaque mailbox handle exchanged between ranks */
 
 /* ACTION_TYPE strings of the reference are method names dispatched by getattr
  * (mrsgym/Environment.py:92 -> mrsgym/Quadcopter.py:26-65). */
@@ -77,6 +79,7 @@ typedef enum {
 /* status word bits (device, sticky; the host reads them lazily) */
 #define MRS_STATUS_NAN_ACTION 1u   /* mirrors the NaN guard of mrsgym/MRS.py:247-248 */
 #define MRS_STATUS_NONFINITE 2u    /* a state component left the finite range        */
+#define MRS_STATUS_COMM_TIMEOUT 4u /* mrs_stats_allreduce / mrs_comm_barrier gave up waiting for a peer */
 
 /* stats slots (unsigned long long, device; summed across GPUs per rollout) */
 #define MRS_STAT_AGENT_CONTACTS 0  /* sphere-sphere contact rows that pushed         */
@@ -256,6 +259,37 @@ int mrs_raycast(const MrsConfig* cfg, const MrsBuffers* bufs, const float* direc
 int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host,
                      float* dev_actions, float* X_host, float* A_host, int T, int slot_x_first,
                      int slot_a_first, void* stream);
+
+/* ---- the one exchange step of the path: per-rollout statistics reduction across env shards (SURVEY.md §8b/§8e;
+ * the reference runs one environment per process and has no counterpart, examples/simulating_data/helper/
+ * DataGenerator.py:8-48 gathers its episodes on the host).
+ *
+ * Environments shard across the GPUs of one node with no traffic on the step; only the MRS_STATS_SLOTS counters
+ * are summed across ranks, once per rollout.  64 bytes are a latency problem, so instead of an ncclComm_t the
+ * library carries its own peer-memory communicator: every rank owns a small device mailbox (the one device
+ * allocation this library makes), all mailboxes are mapped into every process, and the reduction is ONE
+ * 32-thread kernel per GPU that pushes its counters into the peers' mailboxes with NVLink stores, waits on
+ * local flags and sums in rank order -- stream-ordered, no host involvement, capturable in a CUDA graph.
+ *
+ *   one process per GPU:  mrs_comm_create -> mrs_comm_handle -> exchange the world x 64 handle bytes by any
+ *                         means (torch.distributed, MPI, a file) -> mrs_comm_connect.
+ *   one process, N GPUs:  mrs_comm_create per device -> mrs_comm_mailbox -> mrs_comm_connect_ptrs.
+ * All calls of one communicator are collective: every rank issues the same sequence of mrs_stats_allreduce /
+ * mrs_comm_barrier calls.  A rank that waits more than 4 s for a peer gives up, raises MRS_STATUS_COMM_TIMEOUT in
+ * its status word and reports its local counters. */
+typedef struct MrsPeerComm MrsPeerComm;
+int mrs_comm_create(int rank, int world, MrsPeerComm** out);          /* on the CURRENT device; world <= MRS_COMM_MAX_WORLD */
+int mrs_comm_handle(const MrsPeerComm* comm, unsigned char* out_handle /* [MRS_COMM_HANDLE_BYTES] */);
+int mrs_comm_connect(MrsPeerComm* comm, const unsigned char* handles /* [world][MRS_COMM_HANDLE_BYTES], rank order */);
+void* mrs_comm_mailbox(const MrsPeerComm* comm);
+int mrs_comm_connect_ptrs(MrsPeerComm* comm, void* const* mailboxes /* [world] */, const int* devices /* [world] or NULL */);
+int mrs_comm_destroy(MrsPeerComm* comm);
+/* Device-side barrier across the ranks on `stream` (bench: aligns the start of a timed region on the device). */
+int mrs_comm_barrier(MrsPeerComm* comm, unsigned int* status /* device, may be NULL */, void* stream);
+/* out[i] (device u64[MRS_STATS_SLOTS], caller-owned) = sum over ranks of bufs->stats[i]; bufs->stats is left as
+ * it is.  cfg is unused today (kept for the survey's signature). */
+int mrs_stats_allreduce(const MrsConfig* cfg, const MrsBuffers* bufs, MrsPeerComm* comm, unsigned long long* out,
+                        void* stream);
 
 #ifdef __cplusplus
 }

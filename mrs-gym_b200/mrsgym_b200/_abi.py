@@ -29,6 +29,9 @@ STATE_DIMS = {X_NONE: 0, X_POS_VEL: 6, X_FULL: 13}
 
 STATUS_NAN_ACTION = 1
 STATUS_NONFINITE = 2
+STATUS_COMM_TIMEOUT = 4
+COMM_MAX_WORLD = 16
+COMM_HANDLE_BYTES = 64
 STAT_NAMES = ('agent_contact_rows', 'ground_contacts', 'nonfinite', 'nan_actions')
 
 f = C.c_float
@@ -107,6 +110,14 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_void_p]),
     'mrs_raycast': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_int, C.POINTER(C.c_float),
                               C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mrs_comm_create': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    'mrs_comm_handle': (C.c_int, [C.c_void_p, C.c_char_p]),
+    'mrs_comm_connect': (C.c_int, [C.c_void_p, C.c_char_p]),
+    'mrs_comm_mailbox': (C.c_void_p, [C.c_void_p]),
+    'mrs_comm_connect_ptrs': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    'mrs_comm_destroy': (C.c_int, [C.c_void_p]),
+    'mrs_comm_barrier': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mrs_stats_allreduce': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

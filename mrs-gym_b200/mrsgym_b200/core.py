@@ -95,6 +95,7 @@ class Swarm:
         self.ha = self.L - self.K - 1
         self.ring = bool(ring)     # True: heads wrap around the tape, nothing is ever moved (graph rollouts)
         self.a_empty = True        # no A slice pushed since the last full reset (MRS.py:186)
+        self._stats_sum = None     # result buffer of allreduce_stats(comm)
         self.launches = 0          # kernel launches issued through the ABI (bench: gpu_launches)
         self._launches_per_step = self._step_launches()
 
@@ -267,13 +268,14 @@ class Swarm:
         for t in range(T):
             self.step(actions[t] if actions is not None else None)
 
-    def capture_rollout(self, actions, T: int):
+    def capture_rollout(self, actions, T: int, stats_comm=None):
         """CUDA-graph a T-step rollout (launch-bound loops belong in graphs): returns a
         GraphRollout whose replay() advances all envs by T steps reading actions[t] from the
         given device buffer (refill it between replays).  Capturing itself leaves the swarm where it was.  The swarm switches to ring mode (tape heads
         wrap around, no slots are moved); T must be a multiple of the tape size, so every replay
-        ends on the slots it started from (pass tape_slots=T to the constructor)."""
-        return GraphRollout(self, actions, T)
+        ends on the slots it started from (pass tape_slots=T to the constructor).  stats_comm (dist.PeerComm):
+        the per-rollout statistics reduction becomes the last node of the graph (result: swarm._stats_sum)."""
+        return GraphRollout(self, actions, T, stats_comm)
 
     def push_A(self):
         """MRS.calc_Ak outside step: adjacency of the current positions becomes the newest slot."""
@@ -432,16 +434,26 @@ class Swarm:
         v = self.stats.tolist()
         return {n: v[i] for i, n in enumerate(_abi.STAT_NAMES)}
 
-    def allreduce_stats(self, group=None):
-        """Per-rollout statistics reduction across env shards: the ONLY collective of the path
-        (NCCL over NVLink when the process group is nccl)."""
+    def allreduce_stats(self, comm=None, group=None):
+        """Per-rollout statistics reduction across env shards: the ONLY exchange of the path.
+        comm = dist.PeerComm: the library's peer-memory kernel (mrs_stats_allreduce) on the current stream, no
+        host involvement, capturable in a CUDA graph; the result tensor is reused between calls.
+        comm = None: torch.distributed all-reduce (gloo in the CPU tests, NCCL otherwise)."""
+        if comm is not None:
+            if self._stats_sum is None:
+                self._stats_sum = torch.zeros_like(self.stats)
+            _abi.check(self.lib.mrs_stats_allreduce(self._cfg_ref, self._bufs_ref, comm.handle, _ptr(self._stats_sum),
+                                                    self._stream()), 'mrs_stats_allreduce')
+            self.launches += 1
+            return self._stats_sum
         from .dist import allreduce_stats
         return allreduce_stats(self.stats, group)
 
 
 class GraphRollout:
-    def __init__(self, swarm: Swarm, actions, T: int):
+    def __init__(self, swarm: Swarm, actions, T: int, stats_comm=None):
         sw = self.swarm = swarm
+        self.stats_comm = stats_comm
         if T < 1 or T % sw.L != 0:
             raise ValueError('capture_rollout: T=%d must be a multiple of the tape size (%d slots); build the '
                              'swarm with tape_slots=T' % (T, sw.L))
@@ -483,6 +495,8 @@ class GraphRollout:
             sw.step_many(self.actions, self.T)       # wide path: per-step kernels anyway, adjacency overlapped
         else:
             sw.step_many_single(self.actions, self.T)
+        if self.stats_comm is not None:
+            sw.allreduce_stats(self.stats_comm)
 
     def replay(self):
         self.graph.replay()

@@ -29,7 +29,7 @@ def _lib():
 def test_header_symbols_are_exported():
     _abi = _lib()
     text = open(HEADER).read()
-    names = set(re.findall(r'^\s*(?:int|size_t|const char\*)\s+(mrs_\w+)\s*\(', text, flags=re.M))
+    names = set(re.findall(r'^\s*(?:int|size_t|const char\*|void\*)\s+(mrs_\w+)\s*\(', text, flags=re.M))
     assert len(names) >= 13
     handle = ctypes.CDLL(_abi.LIB_PATH)
     for n in names:
