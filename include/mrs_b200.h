@@ -40,12 +40,13 @@
 extern "C" {
 #endif
 
-#define MRS_ABI_VERSION 1
+#define MRS_ABI_VERSION 2
 #define MRS_STATE_PLANES 13
 #define MRS_CTRL_PLANES 18
 #define MRS_STATS_SLOTS 8
 #define MRS_SCRATCH_PLANES 7          /* N <= 128 */
 #define MRS_SCRATCH_PAIR_SPLITS 32    /* N > 128: + 2 planes (partial pair sum, flag) per partner slice, <= 32 slices */
+#define MRS_SYNC_WORDS 2056           /* u64 words of MrsBuffers.sync (launch-to-launch range hand-over of mrs_rollout) */
 #define MRS_COMM_MAX_WORLD 16         /* GPUs of one node a peer communicator spans */
 #define MRS_COMM_HANDLE_BYTES 64      /* size of the opaque mailbox handle exchanged between ranks */
 
@@ -79,6 +80,7 @@ typedef enum {
 /* status word bits (device, sticky; the host reads them lazily) */
 #define MRS_STATUS_NAN_ACTION 1u   /* mirrors the NaN guard of mrsgym/MRS.py:247-248 */
 #define MRS_STATUS_NONFINITE 2u    /* a state component left the finite range        */
+#define MRS_STATUS_SYNC_TIMEOUT 8u /* a chained launch of mrs_rollout waited > 2 s for its predecessor's range    */
 #define MRS_STATUS_COMM_TIMEOUT 4u /* mrs_stats_allreduce / mrs_comm_barrier gave up waiting for a peer */
 
 /* stats slots (unsigned long long, device; summed across GPUs per rollout) */
@@ -142,6 +144,8 @@ typedef struct {
     float* scratch;                      /* [mrs_scratch_planes(E, N)][S], needed iff N > 32 */
     unsigned int* status;                /* [1] */
     unsigned long long* stats;           /* [MRS_STATS_SLOTS] */
+    unsigned long long* sync;            /* [MRS_SYNC_WORDS], zero-initialised once by the caller, owned by the library
+                                            afterwards; NULL = mrs_rollout falls back to grid-wide dependencies */
 } MrsBuffers;
 
 int mrs_abi_version(void);
@@ -191,6 +195,16 @@ int mrs_step(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions,
  * examples/simulating_data/helper/DataGenerator.py:8-48 with pre-computed actions. */
 int mrs_step_many(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T,
                   int slot_x_first, int slot_a_first, void* stream);
+
+/* T consecutive steps as T single-step launches (every step reads and writes the whole state in HBM / L2, one
+ * launch per env.step as in a closed loop) with pre-computed actions float[T][E][N][ACTION_DIM]; tape slots as in
+ * mrs_step_many.  For N in {8, 16, 32} and jobs that fill the GPU the launches are CHAINED: environments are
+ * independent, so the chunk range a CTA of step t has finished is handed to a CTA of step t+1 through
+ * bufs->sync (a queue in completion order) instead of waiting for the whole grid of step t -- an SM never waits
+ * for the slowest SM of the previous step.  Everything else behaves like T calls of mrs_step.  Capturable in a
+ * CUDA graph.  The rollout loop of examples/simulating_data/helper/DataGenerator.py:8-48. */
+int mrs_rollout(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T, int slot_x_first,
+                int slot_a_first, void* stream);
 
 /* Observation only: X (state layout) and/or A (adjacency) of the CURRENT state into tape
  * slot `slot`.  Replaces MRS.calc_Xk / MRS.calc_Ak+calc_A (MRS.py:87-124) outside step. */

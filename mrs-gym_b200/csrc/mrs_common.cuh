@@ -27,6 +27,8 @@ struct StepArgs {
     float* A0;
     long long xstride, astride;
     int G;                 // group width (power of two >= N), group path only
+    int role;              // range hand-over between chained single-step launches: 0 none, 1 head, 2 link (mrs_step.cuh)
+    int seq;               // position of the launch in its chain (0 = head)
     int chunk_lo, nchunks; // this launch walks the warp-sized work items [chunk_lo, nchunks), group path only
 };
 
@@ -158,6 +160,21 @@ __device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// acquire / release accesses and the nanosecond clock of the launch-to-launch range hand-over
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ------------------------------------------------------------------------------ host side
 inline int sm_count() {

@@ -392,7 +392,7 @@ extern template int dispatch_step<MRS_NO_ACTION>(const MrsConfig&, const MrsBuff
 #endif
 
 static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T, int slot_x, int slot_a,
-                     void* stream) {
+                     void* stream, int role = 0, int seq = 0) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (!bufs || !bufs->state || !bufs->ctrl) return MRS_ERR_ARG;
@@ -406,6 +406,8 @@ static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
     a.slot_x = slot_x;
     a.slot_a = slot_a;
     a.G = 0;
+    a.role = role;
+    a.seq = seq;
     a.chunk_lo = 0;
     a.nchunks = 0;
     a.X0 = a.A0 = nullptr;
@@ -579,6 +581,23 @@ int mrs_step(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions,
 int mrs_step_many(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T, int slot_x_first,
                   int slot_a_first, void* stream) {
     return step_impl(cfg, bufs, actions, T, slot_x_first, slot_a_first, stream);
+}
+
+int mrs_rollout(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions, int T, int slot_x_first,
+                int slot_a_first, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (T <= 0) return MRS_ERR_ARG;
+    if (cfg->N > 32) return step_impl(cfg, bufs, actions, T, slot_x_first, slot_a_first, stream);   // per-step kernels anyway
+    const size_t per_step = (size_t)cfg->E * cfg->N * (size_t)mrs_action_dim(cfg->action_type);
+    constexpr int kMaxChain = 32768;         // the position travels in 16 bits of a queue entry
+    for (int t = 0; t < T; ++t) {
+        const int pos = t % kMaxChain;
+        rc = step_impl(cfg, bufs, actions ? actions + (size_t)t * per_step : nullptr, 1, slot_x_first - t, slot_a_first - t,
+                       stream, (bufs && bufs->sync) ? (pos == 0 ? 1 : 2) : 0, pos);
+        if (rc) return rc;
+    }
+    return MRS_OK;
 }
 
 int mrs_observe(const MrsConfig* cfg, const MrsBuffers* bufs, int slot, int write_X, int write_A, void* stream) {

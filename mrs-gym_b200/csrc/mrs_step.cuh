@@ -59,8 +59,34 @@ template <int MODE, int GT> __host__ __device__ constexpr int group_warp_smem_by
     return 1024 + ((MRS_PREFETCH && GT != 0) ? mode_stage_floats<MODE>() * 4 : 0);
 }
 
-template <int MODE, int GT, int WPB, bool BAKED>
-__global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : 1)
+//
+// MANY: T > 1 steps per launch (mrs_step_many: the state stays in registers across steps); the single-step
+// kernels carry no step loop, no action double-buffering and no tape strides.
+//
+// Hand-over between consecutive single-step launches (kHand: SM-filling CTAs over full chunks, a.role != 0; host
+// side: mrs_rollout).  Envs are independent, so chunk range r of step t+1 depends on range r of step t ONLY.
+// With a grid-wide dependency every step pays the slowest SM of the previous one plus the grid boundary
+// (tools/trace_c5.py: first CTA done after 14.4 us, last after 16.6 us, next grid released 0.8 us later).
+// Instead a CTA that finishes range r publishes r in a queue (bufs.sync) and CTA i of the NEXT launch -- the block
+// scheduler starts CTAs in index order on whichever SM has just become free -- takes the i-th finished range:
+// ranges flow from launch to launch in completion order and an SM never waits for another SM.
+//   sync[0]               epoch: bumped by the head of every chain
+//   sync[1 + p]           ranges published so far by launches of parity p of the current chain
+//   sync[8 + 1024 p + i]  i-th range published by the newest launch of parity p: epoch << 32 | (position + 1) << 16 | range
+// role 1 (head, position 0): waits for the whole previous grid (griddepcontrol.wait), resets the counters, bumps
+//   the epoch, takes range = blockIdx, publishes.
+// role 2 (link, position t): does NOT wait for the previous grid; CTA i waits for entry i of launch t - 1.
+// All state / PID / action reads of these kernels are cp.async.cg (L2); the publishing thread fences after the
+// CTA barrier that follows the state stores.  A link that waits longer than 2 s falls back to the grid-wide wait
+// and raises MRS_STATUS_SYNC_TIMEOUT.
+constexpr int kSyncQueue = 8, kSyncQueueLen = 1024;
+#ifndef MRS_DEFAULT_CPS
+#define MRS_DEFAULT_CPS 4          // CTAs per SM of the single-step SM-filling shape (each with 1 / CPS of the SM's warps)
+#endif
+static_assert(kSyncQueue + 2 * kSyncQueueLen <= MRS_SYNC_WORDS, "sync buffer layout");
+
+template <int MODE, int GT, int WPB, bool BAKED, bool MANY>
+__global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : (4 * ModeTraits<MODE>::minb) / WPB)
 step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant__ Derived d_in, const MrsBuffers b,
                   const StepArgs a) {
     MrsConfig c_bk;
@@ -74,7 +100,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     // shared memory, one contiguous region per warp so that every address is one per-warp base plus an
     // immediate: [32 positions | 32 velocities] (the pair tile, 1 KB) [prefetch stage]
     constexpr int kWarpBytes = group_warp_smem_bytes<MODE, GT>();
-    __shared__ int sh_counter, sh_hi;
+    __shared__ int sh_counter, sh_hi, sh_range;
     __shared__ unsigned sh_events[5];       // CTA-level status word + the four statistics counters
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + wib * kWarpBytes;
@@ -97,27 +123,65 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     // a shared-memory counter; a warp always knows its next chunk (the stage prefetch needs it) and
     // draws the one after next at the top of an iteration, so the atomic's latency is never waited for.
     constexpr bool kLocal = WPB > 4;
+    constexpr bool kHand = kLocal && MRS_PREFETCH && GT != 0 && !MANY;
+    const int T = MANY ? a.T : 1;
     const int gw = blockIdx.x * WPB + wib;
     if (threadIdx.x < 5) sh_events[threadIdx.x] = 0u;
+    const int role = kHand ? a.role : 0;
+    unsigned epoch = 0;             // thread 0 only
+    if (role == 2) {
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (threadIdx.x == 0) {
+            const unsigned long long* q = b.sync + kSyncQueue + ((a.seq - 1) & 1) * kSyncQueueLen + blockIdx.x;
+            unsigned long long e = ld_acquire_gpu_u64(q), t0 = 0;
+            epoch = (unsigned)ld_acquire_gpu_u64(b.sync);
+            while ((e >> 16) != (((unsigned long long)epoch << 16) | (unsigned)a.seq)) {
+                if (t0 == 0) t0 = global_ns();
+                else if (global_ns() - t0 > 2000000000ull) {       // 2 s: the chain is broken -- fall back, flag it
+                    if (b.status) atomicOr(b.status, MRS_STATUS_SYNC_TIMEOUT);
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+                    e = blockIdx.x;
+                    break;
+                }
+                e = ld_acquire_gpu_u64(q);
+                epoch = (unsigned)ld_acquire_gpu_u64(b.sync);
+            }
+            sh_range = (int)(e & 0xffffull);
+        }
+    } else {
+        if (role == 0) asm volatile("griddepcontrol.launch_dependents;");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (threadIdx.x == 0) sh_range = blockIdx.x;
+        if (role == 1) {
+            // everything before this launch is complete: start a new chain, then let the first link in
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                atomicExch(b.sync + 1, 0ull);
+                atomicExch(b.sync + 2, 0ull);
+                atomicAdd(b.sync, 1ull);
+                __threadfence();
+            }
+            __syncthreads();
+            asm volatile("griddepcontrol.launch_dependents;");
+        }
+    }
     if (threadIdx.x == 0) {
         const int nwork = a.nchunks - a.chunk_lo;
-        sh_counter = a.chunk_lo + (int)(((long long)blockIdx.x * nwork) / gridDim.x);
-        sh_hi = a.chunk_lo + (int)(((long long)(blockIdx.x + 1) * nwork) / gridDim.x);
+        const int r = sh_range;
+        sh_counter = a.chunk_lo + (int)(((long long)r * nwork) / gridDim.x);
+        sh_hi = a.chunk_lo + (int)(((long long)(r + 1) * nwork) / gridDim.x);
     }
     __syncthreads();
-    // lane 0 draws a chunk index (-1 when the share is used up); the others get it by shuffle later
+    // one elected lane draws a chunk index (-1 when the share is used up); the others get it by shuffle later.
+    // elect.sync keeps ptxas from wrapping the single-lane atomic in its warp-aggregation sequence (vote, popc,
+    // ltmask, shuffle + a divergent block: 17 instructions; this form is 6).
     auto draw = [&]() -> int {
-        int v = -1;
-        if (lane == 0) {
-            // (ptxas wraps this atomic in its warp-aggregation sequence -- vote, popc, ltmask, shuffle: 14
-            // instructions -- although one lane is active; .inc with the maximal bound, a run-time addend and an
-            // addend read from shared memory all end up the same)
-            asm volatile("atom.shared.add.u32 %0, [%1], 1;"
-                         : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(&sh_counter)) : "memory");
-            v = (v < sh_hi) ? v : -1;
-        }
-        return v;
+        int v = 0;
+        asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n @p atom.shared.add.u32 %0, [%1], 1;\n}"
+                     : "+r"(v) : "r"((unsigned)__cvta_generic_to_shared(&sh_counter)) : "memory");
+        return v;           // valid in lane 0 (the elected lane of a full warp)
     };
+    const int chunk_hi = sh_hi;
+    auto claim = [&](int v) -> int { return (v < chunk_hi) ? v : -1; };
     // chunk = 32 consecutive agent slots (kFull).  The stage is filled in 16-byte pieces, piece q at float
     // offset 4 q, lane l moves pieces l, l + 32, ...:  [0, 96) state planes 0-11 (plane q >> 3, sub-piece
     // q & 7: a lane's plane advances by 4 per round, so its element index is lane part + round part +
@@ -175,15 +239,13 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     };
     stamp();
 #endif
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef MRS_TRACE
     stamp();
 #endif
     int chunk, chunk_next;
     if (kLocal) {
-        chunk = __shfl_sync(kFull32, draw(), 0);
-        chunk_next = __shfl_sync(kFull32, chunk >= 0 ? draw() : -1, 0);
+        chunk = claim(__shfl_sync(kFull32, draw(), 0));
+        chunk_next = chunk >= 0 ? claim(__shfl_sync(kFull32, draw(), 0)) : -1;
     } else {
         chunk = a.chunk_lo + gw;
         chunk_next = chunk + wtotal;
@@ -248,7 +310,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             if (valid) (void)load_action<MODE>(a.actions, (size_t)s, tmp);
             act0 = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
         }
-        for (int t = 0; t < a.T; ++t, Xs -= a.xstride, As -= a.astride) {
+        for (int t = 0; t < T; ++t, Xs -= a.xstride, As -= a.astride) {
             // per-step event word: the registers behind it live only as long as the step needs them
             unsigned status = 0;
             unsigned n_agent_rows = 0, n_ground = 0;
@@ -256,7 +318,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             float act[4] = {act0.x, act0.y, act0.z, act0.w};
             if (kA > 0 && valid && (isnan(act0.x) || isnan(act0.y) || isnan(act0.z) || (kA == 4 && isnan(act0.w))))
                 status |= MRS_STATUS_NAN_ACTION;
-            if (t + 1 < a.T && valid) {
+            if (MANY && t + 1 < T && valid) {
                 float tmp[4];
                 (void)load_action<MODE>(a.actions, (size_t)(t + 1) * S + s, tmp);
                 act0 = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
@@ -474,7 +536,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
 #endif
         chunk = chunk_next;
         if (kLocal) {
-            chunk_next = __shfl_sync(kFull32, ticket, 0);
+            chunk_next = (chunk >= 0) ? claim(__shfl_sync(kFull32, ticket, 0)) : -1;
         } else {
             chunk_next = (chunk >= 0 && chunk + wtotal < a.nchunks) ? chunk + wtotal : -1;
         }
@@ -487,6 +549,14 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             if (sh_events[2]) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)sh_events[2]);
             if (sh_events[3]) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)sh_events[3]);
             if (sh_events[4]) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, (unsigned long long)sh_events[4]);
+        }
+        if (role != 0) {
+            // publish the finished range (the CTA barrier above ordered every thread's state stores before this fence)
+            __threadfence();
+            if (role == 1) epoch = (unsigned)ld_acquire_gpu_u64(b.sync);
+            const unsigned long long j = atomicAdd(b.sync + 1 + (a.seq & 1), 1ull) - (unsigned long long)gridDim.x * (unsigned)(a.seq >> 1);
+            st_release_gpu_u64(b.sync + kSyncQueue + (a.seq & 1) * kSyncQueueLen + (int)(j & (kSyncQueueLen - 1)),
+                               ((unsigned long long)epoch << 32) | ((unsigned long long)(a.seq + 1) << 16) | (unsigned)sh_range);
         }
     }
 #ifdef MRS_TRACE
@@ -851,7 +921,7 @@ step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ De
 }
 
 // ------------------------------------------------------------------------------ launch
-template <int MODE, int GT, int WPB, bool BAKED>
+template <int MODE, int GT, int WPB, bool BAKED, bool MANY>
 static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
                             bool pdl, cudaStream_t st) {
     constexpr size_t smem = (size_t)WPB * group_warp_smem_bytes<MODE, GT>();
@@ -860,7 +930,7 @@ static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffe
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MRS_ERR_CUDA;
     if (!configured[dev]) {
         if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB, BAKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB, BAKED, MANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
                 cudaSuccess)
             return MRS_ERR_CUDA;
         configured[dev] = true;
@@ -875,35 +945,62 @@ static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffe
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&lc, step_group_kernel<MODE, GT, WPB, BAKED>, c, d, b, a) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&lc, step_group_kernel<MODE, GT, WPB, BAKED, MANY>, c, d, b, a) != cudaSuccess) {
         (void)cudaGetLastError();
         return MRS_ERR_CUDA;
     }
     return last_error();
 }
 
+template <int MODE, int GT, int WPB>
+static int launch_group_variant(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
+                                bool pdl, bool baked, cudaStream_t st) {
+    if (a.T > 1)
+        return baked ? launch_group_wpb<MODE, GT, WPB, true, true>(c, d, b, a, blocks, pdl, st)
+                     : launch_group_wpb<MODE, GT, WPB, false, true>(c, d, b, a, blocks, pdl, st);
+    return baked ? launch_group_wpb<MODE, GT, WPB, true, false>(c, d, b, a, blocks, pdl, st)
+                 : launch_group_wpb<MODE, GT, WPB, false, false>(c, d, b, a, blocks, pdl, st);
+}
+
 template <int MODE, int GT>
-static int launch_group(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
+static int launch_group(const MrsConfig& c, const Derived& d, const MrsBuffers& b, StepArgs a, cudaStream_t st) {
     constexpr int kBig = 4 * ModeTraits<MODE>::minb;            // warps of a CTA that owns a whole SM
     const int sms = sm_count();
     if (sms <= 0) return MRS_ERR_CUDA;
     static const int use_pdl = env_int("MRS_B200_PDL", 1);
     static const int use_big = env_int("MRS_B200_BIGCTA", 1);
+    static const int use_hand = env_int("MRS_B200_HANDOVER", 1);
     // large jobs (every warp of the GPU gets more than two chunks): one SM-sized CTA per SM with the
     // shared-memory hand-out.  Programmatic dependent launch pays off for full waves (measured
     // -2.3 % at C5); partial waves are faster with plain stream order (C3: +11 % with PDL).
     static const int use_baked = env_int("MRS_B200_BAKED", 1);
     const bool baked = use_baked && config_is_baked(c, d);
     const int nwork = a.nchunks - a.chunk_lo;
-    if (use_big && nwork > 2 * sms * kBig)
-        return baked ? launch_group_wpb<MODE, GT, kBig, true>(c, d, b, a, sms, use_pdl != 0, st)
-                     : launch_group_wpb<MODE, GT, kBig, false>(c, d, b, a, sms, use_pdl != 0, st);
+    if (use_big && nwork > 2 * sms * kBig) {
+        // One launch per step: kCps CTAs per SM (each with 1 / kCps of the SM's warps) and the range hand-over
+        // between the launches of a chain (mrs_rollout; needs the sync words, PDL, full chunks).  Measured at C5
+        // (us per step, 200-step graphs): 1 / 2 / 4 CTAs per SM with a grid-wide dependency 16.7 / 16.6 / 16.8,
+        // with the hand-over 17.2 / 14.7 / 14.3 -- an SM-sized CTA leaves its SM idle through its own hand-over
+        // latency, four small ones hide it behind each other.  Multi-step launches keep one CTA per SM (4.5e10 vs
+        // 3.9e10 agent-steps/s with four).
+        if (a.T > 1) {
+            a.role = 0;
+            return launch_group_variant<MODE, GT, kBig>(c, d, b, a, sms, use_pdl != 0, baked, st);
+        }
+        static const int cps = env_int("MRS_B200_CPS", MRS_DEFAULT_CPS);          // dev builds: 1, 2 or 4
+        if (!(use_hand && use_pdl && b.sync && GT != 0 && sms * cps <= kSyncQueueLen)) a.role = 0;
+#ifdef MRS_CPS_VARIANTS
+        if (cps == 1) return launch_group_variant<MODE, GT, kBig>(c, d, b, a, sms, use_pdl != 0, baked, st);
+        if (cps == 2) return launch_group_variant<MODE, GT, kBig / 2>(c, d, b, a, 2 * sms, use_pdl != 0, baked, st);
+#endif
+        return launch_group_variant<MODE, GT, kBig / MRS_DEFAULT_CPS>(c, d, b, a, MRS_DEFAULT_CPS * sms, use_pdl != 0, baked, st);
+    }
+    a.role = 0;
     const long long need = ((long long)nwork + 3) / 4;
     const long long cap = (long long)sms * ModeTraits<MODE>::minb;
     const long long blocks = need < cap ? need : cap;
     const bool pdl = use_pdl && need >= cap;
-    return baked ? launch_group_wpb<MODE, GT, 4, true>(c, d, b, a, blocks, pdl, st)
-                 : launch_group_wpb<MODE, GT, 4, false>(c, d, b, a, blocks, pdl, st);
+    return launch_group_variant<MODE, GT, 4>(c, d, b, a, blocks, pdl, baked, st);
 }
 
 template <int MODE, int LPA, int LPB>
@@ -1020,6 +1117,7 @@ int dispatch_step(const MrsConfig& c, const MrsBuffers& b, StepArgs a, cudaStrea
         if (rc == MRS_OK && nfull < nchunks) {
             a.chunk_lo = nfull;
             a.nchunks = nchunks;
+            a.role = 0;
             rc = launch_group<MODE, 0>(c, d, b, a, st);
         }
         return rc;

@@ -11,11 +11,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MRS_B200_LIB') or os.path.join(_HERE, 'libmrs_b200.so')   # override: A/B builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 STATE_PLANES = 13
 CTRL_PLANES = 18
 STATS_SLOTS = 8
 SCRATCH_PLANES = 7
+SYNC_WORDS = 2056
 
 # MrsActionType: the reference's ACTION_TYPE strings are Quadcopter method names
 # (/root/reference/mrsgym/Environment.py:92)
@@ -30,6 +31,7 @@ STATE_DIMS = {X_NONE: 0, X_POS_VEL: 6, X_FULL: 13}
 STATUS_NAN_ACTION = 1
 STATUS_NONFINITE = 2
 STATUS_COMM_TIMEOUT = 4
+STATUS_SYNC_TIMEOUT = 8
 COMM_MAX_WORLD = 16
 COMM_HANDLE_BYTES = 64
 STAT_NAMES = ('agent_contact_rows', 'ground_contacts', 'nonfinite', 'nan_actions')
@@ -73,7 +75,7 @@ class MrsConfig(C.Structure):
 class MrsBuffers(C.Structure):
     _fields_ = [('state', C.c_void_p), ('ctrl', C.c_void_p), ('rpm', C.c_void_p),
                 ('X_tape', C.c_void_p), ('A_tape', C.c_void_p), ('scratch', C.c_void_p),
-                ('status', C.c_void_p), ('stats', C.c_void_p)]
+                ('status', C.c_void_p), ('stats', C.c_void_p), ('sync', C.c_void_p)]
 
 
 class MrsError(RuntimeError):
@@ -94,6 +96,8 @@ _SIGNATURES = {
     'mrs_step': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'mrs_step_many': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p]),
+    'mrs_rollout': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p]),
     'mrs_observe': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'mrs_adjacency': (C.c_int, [C.POINTER(MrsConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
     'mrs_set_state': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_void_p, C.c_void_p,

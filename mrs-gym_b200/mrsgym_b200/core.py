@@ -87,6 +87,7 @@ class Swarm:
         self.scratch = torch.zeros(self.lib.mrs_scratch_planes(self.E, self.N), self.S, **z) if self.N > 32 else None
         self.status = torch.zeros(1, device=dev, dtype=torch.int32)
         self.stats = torch.zeros(_abi.STATS_SLOTS, device=dev, dtype=torch.int64)
+        self.sync = torch.zeros(_abi.SYNC_WORDS, device=dev, dtype=torch.int64)    # range hand-over of mrs_rollout
         self.bufs = _abi.MrsBuffers()
         self._cfg_ref, self._bufs_ref = C.byref(self.cfg), C.byref(self.bufs)     # reused by the per-step calls
         self._mrs_step = self.lib.mrs_step
@@ -108,6 +109,7 @@ class Swarm:
         b.A_tape = self.A_tape.data_ptr() if self.A_tape is not None else None
         b.scratch = self.scratch.data_ptr() if self.scratch is not None else None
         b.status, b.stats = self.status.data_ptr(), self.stats.data_ptr()
+        b.sync = self.sync.data_ptr()
 
     def _stream(self):
         if torch.cuda.current_device() != self.device.index:
@@ -267,6 +269,26 @@ class Swarm:
         """T steps as T separate mrs_step launches (each reads and writes the state in HBM)."""
         for t in range(T):
             self.step(actions[t] if actions is not None else None)
+
+    def rollout(self, actions, T: int):
+        """mrs_rollout: T steps as T single-step launches issued by ONE C call; for N in {8, 16, 32} at scale the
+        launches are chained (range hand-over through `sync`, no grid-wide dependency).  Chunks at tape wrap-arounds."""
+        self._check_actions(actions, T)
+        done = 0
+        while done < T:
+            hx = self._make_room(1) if self.X_tape is not None else T
+            ha = self._make_room(2) if self.A_tape is not None else T
+            n = min(T - done, hx, ha)
+            a = actions[done:done + n] if actions is not None else None
+            _abi.check(self.lib.mrs_rollout(self._cfg_ref, self._bufs_ref, _ptr(a), n, hx - 1, ha - 1, self._stream()),
+                       'mrs_rollout')
+            self.launches += self._step_launches(n)
+            if self.X_tape is not None:
+                self.hx = hx - n
+            if self.A_tape is not None:
+                self.ha = ha - n
+                self.a_empty = False
+            done += n
 
     def capture_rollout(self, actions, T: int, stats_comm=None):
         """CUDA-graph a T-step rollout (launch-bound loops belong in graphs): returns a
@@ -494,7 +516,7 @@ class GraphRollout:
         if sw.N > 32:
             sw.step_many(self.actions, self.T)       # wide path: per-step kernels anyway, adjacency overlapped
         else:
-            sw.step_many_single(self.actions, self.T)
+            sw.rollout(self.actions, self.T)             # single-step launches, chained where the shape allows
         if self.stats_comm is not None:
             sw.allreduce_stats(self.stats_comm)
 

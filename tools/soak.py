@@ -1,6 +1,9 @@
-"""Soak: two independent swarms run the same long graph rollout (single-step launches, dynamic chunk hand-out,
-programmatic dependent launch) and one runs it as multi-step launches; all three must end bit-identical, finite,
-with unit quaternions and a symmetric, zero-diagonal adjacency.   python tools/soak.py [workload] [steps]"""
+"""Soak: two independent swarms run the same long graph rollout (chained single-step launches: dynamic chunk
+hand-out inside a CTA, range hand-over between launches) and one runs the same steps as plain stream-ordered
+mrs_step launches; all three must end bit-identical, finite, with unit quaternions and a symmetric, zero-diagonal
+adjacency.  A fourth runs multi-step launches (separately compiled kernel: float32 rounding level, checked over the
+first 10 steps -- a tumbling swarm is chaotic, rounding differences grow e-fold every few steps).
+python tools/soak.py [workload] [steps]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
@@ -14,19 +17,28 @@ E, N, K, T = min(w['E'], 16384 + 3), w['N'], w['K'], 100          # +3: ragged l
 st, act = bench.make_inputs(w, E, T, 5)
 actions = torch.from_numpy(act).cuda()
 sws = []
-for i in range(3):
+for i in range(4):
     sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T, ring=True)
     H.upload_state(sw, st)
     sws.append(sw)
 rolls = [sws[0].capture_rollout(actions, T), sws[1].capture_rollout(actions, T)]
+sws[3].step_many(actions[:10], 10)
+for t in range(10):
+    sws[2].step(actions[t])
+torch.cuda.synchronize()
+dev = float((sws[3].state - sws[2].state).abs().max())
+assert dev < 1e-4, 'step_many drifts from the single-step kernels: %g' % dev
+H.upload_state(sws[2], st)
+sws[2].ctrl.copy_(sws[0].ctrl)
 for r in range(steps // T):
     for roll in rolls:
         roll.replay()
-    sws[2].step_many(actions, T)
+    for t in range(T):
+        sws[2].step(actions[t])
 torch.cuda.synchronize()
-a, b, c = sws
+a, b, c, _ = sws
 assert torch.equal(a.state, b.state), 'two graph rollouts differ'
-assert torch.equal(a.state, c.state), 'graph rollout and step_many differ'
+assert torch.equal(a.state, c.state), 'graph rollout and plain steps differ'
 assert torch.equal(a.X_tape, b.X_tape) and torch.equal(a.A_tape, b.A_tape)
 assert bool(torch.isfinite(a.state).all()) and a.read_status() == 0, a.read_status()
 qn = (a.state[3:7] ** 2).sum(0)
