@@ -40,13 +40,13 @@
 extern "C" {
 #endif
 
-#define MRS_ABI_VERSION 2
+#define MRS_ABI_VERSION 3
 #define MRS_STATE_PLANES 13
 #define MRS_CTRL_PLANES 18
 #define MRS_STATS_SLOTS 8
 #define MRS_SCRATCH_PLANES 7          /* N <= 128 */
 #define MRS_SCRATCH_PAIR_SPLITS 32    /* N > 128: + 2 planes (partial pair sum, flag) per partner slice, <= 32 slices */
-#define MRS_SYNC_WORDS 2056           /* u64 words of MrsBuffers.sync (launch-to-launch range hand-over of mrs_rollout) */
+#define MRS_SYNC_WORDS 8208           /* u64 words of MrsBuffers.sync (launch-to-launch range hand-over of mrs_rollout) */
 #define MRS_COMM_MAX_WORLD 16         /* GPUs of one node a peer communicator spans */
 #define MRS_COMM_HANDLE_BYTES 64      /* size of the opaque mailbox handle exchanged between ranks */
 
@@ -80,6 +80,7 @@ typedef enum {
 /* status word bits (device, sticky; the host reads them lazily) */
 #define MRS_STATUS_NAN_ACTION 1u   /* mirrors the NaN guard of mrsgym/MRS.py:247-248 */
 #define MRS_STATUS_NONFINITE 2u    /* a state component left the finite range        */
+#define MRS_STATUS_CONTACT_OVERFLOW 16u /* N > 32: an env had more agents / pairs in contact than the solver holds */
 #define MRS_STATUS_SYNC_TIMEOUT 8u /* a chained launch of mrs_rollout waited > 2 s for its predecessor's range    */
 #define MRS_STATUS_COMM_TIMEOUT 4u /* mrs_stats_allreduce / mrs_comm_barrier gave up waiting for a peer */
 
@@ -88,6 +89,8 @@ typedef enum {
 #define MRS_STAT_GROUND_CONTACTS 1
 #define MRS_STAT_NONFINITE 2
 #define MRS_STAT_NAN_ACTIONS 3
+#define MRS_STAT_CONTACT_CHUNKS 4   /* N <= 32: warp-chunk steps that took the contact path (solver) */
+#define MRS_STAT_SOLVER_SWEEPS 5    /* N <= 32: Gauss-Seidel sweeps summed over those chunk steps */
 
 /* cf2x.urdf properties (mrsgym/models/cf2x.urdf:5,11-12,42-78), the derived ones of
  * Quadcopter.calculate_parameters (Quadcopter.py:153-168) and the QuadControl gains
@@ -122,7 +125,11 @@ typedef struct {
     float mu_ground, ground_z;
     float col_radius, col_halfheight, col_margin;
     int ground_contact, agent_contact;
-    float agent_radius;                  /* MRS.AGENT_RADIUS, MRS.py:28 */
+    float agent_radius;                  /* MRS.AGENT_RADIUS, MRS.py:28: minimum start separation / 2 (mrs_spawn) */
+    float contact_radius;                /* agent-agent contact sphere (north star: = AGENT_RADIUS; 0.06 = the cf2x hull) */
+    float mu_agent;                      /* quad-quad friction: link default 0.5 x 0.5 */
+    int solver_iters;                    /* Gauss-Seidel sweeps of the contact solver (Bullet numSolverIterations 50) */
+    float solver_tol;                    /* early exit: largest change of a row's contact-point velocity in a sweep [m/s] */
 } MrsPhysicsParams;
 
 typedef struct {

@@ -40,6 +40,15 @@ __device__ __forceinline__ void load_agent(const float* __restrict__ st, unsigne
     a.wx = st[10 * S + s]; a.wy = st[11 * S + s]; a.wz = st[12 * S + s];
 }
 
+// the same through L2 (ld.global.cg): the contact path reads state another SM may have written moments ago
+__device__ __forceinline__ void load_agent_cg(const float* st, unsigned S, unsigned s, Agent& a) {
+    a.px = __ldcg(st + 0 * (size_t)S + s); a.py = __ldcg(st + 1 * (size_t)S + s); a.pz = __ldcg(st + 2 * (size_t)S + s);
+    a.qx = __ldcg(st + 3 * (size_t)S + s); a.qy = __ldcg(st + 4 * (size_t)S + s); a.qz = __ldcg(st + 5 * (size_t)S + s);
+    a.qw = __ldcg(st + 6 * (size_t)S + s);
+    a.vx = __ldcg(st + 7 * (size_t)S + s); a.vy = __ldcg(st + 8 * (size_t)S + s); a.vz = __ldcg(st + 9 * (size_t)S + s);
+    a.wx = __ldcg(st + 10 * (size_t)S + s); a.wy = __ldcg(st + 11 * (size_t)S + s); a.wz = __ldcg(st + 12 * (size_t)S + s);
+}
+
 __device__ __forceinline__ void store_agent(float* __restrict__ st, unsigned S, unsigned s, const Agent& a) {
     st[0 * S + s] = a.px; st[1 * S + s] = a.py; st[2 * S + s] = a.pz;
     st[3 * S + s] = a.qx; st[4 * S + s] = a.qy; st[5 * S + s] = a.qz; st[6 * S + s] = a.qw;
@@ -72,6 +81,28 @@ __device__ __forceinline__ void load_ctrl(const float* __restrict__ ct, unsigned
             k.lve[i] = ct[(9 + i) * S + s];
             k.dve[i] = ct[(12 + i) * S + s];
             k.ltv[i] = ct[(15 + i) * S + s];
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void load_ctrl_cg(const float* ct, unsigned S, unsigned s, Ctrl& k) {
+    using MT = ModeTraits<MODE>;
+    if constexpr (MT::io) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) k.io[i] = __ldcg(ct + (size_t)(0 + i) * S + s);
+    }
+    if constexpr (MT::ip) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) k.ip[i] = __ldcg(ct + (size_t)(3 + i) * S + s);
+    }
+    if constexpr (MT::vel) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            k.iv[i] = __ldcg(ct + (size_t)(6 + i) * S + s);
+            k.lve[i] = __ldcg(ct + (size_t)(9 + i) * S + s);
+            k.dve[i] = __ldcg(ct + (size_t)(12 + i) * S + s);
+            k.ltv[i] = __ldcg(ct + (size_t)(15 + i) * S + s);
         }
     }
 }
@@ -233,9 +264,11 @@ inline Derived make_derived(const MrsConfig& c) {
     const double cap_ang = 0.5 * 1.57079632679489661923 / (double)c.dt;      // Bullet: 0.5 * SIMD_HALF_PI / dt
     d.cap_k = (float)(sin(0.5 * cap_ang * (double)c.dt) / cap_ang);
     d.cap_c = (float)cos(0.5 * cap_ang * (double)c.dt);
-    const float lim = 2.f * p.agent_radius + p.contact_margin;
+    const float lim = 2.f * p.contact_radius + p.contact_margin;
     d.lim2 = lim * lim;
-    d.gnd_skip_z = p.ground_z + p.contact_margin + p.col_radius + p.col_halfheight + p.col_margin + 1e-3f;
+    // no rim point of the collision cylinder reaches lower than sqrt(r^2 + h^2) below the CoM
+    d.gnd_skip_z = p.ground_z + p.contact_margin + sqrtf(p.col_radius * p.col_radius + p.col_halfheight * p.col_halfheight) +
+                   p.col_margin + 1e-3f;
     d.inv_dt = (float)(1.0 / (double)c.dt);
     d.erp_dt = (float)((double)p.erp2 / (double)c.dt);
     d.comm_inf = isinf(c.comm_range) && c.comm_range > 0.f;
@@ -277,6 +310,9 @@ inline void pair_split(int E, int N, int* jw, int* nsplit) {
 // defined in mrs_kernels.cu
 int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, int N, float s_max, int comm_inf,
                      cudaStream_t st);
+// wide path (N > 32): joint contact solve per env (one CTA per env) and the per-agent post pass
+int launch_contact_env(const MrsConfig& c, const Derived& d, const MrsBuffers& b, cudaStream_t st);
+int launch_step_post(const MrsConfig& c, const Derived& d, const MrsBuffers& b, int slot, cudaStream_t st);
 struct SideLane {
     cudaStream_t s = nullptr;
     cudaEvent_t posted = nullptr, adj_done = nullptr;

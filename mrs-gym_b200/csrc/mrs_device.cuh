@@ -93,7 +93,7 @@ struct Derived {
     float q_x2;          // 0.25*dt^2: squared half rotation angle per unit |w|^2
     float cap_w2;        // (ang_motion_threshold/dt)^2
     float cap_k, cap_c;  // sin(pi/8) / ((pi/4)/dt), cos(pi/8): Bullet's capped angular step
-    float lim2;          // (2*agent_radius + contact_margin)^2
+    float lim2;          // (2*contact_radius + contact_margin)^2
     float gnd_skip_z;    // above this height the ground contact row cannot be active
     float inv_dt, erp_dt;
     float s_max;         // adjacency threshold on the squared distance
@@ -357,46 +357,204 @@ __device__ __forceinline__ void apply_wrench(const MrsConfig& c, const Derived& 
     s.wz = clampf(s.wz + c.dt * (R[6] * wd[0] + R[7] * wd[1] + R[8] * wd[2]), -mv, mv);
 }
 
-// contact row right-hand side (bullet_model._contact_rhs)
-__device__ __forceinline__ float contact_rhs(const MrsPhysicsParams& ph, const Derived& d, float dist, float vn) {
-    const float pen = dist + ph.slop;
-    const float rhs = (pen > 0.f) ? (-vn - pen * d.inv_dt) : (-vn - pen * d.erp_dt);
-    return fmaxf(rhs, 0.f);
+// ------------------------------------------------------------------------------------------
+// Contact solver (bullet_model.solve_contacts): velocity-level sequential impulses, restitution 0, Baumgarte
+// push-out, `solver_iters` Gauss-Seidel sweeps with early exit below `solver_tol`.  Sweep order: the ground rows
+// of every agent (four lower-rim points of the collision cylinder, normal rows applied AT the points -> righting
+// torque; two friction rows at the CoM), then the agent-agent rows (CONTACT_RADIUS spheres: central normal row +
+// two friction rows on the CoM velocities) in round-robin-tournament order -- the rows of one round touch disjoint
+// agents, so a warp (N <= 32) or a CTA (N > 32) processes a round in parallel without changing the result.
+
+// the constants the contact rows use, gathered from MrsPhysicsParams / Derived at the call site: a plain value
+// (the out-of-line warp solver takes it by value, so the hot kernels never have to keep their configuration in memory)
+struct ContactParams {
+    float mass, inv_mass, inv_I[3];
+    float col_radius, col_halfheight, col_margin, ground_z, contact_margin, slop, inv_dt, erp_dt;
+    float mu_ground, mu_agent, contact_radius, lim2, gnd_skip_z, solver_tol;
+    int solver_iters, ground_contact, agent_contact;
+};
+__device__ __forceinline__ ContactParams make_contact_params(const MrsPhysicsParams& ph, const Derived& d) {
+    ContactParams cp;
+    cp.mass = ph.mass; cp.inv_mass = d.inv_mass;
+    cp.inv_I[0] = d.inv_I[0]; cp.inv_I[1] = d.inv_I[1]; cp.inv_I[2] = d.inv_I[2];
+    cp.col_radius = ph.col_radius; cp.col_halfheight = ph.col_halfheight; cp.col_margin = ph.col_margin;
+    cp.ground_z = ph.ground_z; cp.contact_margin = ph.contact_margin; cp.slop = ph.slop;
+    cp.inv_dt = d.inv_dt; cp.erp_dt = d.erp_dt;
+    cp.mu_ground = ph.mu_ground; cp.mu_agent = ph.mu_agent; cp.contact_radius = ph.contact_radius;
+    cp.lim2 = d.lim2; cp.gnd_skip_z = d.gnd_skip_z; cp.solver_tol = ph.solver_tol;
+    cp.solver_iters = ph.solver_iters; cp.ground_contact = ph.ground_contact; cp.agent_contact = ph.agent_contact;
+    return cp;
 }
 
-// sphere-sphere contact of agent i with agent j (bullet_model.agent_contact_dv): d = p_i - p_j,
-// dv = v*_i - v*_j; returns true and adds this row's velocity change to acc when it pushes.
-// 1/|d| from the SFU with one Newton step (full float32 accuracy): a swarm that has come to rest on
-// the ground in a heap takes this path for every pair and step.
-__device__ __forceinline__ bool agent_contact_pair(const MrsPhysicsParams& ph, const Derived& dd, float dx, float dy,
-                                                   float dz, float dvx, float dvy, float dvz, float* acc) {
+// velocity bound of a normal row: vn >= bias after the solve (bullet_model._contact_bias)
+__device__ __forceinline__ float contact_bias(const ContactParams& cp, float dist) {
+    const float pen = dist + cp.slop;
+    return (pen > 0.f) ? -pen * cp.inv_dt : -pen * cp.erp_dt;
+}
+
+// ground rows of one agent.  nb = world z in the body frame (row 2 of R); the contact points are
+// c_p = (+-r, 0, cz), (0, +-r, cz) on the rim of the face that looks down (cz = -h sign(R22));
+// a_p = c_p x nb is the angular Jacobian of point p's normal row in the body frame.
+struct GroundRows {
+    float A, B, rnx, rny, rnz;      // a_0 = (A, B - rnz, rny), a_1 = (A + rnz, B, -rnx), a_2 = (A, B + rnz, -rny), a_3 = (A - rnz, B, rnx)
+    float K[4], invK[4], bias[4];
+    unsigned act;                   // bit p: point p is within the contact margin
+};
+
+__device__ __forceinline__ void ground_point_jacobian(const GroundRows& g, int p, float* a) {
+    a[0] = g.A + ((p == 1) ? g.rnz : (p == 3) ? -g.rnz : 0.f);
+    a[1] = g.B + ((p == 0) ? -g.rnz : (p == 2) ? g.rnz : 0.f);
+    a[2] = (p == 0) ? g.rny : (p == 1) ? -g.rnx : (p == 2) ? -g.rny : g.rnx;
+}
+
+__device__ __forceinline__ void ground_setup(const ContactParams& cp, float pz, const float* R,
+                                             GroundRows& g) {
+    const float nx = R[6], ny = R[7], nz = R[8];
+    const float cz = (nz >= 0.f) ? -cp.col_halfheight : cp.col_halfheight;
+    g.A = -cz * ny; g.B = cz * nx;
+    g.rnx = cp.col_radius * nx; g.rny = cp.col_radius * ny; g.rnz = cp.col_radius * nz;
+    const float zc = pz + cz * nz - cp.col_margin - cp.ground_z;
+    const float dist[4] = {zc + g.rnx, zc + g.rny, zc - g.rnx, zc - g.rny};
+    g.act = 0u;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float a[3];
+        ground_point_jacobian(g, p, a);
+        g.K[p] = cp.inv_mass + a[0] * a[0] * cp.inv_I[0] + a[1] * a[1] * cp.inv_I[1] + a[2] * a[2] * cp.inv_I[2];
+        g.invK[p] = 1.f / g.K[p];
+        g.bias[p] = contact_bias(cp, dist[p]);
+        if (dist[p] < cp.contact_margin) g.act |= 1u << p;
+    }
+}
+
+// one sweep over the ground rows of one agent; v world, wb body-frame angular velocity; returns the largest
+// change of a row's contact-point velocity in the sweep
+__device__ __forceinline__ float ground_sweep(const ContactParams& cp, const GroundRows& g, float* lam,
+                                              float* fl, float* v, float* wb) {
+    float worst = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float a[3];
+        ground_point_jacobian(g, p, a);
+        const float vn = v[2] + a[0] * wb[0] + a[1] * wb[1] + a[2] * wb[2];
+        const float ln = fmaxf(lam[p] + (g.bias[p] - vn) * g.invK[p], 0.f);
+        const float dl = ((g.act >> p) & 1u) ? ln - lam[p] : 0.f;
+        lam[p] += dl;
+        v[2] += dl * cp.inv_mass;
+        wb[0] += a[0] * cp.inv_I[0] * dl; wb[1] += a[1] * cp.inv_I[1] * dl; wb[2] += a[2] * cp.inv_I[2] * dl;
+        worst = fmaxf(worst, fabsf(dl) * g.K[p]);
+    }
+    const float lim = cp.mu_ground * ((lam[0] + lam[1]) + (lam[2] + lam[3]));
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float ln = clampf(fl[k] - v[k] * cp.mass, -lim, lim);
+        const float dl = ln - fl[k];
+        fl[k] = ln;
+        v[k] += dl * cp.inv_mass;
+        worst = fmaxf(worst, fabsf(dl) * cp.inv_mass);
+    }
+    return worst;
+}
+
+// ground rows only (an agent that touches nothing but the ground): all sweeps at once.  Returns true when a
+// normal impulse acted.
+__device__ __forceinline__ bool ground_solve(const ContactParams& cp, Agent& s, const float* R, unsigned* sweeps = nullptr) {
+    GroundRows g;
+    ground_setup(cp, s.pz, R, g);
+    if (g.act == 0u) return false;
+    float lam[4] = {0.f, 0.f, 0.f, 0.f}, fl[2] = {0.f, 0.f};
+    float v[3] = {s.vx, s.vy, s.vz};
+    float wb[3] = {R[0] * s.wx + R[3] * s.wy + R[6] * s.wz, R[1] * s.wx + R[4] * s.wy + R[7] * s.wz,
+                   R[2] * s.wx + R[5] * s.wy + R[8] * s.wz};
+    unsigned n = 0;
+    for (int it = 0; it < cp.solver_iters; ++it) {
+        ++n;
+        if (ground_sweep(cp, g, lam, fl, v, wb) < cp.solver_tol) break;
+    }
+    if (sweeps) *sweeps = n;
+    s.vx = v[0]; s.vy = v[1]; s.vz = v[2];
+    s.wx = R[0] * wb[0] + R[1] * wb[1] + R[2] * wb[2];
+    s.wy = R[3] * wb[0] + R[4] * wb[1] + R[5] * wb[2];
+    s.wz = R[6] * wb[0] + R[7] * wb[1] + R[8] * wb[2];
+    return (lam[0] + lam[1]) + (lam[2] + lam[3]) > 0.f;
+}
+
+// btPlaneSpace1: two unit tangents of the unit normal n (p is odd in n, q even: the two agents of a pair derive
+// the same rows from n and -n)
+__device__ __forceinline__ void plane_space(const float* n, float* p, float* q) {
+    if (fabsf(n[2]) > 0.7071067811865475f) {
+        const float a = n[1] * n[1] + n[2] * n[2];
+        const float k = rsqrt_nr(a);
+        p[0] = 0.f; p[1] = -n[2] * k; p[2] = n[1] * k;
+        q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+    } else {
+        const float a = n[0] * n[0] + n[1] * n[1];
+        const float k = rsqrt_nr(a);
+        p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0.f;
+        q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+    }
+}
+
+// agent-agent rows of one pair as seen from agent `me` (d = p_me - p_partner, dv = v_me - v_partner): updates the
+// three accumulated impulses and returns the velocity change of `me` (the partner, evaluating the same rows from
+// its side with -d and -dv, gets the exact opposite).  mass-normalised: both agents weigh the same, K = 2 / m.
+__device__ __forceinline__ float pair_rows(const ContactParams& cp, float dx, float dy, float dz,
+                                           const float* vme, const float* vpt, float* lam3, float* dv_me, bool& active) {
     const float d2 = dx * dx + dy * dy + dz * dz;
-    if (!(d2 < dd.lim2) || !(d2 > 0.f)) return false;
-    const float inv = rsqrt_nr(d2);
-    const float d = d2 * inv;
-    const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
-    const float vn = dvx * nx + dvy * ny + dvz * nz;
-    const float rhs = 0.5f * contact_rhs(ph, dd, d - 2.f * ph.agent_radius, vn);
-    acc[0] += rhs * nx; acc[1] += rhs * ny; acc[2] += rhs * nz;
-    return rhs > 0.f;
+    const float inv = rsqrt_nr(fmaxf(d2, 1e-30f));
+    const float dist = d2 * inv - 2.f * cp.contact_radius;
+    active = (dist < cp.contact_margin) && (d2 > 0.f);
+    dv_me[0] = dv_me[1] = dv_me[2] = 0.f;
+    if (!active) return 0.f;
+    const float n[3] = {dx * inv, dy * inv, dz * inv};
+    float t1[3], t2[3];
+    plane_space(n, t1, t2);
+    const float half_m = 0.5f * cp.mass;
+    float rel[3] = {vme[0] - vpt[0], vme[1] - vpt[1], vme[2] - vpt[2]};
+    float worst = 0.f;
+    // normal row
+    {
+        const float vr = n[0] * rel[0] + n[1] * rel[1] + n[2] * rel[2];
+        const float ln = fmaxf(lam3[0] + (contact_bias(cp, dist) - vr) * half_m, 0.f);
+        const float dl = (ln - lam3[0]) * cp.inv_mass;
+        lam3[0] = ln;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { dv_me[k] += n[k] * dl; rel[k] += 2.f * n[k] * dl; }
+        worst = 2.f * fabsf(dl);
+    }
+    const float lim = cp.mu_agent * lam3[0];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const float* u = r ? t2 : t1;
+        const float vr = u[0] * rel[0] + u[1] * rel[1] + u[2] * rel[2];
+        const float ln = clampf(lam3[1 + r] - vr * half_m, -lim, lim);
+        const float dl = (ln - lam3[1 + r]) * cp.inv_mass;
+        lam3[1 + r] = ln;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { dv_me[k] += u[k] * dl; rel[k] += 2.f * u[k] * dl; }
+        worst = fmaxf(worst, 2.f * fabsf(dl));
+    }
+    return worst;
 }
 
-// ground plane vs the quad's collision cylinder, impulse at the CoM (bullet_model.ground_contact).
-// Agents higher than gnd_skip_z cannot have an active row whatever their attitude: early out.
-__device__ __forceinline__ bool ground_contact(const MrsPhysicsParams& ph, const Derived& d, Agent& s) {
-    if (s.pz >= d.gnd_skip_z) return false;
-    const float R22 = 1.f - 2.f * (s.qx * s.qx + s.qy * s.qy);
-    // SFU sqrt / rcp: a swarm resting on the ground takes this path for every agent and step
-    const float ext = ph.col_radius * fast_sqrt(fmaxf(1.f - R22 * R22, 0.f)) + ph.col_halfheight * fabsf(R22) + ph.col_margin;
-    const float dist = s.pz - ext - ph.ground_z;
-    if (!(dist < ph.contact_margin)) return false;
-    const float jn = contact_rhs(ph, d, dist, s.vz);
-    const float vt2 = s.vx * s.vx + s.vy * s.vy;
-    const float scale = (vt2 > 0.f) ? fminf(1.f, ph.mu_ground * jn * fast_rsqrt(vt2)) : 0.f;
-    s.vz += jn;
-    s.vx -= s.vx * scale;
-    s.vy -= s.vy * scale;
-    return jn > 0.f;
+// round-robin tournament over M = N rounded up to even (bullet_model.tournament_partner): partner of agent i in
+// round r (i itself = sits out), and the round in which i < j meet
+__device__ __forceinline__ int tour_partner(int r, int i, int N) {
+    const int M = N + (N & 1), m1 = M - 1;
+    int j;
+    if (i == m1) j = r;
+    else {
+        j = 2 * r - i;
+        if (j < 0) j += m1;
+        if (j >= m1) j -= m1;
+        if (j == i) j = m1;
+    }
+    return (j >= N) ? i : j;
+}
+__device__ __forceinline__ int tour_round(int i, int j, int N) {          // i < j < N
+    const int M = N + (N & 1), m1 = M - 1;
+    if (j == m1) return i;
+    return (int)(((long long)(i + j) * (M / 2)) % m1);
 }
 
 // btMultiBody::stepPositionsMultiDof (bullet_model.integrate_positions): p += dt v; q <- dq (x) q

@@ -339,6 +339,209 @@ tape_fill_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t 
     }
 }
 
+// ------------------------------------------------------------------------------ wide path: contact + post
+// Joint contact solve of ONE env of the wide path (N > 32; bullet_model.solve_contacts), one CTA per env, one thread
+// per FLAGGED agent (agents within contact range of another agent: scratch plane 6, written by the pre pass).  An
+// env without flagged agents costs one coalesced read of its flags.  The flagged agents' velocities live in shared
+// memory; the pairs in range are listed once (they are pairs of flagged agents) with their tournament round; a
+// sweep runs the ground rows of the flagged agents, then the rounds that hold a pair in ascending order -- the pairs
+// of one round touch disjoint agents, so the threads process them in parallel (CTA barrier between rounds).
+// Agents that touch only the ground are solved on their own in step_post_kernel.
+// Limits: blockDim flagged agents and 4 * blockDim pairs per env (blockDim = N rounded up to a warp, <= 1024);
+// beyond that the surplus is left unsolved and MRS_STATUS_CONTACT_OVERFLOW is raised.
+__host__ __device__ inline size_t contact_env_smem(int threads) {
+    return (size_t)threads * (4 + 12 + 12) + (size_t)(4 * threads) * (4 + 4 + 12) + 128 * 4;
+}
+
+__global__ void __launch_bounds__(1024)
+contact_env_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int n_flag, n_pair;
+    __shared__ unsigned worst_bits;
+    const int cap = blockDim.x, pcap = 4 * blockDim.x;
+    int* fl_idx = reinterpret_cast<int*>(smem_raw);
+    float* sp = reinterpret_cast<float*>(fl_idx + cap);            // [cap][3] pre-step positions
+    float* sv = sp + 3 * cap;                                       // [cap][3] velocities
+    unsigned* pr_ij = reinterpret_cast<unsigned*>(sv + 3 * cap);    // [pcap] lo | hi << 16 (local indices)
+    int* pr_round = reinterpret_cast<int*>(pr_ij + pcap);           // [pcap]
+    float* pr_lam = reinterpret_cast<float*>(pr_round + pcap);      // [pcap][3]
+    unsigned* rmask = reinterpret_cast<unsigned*>(pr_lam + 3 * pcap);   // [128] rounds that hold a pair
+    const int N = c.N, tid = threadIdx.x;
+    const size_t S = (size_t)c.E * N, env0 = (size_t)blockIdx.x * N;
+    const MrsPhysicsParams& ph = c.phys;
+    const ContactParams cp = make_contact_params(ph, d);
+    const float* __restrict__ sc = b.scratch;
+    if (tid == 0) { n_flag = 0; n_pair = 0; }
+    if (tid < 128) rmask[tid] = 0u;
+    __syncthreads();
+    for (int i = tid; i < N; i += blockDim.x)
+        if (sc[6 * S + env0 + i] != 0.f) {
+            const int f = atomicAdd(&n_flag, 1);
+            if (f < cap) fl_idx[f] = i;
+        }
+    __syncthreads();
+    if (n_flag == 0) return;
+    const int F = min(n_flag, cap);
+    // my agent (thread f < F)
+    const bool mine = tid < F;
+    const int ai = mine ? fl_idx[tid] : 0;
+    const size_t s = env0 + ai;
+    float R[9], wb[3] = {0.f, 0.f, 0.f};
+    GroundRows g;
+    g.act = 0u;
+    float lam_g[4] = {0.f, 0.f, 0.f, 0.f}, fl[2] = {0.f, 0.f};
+    if (mine) {
+        Agent st;
+        st.qx = b.state[3 * S + s]; st.qy = b.state[4 * S + s]; st.qz = b.state[5 * S + s]; st.qw = b.state[6 * S + s];
+        quat_to_mat(st, R);
+        const float wx = b.state[10 * S + s], wy = b.state[11 * S + s], wz = b.state[12 * S + s];
+        wb[0] = R[0] * wx + R[3] * wy + R[6] * wz; wb[1] = R[1] * wx + R[4] * wy + R[7] * wz;
+        wb[2] = R[2] * wx + R[5] * wy + R[8] * wz;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sp[3 * tid + k] = sc[(3 + k) * S + s]; sv[3 * tid + k] = sc[k * S + s]; }
+        if (ph.ground_contact && sp[3 * tid + 2] < d.gnd_skip_z) ground_setup(cp, sp[3 * tid + 2], R, g);
+    }
+    __syncthreads();
+    if (mine) {
+        for (int q = 0; q < F; ++q) {
+            const int aj = fl_idx[q];
+            if (aj <= ai) continue;
+            const float dx = sp[3 * tid] - sp[3 * q], dy = sp[3 * tid + 1] - sp[3 * q + 1], dz = sp[3 * tid + 2] - sp[3 * q + 2];
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < d.lim2 && d2 > 0.f) {
+                const int k = atomicAdd(&n_pair, 1);
+                if (k < pcap) {
+                    const int r = tour_round(ai, aj, N);
+                    pr_ij[k] = (unsigned)tid | ((unsigned)q << 16);
+                    pr_round[k] = r;
+                    pr_lam[3 * k] = pr_lam[3 * k + 1] = pr_lam[3 * k + 2] = 0.f;
+                    atomicOr(&rmask[r >> 5], 1u << (r & 31));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int P = min(n_pair, pcap);
+    if ((n_flag > cap || n_pair > pcap) && tid == 0 && b.status) atomicOr(b.status, MRS_STATUS_CONTACT_OVERFLOW);
+    const int words = (N + (N & 1) - 1 + 31) / 32;
+    for (int it = 0; it < ph.solver_iters; ++it) {
+        if (tid == 0) worst_bits = 0u;
+        float worst = 0.f;
+        if (mine && g.act) {
+            float v[3] = {sv[3 * tid], sv[3 * tid + 1], sv[3 * tid + 2]};
+            worst = ground_sweep(cp, g, lam_g, fl, v, wb);
+            sv[3 * tid] = v[0]; sv[3 * tid + 1] = v[1]; sv[3 * tid + 2] = v[2];
+        }
+        __syncthreads();
+        for (int w = 0; w < words; ++w) {
+            for (unsigned m = rmask[w]; m; m &= m - 1u) {
+                const int r = 32 * w + __ffs(m) - 1;
+                for (int k = tid; k < P; k += blockDim.x) {
+                    if (pr_round[k] != r) continue;
+                    const int lo = pr_ij[k] & 0xffffu, hi = pr_ij[k] >> 16;
+                    float dv[3];
+                    bool act;
+                    const float wr = pair_rows(cp, sp[3 * lo] - sp[3 * hi], sp[3 * lo + 1] - sp[3 * hi + 1],
+                                               sp[3 * lo + 2] - sp[3 * hi + 2], sv + 3 * lo, sv + 3 * hi, pr_lam + 3 * k, dv, act);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { sv[3 * lo + q] += dv[q]; sv[3 * hi + q] -= dv[q]; }
+                    worst = fmaxf(worst, wr);
+                }
+                __syncthreads();
+            }
+        }
+        atomicMax(&worst_bits, __float_as_uint(worst));
+        __syncthreads();
+        const bool done = __uint_as_float(worst_bits) < ph.solver_tol;
+        __syncthreads();
+        if (done) break;
+    }
+    unsigned rows = 0;
+    for (int k = tid; k < P; k += blockDim.x)
+        if (pr_lam[3 * k] > 0.f) rows += 2;           // counted per agent, like the N <= 32 path
+    if (mine) {
+        float* scw = b.scratch;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) scw[k * S + s] = sv[3 * tid + k];
+        b.state[10 * S + s] = R[0] * wb[0] + R[1] * wb[1] + R[2] * wb[2];
+        b.state[11 * S + s] = R[3] * wb[0] + R[4] * wb[1] + R[5] * wb[2];
+        b.state[12 * S + s] = R[6] * wb[0] + R[7] * wb[1] + R[8] * wb[2];
+    }
+    const unsigned gnd = (mine && (lam_g[0] + lam_g[1]) + (lam_g[2] + lam_g[3]) > 0.f) ? 1u : 0u;
+    const unsigned w_rows = __reduce_add_sync(kFull32, rows), w_gnd = __reduce_add_sync(kFull32, gnd);
+    if ((tid & 31) == 0 && b.stats) {
+        if (w_rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)w_rows);
+        if (w_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)w_gnd);
+    }
+}
+
+// post pass of the wide path, one thread per agent: ground-only contact solve (agents flagged for agent-agent
+// contact were solved by contact_env_kernel), position / attitude integration, state store, newest X slice
+__global__ void __launch_bounds__(kBlock)
+step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int slot) {
+    const unsigned S = (unsigned)c.E * (unsigned)c.N;
+    const unsigned gid = blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = gid < S;
+    const unsigned s = valid ? gid : 0u;
+    const MrsPhysicsParams& ph = c.phys;
+    const float* __restrict__ sc = b.scratch;
+    unsigned gnd = 0, bad = 0;
+    if (valid) {
+        Agent st;
+        st.px = sc[3 * (size_t)S + s]; st.py = sc[4 * (size_t)S + s]; st.pz = sc[5 * (size_t)S + s];
+        st.vx = sc[0 * (size_t)S + s]; st.vy = sc[1 * (size_t)S + s]; st.vz = sc[2 * (size_t)S + s];
+        const bool solved = sc[6 * (size_t)S + s] != 0.f;
+        st.qx = b.state[3 * (size_t)S + s]; st.qy = b.state[4 * (size_t)S + s]; st.qz = b.state[5 * (size_t)S + s];
+        st.qw = b.state[6 * (size_t)S + s];
+        st.wx = b.state[10 * (size_t)S + s]; st.wy = b.state[11 * (size_t)S + s]; st.wz = b.state[12 * (size_t)S + s];
+        if (ph.ground_contact && !solved && st.pz < d.gnd_skip_z) {
+            float R[9];
+            quat_to_mat(st, R);
+            if (ground_solve(make_contact_params(ph, d), st, R)) gnd = 1;
+        }
+        integrate(c, d, st);
+        store_agent(b.state, S, s, st);
+        if (b.X_tape && c.state_layout != MRS_X_NONE)
+            write_X(b.X_tape + (size_t)slot * S * state_dim(c.state_layout), c.state_layout, s, st);
+        bad = agent_finite(st) ? 0u : 1u;
+    }
+    // statistics: one warp reduction, then at most two global atomics per warp (not per agent)
+    const unsigned w_gnd = __reduce_add_sync(kFull32, gnd);
+    const unsigned w_bad = __reduce_add_sync(kFull32, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (w_bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
+        if (b.stats) {
+            if (w_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)w_gnd);
+            if (w_bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)w_bad);
+        }
+    }
+}
+
+// launches contact_env_kernel (one CTA per env) when agent-agent contact is enabled
+int launch_contact_env(const MrsConfig& c, const Derived& d, const MrsBuffers& b, cudaStream_t st) {
+    if (!c.phys.agent_contact || c.N < 2) return MRS_OK;
+    int threads = (c.N + 31) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    const size_t smem = contact_env_smem(threads);
+    static bool configured[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MRS_ERR_CUDA;
+    if (!configured[dev]) {
+        if (cudaFuncSetAttribute(contact_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)contact_env_smem(1024)) != cudaSuccess)
+            return MRS_ERR_CUDA;
+        configured[dev] = true;
+    }
+    contact_env_kernel<<<(unsigned)c.E, threads, smem, st>>>(c, d, b);
+    return last_error();
+}
+
+int launch_step_post(const MrsConfig& c, const Derived& d, const MrsBuffers& b, int slot, cudaStream_t st) {
+    const size_t S = (size_t)c.E * c.N;
+    step_post_kernel<<<(unsigned)((S + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, d, b, slot);
+    return last_error();
+}
+
 // ------------------------------------------------------------------------------ host side
 int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, int N, float s_max, int comm_inf,
                             cudaStream_t st) {
@@ -558,7 +761,8 @@ int mrs_default_config(MrsConfig* cfg) {
     p.mu_ground = 0.75f; p.ground_z = 0.5f;
     p.col_radius = 0.06f; p.col_halfheight = 0.0125f; p.col_margin = 0.001f;
     p.ground_contact = 1; p.agent_contact = 1;
-    p.agent_radius = 0.3f;
+    p.agent_radius = 0.3f; p.contact_radius = 0.3f;
+    p.mu_agent = 0.25f; p.solver_iters = 50; p.solver_tol = 1e-6f;
     return MRS_OK;
 }
 

@@ -54,9 +54,177 @@ __device__ __forceinline__ const float* plane_ptr(const float* p0, unsigned S, i
     return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p0) + (unsigned long long)S * (unsigned)(pl * 4));
 }
 
+// ------------------------------------------------------------------------------ contact path of the group kernels
+// One step of one warp-chunk, global memory to global memory, WITH the contact solver
+// (bullet_model.solve_contacts): the group kernels call it for a chunk in which some agent is near the ground or
+// near another agent, and carry no contact code themselves.  It is expanded at ONE place, the top of the chunk loop,
+// where nothing but the loop bookkeeping is live, and reads the kernel parameters (constant bank): the fast path pays
+// no registers for a path free flight never takes.  (A real call was tried: the ABI's caller-saved spills went to
+// local memory across the whole kernel and the chained launches started to miss their hand-over entries.)
+// Same arithmetic as the fast path for everything but the contact rows; plain (unrolled-free) loops.
+// In-warp solve: every lane owns one agent, its ground rows and -- per tournament round -- the pair rows with its
+// round partner; the partner's velocity travels by shuffle, both lanes of a pair evaluate the same rows from their
+// own side and get equal and opposite changes.
+template <int MODE>
+static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr, const Derived* dptr, const MrsBuffers* bptr,
+                                                       const StepArgs* aptr, int G, int chunk, int t0, int T, float4* wpos,
+                                                       unsigned* sh_events) {
+    const MrsConfig& c = *cptr;
+    const Derived& d = *dptr;
+    const MrsBuffers& b = *bptr;
+    const StepArgs& a = *aptr;
+    const int lane = threadIdx.x & 31;
+    const int N = c.N, E = c.E;
+    const int gpw = 32 / G, ai = lane & (G - 1), gb = lane - ai;
+    const unsigned S = (unsigned)E * (unsigned)N;
+    const int e = chunk * gpw + (lane / G);
+    const bool valid = (e < E) && (ai < N);
+    const unsigned s = valid ? (unsigned)e * (unsigned)N + (unsigned)ai : 0u;
+    const MrsPhysicsParams& ph = c.phys;
+    const ContactParams cp = make_contact_params(ph, d);
+    constexpr int kA = ModeTraits<MODE>::A;
+    Agent st;
+    Ctrl k;
+    if (valid) {
+        load_agent_cg(b.state, S, s, st);
+        load_ctrl_cg<MODE>(b.ctrl, S, s, k);
+    } else {
+        dummy_agent(st);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) k.io[i] = k.ip[i] = k.iv[i] = k.lve[i] = k.dve[i] = k.ltv[i] = 0.f;
+    }
+    if (lane == 0) atomicAdd(&sh_events[5], (unsigned)(T - t0));
+  for (int t = t0; t < T; ++t) {
+    unsigned status = 0, n_agent_rows = 0, n_ground = 0, n_sweeps = 0;
+    float act[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid && kA > 0 && load_action<MODE>(a.actions, (size_t)t * S + s, act)) status |= MRS_STATUS_NAN_ACTION;
+    float R[9], rpm[4];
+    quat_to_mat(st, R);
+    action_to_rpm<MODE>(c, c.quad, d, st, R, act, k, rpm);
+    if (b.rpm && MODE != MRS_NO_ACTION && valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b.rpm[(size_t)i * S + s] = rpm[i];
+    }
+    // pair pass 1: downwash on the pre-step positions
+    __syncwarp();
+    wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
+    __syncwarp();
+    float dw = 0.f;
+    bool near = false;
+    for (int r = 1; r < G; ++r) {
+        const int j = ai ^ r;
+        if (j < N) {
+            const float4 pj = wpos[gb + j];
+            const float rx = pj.x - st.px, ry = pj.y - st.py, rz = pj.z - st.pz;
+            const float dxy2 = rx * rx + ry * ry;
+            if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, d, dxy2, rz);
+            near = near || (dxy2 + rz * rz < cp.lim2);
+        }
+    }
+    apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
+    // ---- contact solve
+    const bool gcand = cp.ground_contact && valid && st.pz < cp.gnd_skip_z;
+    GroundRows g;
+    g.act = 0u;
+    if (gcand) ground_setup(cp, st.pz, R, g);
+    // rounds in which some pair of this warp is in range (positions do not change during the solve)
+    unsigned ract = 0u;
+    if (__any_sync(kFull32, cp.agent_contact && near && valid)) {
+        const int rounds = N + (N & 1) - 1;
+        for (int r = 0; r < rounds; ++r) {
+            const int j = valid ? tour_partner(r, ai, N) : ai;
+            const float4 pj = wpos[gb + j];
+            const float dx = st.px - pj.x, dy = st.py - pj.y, dz = st.pz - pj.z;
+            const bool in = (j != ai) && (dx * dx + dy * dy + dz * dz < cp.lim2);
+            if (__any_sync(kFull32, in)) ract |= 1u << r;
+        }
+    }
+    if (__any_sync(kFull32, g.act != 0u) || ract) {
+        float lam_g[4] = {0.f, 0.f, 0.f, 0.f}, fl[2] = {0.f, 0.f};
+        float lam_p[3 * 31];
+        for (unsigned m = ract; m; m &= m - 1u) {
+            const int r = __ffs(m) - 1;
+            lam_p[3 * r] = lam_p[3 * r + 1] = lam_p[3 * r + 2] = 0.f;
+        }
+        float v[3] = {st.vx, st.vy, st.vz};
+        float wb[3] = {R[0] * st.wx + R[3] * st.wy + R[6] * st.wz, R[1] * st.wx + R[4] * st.wy + R[7] * st.wz,
+                       R[2] * st.wx + R[5] * st.wy + R[8] * st.wz};
+        // An env stops sweeping when ITS rows have converged (like the oracle), whatever the other envs of the warp
+        // do: its result does not depend on which envs it shares a warp with (shard invariance).
+        bool alive = valid;
+        for (int it = 0; it < cp.solver_iters; ++it) {
+            float worst = 0.f;
+            if (alive && g.act) worst = ground_sweep(cp, g, lam_g, fl, v, wb);
+            for (unsigned m = ract; m; m &= m - 1u) {
+                const int r = __ffs(m) - 1;
+                const int j = valid ? tour_partner(r, ai, N) : ai;
+                const float vj[3] = {__shfl_sync(kFull32, v[0], gb + j), __shfl_sync(kFull32, v[1], gb + j),
+                                     __shfl_sync(kFull32, v[2], gb + j)};
+                if (alive && j != ai) {
+                    const float4 pj = wpos[gb + j];
+                    float dv[3];
+                    bool on;
+                    const float wr = pair_rows(cp, st.px - pj.x, st.py - pj.y, st.pz - pj.z, v, vj, lam_p + 3 * r, dv, on);
+                    v[0] += dv[0]; v[1] += dv[1]; v[2] += dv[2];
+                    worst = fmaxf(worst, wr);
+                }
+            }
+            if (alive) ++n_sweeps;
+            for (int o = G >> 1; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(kFull32, worst, o));
+            alive = alive && !(worst < cp.solver_tol);
+            if (!__any_sync(kFull32, alive)) break;
+        }
+        st.vx = v[0]; st.vy = v[1]; st.vz = v[2];
+        st.wx = R[0] * wb[0] + R[1] * wb[1] + R[2] * wb[2];
+        st.wy = R[3] * wb[0] + R[4] * wb[1] + R[5] * wb[2];
+        st.wz = R[6] * wb[0] + R[7] * wb[1] + R[8] * wb[2];
+        if ((lam_g[0] + lam_g[1]) + (lam_g[2] + lam_g[3]) > 0.f) ++n_ground;
+        for (unsigned m = ract; m; m &= m - 1u)
+            if (lam_p[3 * (__ffs(m) - 1)] > 0.f) ++n_agent_rows;
+    }
+    integrate(c, d, st);
+    if (!agent_finite(st)) status |= MRS_STATUS_NONFINITE;
+    // ---- observation + state
+    if (a.X0 && valid) write_X(a.X0 - (long long)t * a.xstride, c.state_layout, s, st);
+    if (a.A0) {
+        float* Arow = a.A0 - (long long)t * a.astride + (size_t)s * N;
+        __syncwarp();
+        wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
+        __syncwarp();
+        if (valid) {
+            for (int j = 0; j < N; ++j) {
+                const float4 pj = wpos[gb + j];
+                const float hit = d.comm_inf ? 1.f : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
+                MRS_TAPE_ST(Arow + j, (j == ai) ? 0.f : hit);
+            }
+        }
+        __syncwarp();
+    }
+    if (!valid) { status = 0; n_agent_rows = 0; n_ground = 0; n_sweeps = 0; }
+    {
+        const unsigned any_status = __reduce_or_sync(kFull32, status);
+        const unsigned sum_rows = __reduce_add_sync(kFull32, n_agent_rows);
+        const unsigned sum_gnd = __reduce_add_sync(kFull32, n_ground);
+        const unsigned max_sw = __reduce_max_sync(kFull32, n_sweeps);
+        if (lane == 0) {
+            if (any_status) atomicOr(&sh_events[0], any_status);
+            if (sum_rows) atomicAdd(&sh_events[1], sum_rows);
+            if (sum_gnd) atomicAdd(&sh_events[2], sum_gnd);
+            if (any_status & MRS_STATUS_NONFINITE) atomicAdd(&sh_events[3], 1u);
+            if (any_status & MRS_STATUS_NAN_ACTION) atomicAdd(&sh_events[4], 1u);
+            if (max_sw) atomicAdd(&sh_events[6], max_sw);
+        }
+    }
+  }
+    if (valid) {
+        store_agent(b.state, S, s, st);
+        store_ctrl<MODE>(b.ctrl, S, s, k);
+    }
+}
+
 // dynamic shared memory of one warp of the group kernel: pair tile (+ prefetch stage for full chunks)
 template <int MODE, int GT> __host__ __device__ constexpr int group_warp_smem_bytes() {
-    return 1024 + ((MRS_PREFETCH && GT != 0) ? mode_stage_floats<MODE>() * 4 : 0);
+    return 512 + ((MRS_PREFETCH && GT != 0) ? mode_stage_floats<MODE>() * 4 : 0);
 }
 
 //
@@ -71,24 +239,26 @@ template <int MODE, int GT> __host__ __device__ constexpr int group_warp_smem_by
 // scheduler starts CTAs in index order on whichever SM has just become free -- takes the i-th finished range:
 // ranges flow from launch to launch in completion order and an SM never waits for another SM.
 //   sync[0]               epoch: bumped by the head of every chain
-//   sync[1 + p]           ranges published so far by launches of parity p of the current chain
-//   sync[8 + 1024 p + i]  i-th range published by the newest launch of parity p: epoch << 32 | (position + 1) << 16 | range
+//   sync[8 + q]           ranges published so far by the launch that owns queue q = position & 7
+//   sync[16 + 1024 q + i] i-th range published by that launch: epoch << 32 | (position + 1) << 16 | range
 // role 1 (head, position 0): waits for the whole previous grid (griddepcontrol.wait), resets the counters, bumps
 //   the epoch, takes range = blockIdx, publishes.
-// role 2 (link, position t): does NOT wait for the previous grid; CTA i waits for entry i of launch t - 1.
+// role 2 (link, position t): does NOT wait for the previous grid; CTA i waits for entry i of launch t - 1; its
+//   it also waits for the LAST entry of launch t - 3 (bounds the launches in flight behind a slow CTA), and its
+//   first CTA clears the counter of queue (t + 4) & 7 -- last used by launch t - 4, next by launch t + 4.
 // All state / PID / action reads of these kernels are cp.async.cg (L2); the publishing thread fences after the
 // CTA barrier that follows the state stores.  A link that waits longer than 2 s falls back to the grid-wide wait
 // and raises MRS_STATUS_SYNC_TIMEOUT.
-constexpr int kSyncQueue = 8, kSyncQueueLen = 1024;
+constexpr int kSyncCount = 8, kSyncQueue = 16, kSyncQueueLen = 1024, kSyncQueues = 8;
 #ifndef MRS_DEFAULT_CPS
 #define MRS_DEFAULT_CPS 4          // CTAs per SM of the single-step SM-filling shape (each with 1 / CPS of the SM's warps)
 #endif
-static_assert(kSyncQueue + 2 * kSyncQueueLen <= MRS_SYNC_WORDS, "sync buffer layout");
+static_assert(kSyncQueue + kSyncQueues * kSyncQueueLen <= MRS_SYNC_WORDS, "sync buffer layout");
 
 template <int MODE, int GT, int WPB, bool BAKED, bool MANY>
 __global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : (4 * ModeTraits<MODE>::minb) / WPB)
-step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant__ Derived d_in, const MrsBuffers b,
-                  const StepArgs a) {
+step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant__ Derived d_in,
+                  const __grid_constant__ MrsBuffers b, const __grid_constant__ StepArgs a) {
     MrsConfig c_bk;
     Derived d_bk;
     if constexpr (BAKED) baked_fill(c_bk, d_bk, c_in, d_in);
@@ -98,15 +268,15 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     constexpr bool kFull = GT != 0;
     constexpr bool kStage = MRS_PREFETCH && kFull;
     // shared memory, one contiguous region per warp so that every address is one per-warp base plus an
-    // immediate: [32 positions | 32 velocities] (the pair tile, 1 KB) [prefetch stage]
+    // immediate: [32 positions] (the pair tile, 512 B) [prefetch stage]
     constexpr int kWarpBytes = group_warp_smem_bytes<MODE, GT>();
     __shared__ int sh_counter, sh_hi, sh_range;
-    __shared__ unsigned sh_events[5];       // CTA-level status word + the four statistics counters
+    __shared__ unsigned sh_epoch;
+    __shared__ unsigned sh_events[7];       // CTA-level status word + the six statistics counters
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + wib * kWarpBytes;
     float4* wpos = reinterpret_cast<float4*>(wbase);
-    float4* wvel = wpos + 32;
-    float* stage = reinterpret_cast<float*>(wbase + 1024);
+    float* stage = reinterpret_cast<float*>(wbase + 512);
     const int G = GT ? GT : a.G;
     const int N = GT ? GT : c.N;
     const int E = c.E;
@@ -126,16 +296,26 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     constexpr bool kHand = kLocal && MRS_PREFETCH && GT != 0 && !MANY;
     const int T = MANY ? a.T : 1;
     const int gw = blockIdx.x * WPB + wib;
-    if (threadIdx.x < 5) sh_events[threadIdx.x] = 0u;
+    if (threadIdx.x < 7) sh_events[threadIdx.x] = 0u;
     const int role = kHand ? a.role : 0;
-    unsigned epoch = 0;             // thread 0 only
     if (role == 2) {
         asm volatile("griddepcontrol.launch_dependents;");
         if (threadIdx.x == 0) {
-            const unsigned long long* q = b.sync + kSyncQueue + ((a.seq - 1) & 1) * kSyncQueueLen + blockIdx.x;
-            unsigned long long e = ld_acquire_gpu_u64(q), t0 = 0;
-            epoch = (unsigned)ld_acquire_gpu_u64(b.sync);
-            while ((e >> 16) != (((unsigned long long)epoch << 16) | (unsigned)a.seq)) {
+            // my range: entry blockIdx of the previous launch.  And a bound on the launches in flight: a CTA that
+            // takes the contact path can run many times longer than a step, and the launches behind it would
+            // pile up (each with one CTA spinning for the straggler's range) until they lap the eight queues --
+            // so a launch also waits until the launch three positions back has published ALL its ranges (its
+            // last entry exists).  Then at most the queues of positions t-2 .. t+1 are live.
+            const unsigned long long* q = b.sync + kSyncQueue + ((a.seq - 1) & (kSyncQueues - 1)) * kSyncQueueLen + blockIdx.x;
+            const unsigned long long* q3 = b.sync + kSyncQueue + ((a.seq - 3) & (kSyncQueues - 1)) * kSyncQueueLen + (gridDim.x - 1);
+            const bool bound = a.seq >= 3;
+            unsigned long long e = ld_acquire_gpu_u64(q), e3 = bound ? ld_acquire_gpu_u64(q3) : 0ull, t0 = 0;
+            unsigned epoch = (unsigned)ld_acquire_gpu_u64(b.sync);
+            auto pending = [&]() {
+                const unsigned long long tag = (unsigned long long)epoch << 16;
+                return (e >> 16) != (tag | (unsigned)a.seq) || (bound && (e3 >> 16) != (tag | (unsigned)(a.seq - 2)));
+            };
+            while (pending()) {
                 if (t0 == 0) t0 = global_ns();
                 else if (global_ns() - t0 > 2000000000ull) {       // 2 s: the chain is broken -- fall back, flag it
                     if (b.status) atomicOr(b.status, MRS_STATUS_SYNC_TIMEOUT);
@@ -144,9 +324,13 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                     break;
                 }
                 e = ld_acquire_gpu_u64(q);
+                if (bound) e3 = ld_acquire_gpu_u64(q3);
                 epoch = (unsigned)ld_acquire_gpu_u64(b.sync);
             }
+            // the queue four positions ahead was last used four positions back: that launch is complete now
+            if (blockIdx.x == 0) atomicExch(b.sync + kSyncCount + ((a.seq + 4) & (kSyncQueues - 1)), 0ull);
             sh_range = (int)(e & 0xffffull);
+            sh_epoch = epoch;               // (shared memory: the tag of this CTA's own entry, needed at the very end)
         }
     } else {
         if (role == 0) asm volatile("griddepcontrol.launch_dependents;");
@@ -155,8 +339,8 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
         if (role == 1) {
             // everything before this launch is complete: start a new chain, then let the first link in
             if (blockIdx.x == 0 && threadIdx.x == 0) {
-                atomicExch(b.sync + 1, 0ull);
-                atomicExch(b.sync + 2, 0ull);
+#pragma unroll
+                for (int q = 0; q < kSyncQueues; ++q) atomicExch(b.sync + kSyncCount + q, 0ull);
                 atomicAdd(b.sync, 1ull);
                 __threadfence();
             }
@@ -253,7 +437,21 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
         if (chunk_next >= a.nchunks) chunk_next = -1;
     }
     if (kStage && chunk >= 0) prefetch(chunk);
-    while (chunk >= 0) {
+    // A chunk that needs the contact path is parked here and processed by the out-of-line call at the top of the
+    // next iteration, where nothing but the loop bookkeeping is live (a call in the middle of the step would make
+    // the register allocator keep the step's working set in memory on the fast path too).
+    int slow_chunk = -1, slow_t = 0;
+    while (chunk >= 0 || slow_chunk >= 0) {
+#ifndef MRS_EXP_NOCALL
+        if (slow_chunk >= 0) {
+            __syncwarp();
+            chunk_step_contact<MODE>(&c_in, &d_in, &b, &a, GT ? GT : a.G, slow_chunk, slow_t, T, wpos, sh_events);
+            slow_chunk = -1;
+            continue;
+        }
+#else
+        if (slow_chunk >= 0) { slow_chunk = -1; continue; }
+#endif
         const int ticket = (kLocal && chunk_next >= 0) ? draw() : -1;   // the chunk after next; warp-uniform condition
         // kFull: the chunk is 32 consecutive valid slots; else lanes >= N of a group (and envs >= E) idle
         const int e = chunk * gpw + (lane / G);
@@ -310,6 +508,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             if (valid) (void)load_action<MODE>(a.actions, (size_t)s, tmp);
             act0 = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
         }
+        bool state_stored = false;      // the contact path of a single-step launch stores the state itself
         for (int t = 0; t < T; ++t, Xs -= a.xstride, As -= a.astride) {
             // per-step event word: the registers behind it live only as long as the step needs them
             unsigned status = 0;
@@ -330,20 +529,18 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
 #else
             {
 #endif
-            float R[9];
-            quat_to_mat(st, R);
-            action_to_rpm<MODE>(c, c_in.quad, d, st, R, act, k, rpm);
-            if (b.rpm && MODE != MRS_NO_ACTION && valid) {       // optional Quadcopter.speeds mirror
-#pragma unroll
-                for (int i = 0; i < 4; ++i) *plane_ptr(b.rpm + s, S, i) = rpm[i];
-            }
-
+            // ---- contact (rare): a warp with an agent near the ground or near another agent hands the whole chunk
+            // to the contact path (chunk_step_contact), which redoes this step from the state in global memory with
+            // the sequential-impulse solver; the fast path below carries no contact code at all.  Ground proximity
+            // is known at once, agent proximity after pair pass 1.
+            bool touch = __any_sync(kFull32, valid && ph.ground_contact && st.pz < d.gnd_skip_z);
+            float dw = 0.f;
+            bool near = false;
+            if (!touch) {
             // ---- pair pass 1: downwash + contact proximity on the pre-step positions
             __syncwarp();
             wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
             __syncwarp();
-            float dw = 0.f;
-            bool near = false;
 #ifndef MRS_PAIR_ONCE
 #define MRS_PAIR_ONCE 1
 #endif
@@ -388,30 +585,26 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                     }
                 }
             }
-            apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
-
-            // ---- pair pass 2 (rare): sphere-sphere contact on the unconstrained velocities
-            if (pair_contact && __any_sync(kFull32, near && valid)) {
-                wvel[lane] = make_float4(st.vx, st.vy, st.vz, 0.f);
-                __syncwarp();
-                if (near) {
-                    // st.p still is the pre-step position (integrate comes later)
-                    const float p0x = st.px, p0y = st.py, p0z = st.pz;
-                    float acc[3] = {0.f, 0.f, 0.f};
-                    for (int r = 1; r < G; ++r) {
-                        const int j = ai ^ r;
-                        if (GT || j < N) {
-                            const float4 pj = wpos[gb + j];
-                            const float4 vj = wvel[gb + j];
-                            if (agent_contact_pair(ph, d, p0x - pj.x, p0y - pj.y, p0z - pj.z, st.vx - vj.x,
-                                                   st.vy - vj.y, st.vz - vj.z, acc))
-                                ++n_agent_rows;
-                        }
-                    }
-                    st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
-                }
+            touch = __any_sync(kFull32, valid && pair_contact && near);
             }
-            if (ph.ground_contact && ground_contact(ph, d, st)) ++n_ground;
+            if (touch) {
+                if (MANY && valid) {         // the registers hold the newest state: make it visible to the contact path
+                    store_agent(b.state, S, s, st);
+                    store_ctrl<MODE>(b.ctrl, S, s, k);
+                }
+                slow_chunk = chunk;          // steps t .. T-1 of this chunk run at the top of the next iteration
+                slow_t = t;
+                state_stored = true;
+                break;
+            }
+            float R[9];
+            quat_to_mat(st, R);
+            action_to_rpm<MODE>(c, c_in.quad, d, st, R, act, k, rpm);
+            if (b.rpm && MODE != MRS_NO_ACTION && valid) {       // optional Quadcopter.speeds mirror
+#pragma unroll
+                for (int i = 0; i < 4; ++i) *plane_ptr(b.rpm + s, S, i) = rpm[i];
+            }
+            apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
             integrate(c, d, st);
             if (!agent_finite(st)) status |= MRS_STATUS_NONFINITE;
 
@@ -522,7 +715,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             }
         }
 
-        if (valid) {
+        if (valid && !state_stored) {
             float* p0 = b.state + s;
             *plane_ptr(p0, S, 0) = st.px; *plane_ptr(p0, S, 1) = st.py; *plane_ptr(p0, S, 2) = st.pz;
             *plane_ptr(p0, S, 3) = st.qx; *plane_ptr(p0, S, 4) = st.qy; *plane_ptr(p0, S, 5) = st.qz;
@@ -549,13 +742,16 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             if (sh_events[2]) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)sh_events[2]);
             if (sh_events[3]) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)sh_events[3]);
             if (sh_events[4]) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, (unsigned long long)sh_events[4]);
+            if (sh_events[5]) atomicAdd(b.stats + MRS_STAT_CONTACT_CHUNKS, (unsigned long long)sh_events[5]);
+            if (sh_events[6]) atomicAdd(b.stats + MRS_STAT_SOLVER_SWEEPS, (unsigned long long)sh_events[6]);
         }
         if (role != 0) {
             // publish the finished range (the CTA barrier above ordered every thread's state stores before this fence)
             __threadfence();
-            if (role == 1) epoch = (unsigned)ld_acquire_gpu_u64(b.sync);
-            const unsigned long long j = atomicAdd(b.sync + 1 + (a.seq & 1), 1ull) - (unsigned long long)gridDim.x * (unsigned)(a.seq >> 1);
-            st_release_gpu_u64(b.sync + kSyncQueue + (a.seq & 1) * kSyncQueueLen + (int)(j & (kSyncQueueLen - 1)),
+            const unsigned epoch = (role == 1) ? (unsigned)ld_acquire_gpu_u64(b.sync) : sh_epoch;
+            const int q = a.seq & (kSyncQueues - 1);
+            const unsigned long long j = atomicAdd(b.sync + kSyncCount + q, 1ull);
+            st_release_gpu_u64(b.sync + kSyncQueue + q * kSyncQueueLen + (int)(j & (kSyncQueueLen - 1)),
                                ((unsigned long long)epoch << 32) | ((unsigned long long)(a.seq + 1) << 16) | (unsigned)sh_range);
         }
     }
@@ -845,81 +1041,6 @@ agent_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ De
     agent_pre<MODE>(c, d, b, actions, S, s, dw, fl != 0.f);
 }
 
-template <int LPA>
-__global__ void __launch_bounds__(kBlock)
-step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int slot) {
-    const int N = c.N;
-    const unsigned S = (unsigned)c.E * (unsigned)N;
-    const unsigned gid = (blockIdx.x * kBlock + threadIdx.x) / LPA;
-    const int l = threadIdx.x & (LPA - 1);
-    const bool valid = gid < S;
-    const unsigned s = valid ? gid : 0u;
-    const unsigned env0 = (s / (unsigned)N) * (unsigned)N;
-    const int ai = (int)(s - env0);
-    const MrsPhysicsParams& ph = c.phys;
-    const float* __restrict__ sc = b.scratch;
-    Agent st;
-    st.px = sc[3 * (size_t)S + s]; st.py = sc[4 * (size_t)S + s]; st.pz = sc[5 * (size_t)S + s];
-    st.vx = sc[0 * (size_t)S + s]; st.vy = sc[1 * (size_t)S + s]; st.vz = sc[2 * (size_t)S + s];
-    const bool near = valid && sc[6 * (size_t)S + s] != 0.f;       // uniform over the lane group
-    float acc[3] = {0.f, 0.f, 0.f};
-    unsigned rows = 0;
-    if (near) {
-        const float* __restrict__ qx = sc + 3 * (size_t)S + env0;
-        const float* __restrict__ qy = sc + 4 * (size_t)S + env0;
-        const float* __restrict__ qz = sc + 5 * (size_t)S + env0;
-        for (int j0 = l; j0 < N; j0 += 4 * LPA) {     // 4 independent partner loads in flight per lane
-            float dx[4], dy[4], dz[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u * LPA;
-                const bool ok = j < N && j != ai;
-                const int jj = ok ? j : ai;
-                dx[u] = st.px - qx[jj]; dy[u] = st.py - qy[jj]; dz[u] = st.pz - qz[jj];
-                if (!ok) dx[u] = 1.0e18f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u] < d.lim2) {
-                    const int j = j0 + u * LPA;
-                    const float vjx = sc[0 * (size_t)S + env0 + j], vjy = sc[1 * (size_t)S + env0 + j],
-                                vjz = sc[2 * (size_t)S + env0 + j];
-                    if (agent_contact_pair(ph, d, dx[u], dy[u], dz[u], st.vx - vjx, st.vy - vjy, st.vz - vjz, acc)) ++rows;
-                }
-            }
-        }
-    }
-    // every lane of the warp takes part in the shuffles (groups without contact add zeros)
-    acc[0] = group_sum<LPA>(acc[0]); acc[1] = group_sum<LPA>(acc[1]); acc[2] = group_sum<LPA>(acc[2]);
-    rows = (unsigned)group_sum<LPA>((float)rows);
-    const bool lead = (l == 0) && valid;
-    unsigned gnd = 0, bad = 0;
-    if (lead) {
-        st.vx += acc[0]; st.vy += acc[1]; st.vz += acc[2];
-        st.qx = b.state[3 * (size_t)S + s]; st.qy = b.state[4 * (size_t)S + s]; st.qz = b.state[5 * (size_t)S + s];
-        st.qw = b.state[6 * (size_t)S + s];
-        st.wx = b.state[10 * (size_t)S + s]; st.wy = b.state[11 * (size_t)S + s]; st.wz = b.state[12 * (size_t)S + s];
-        if (ph.ground_contact && ground_contact(ph, d, st)) gnd = 1;
-        integrate(c, d, st);
-        store_agent(b.state, S, s, st);
-        if (b.X_tape && c.state_layout != MRS_X_NONE)
-            write_X(b.X_tape + (size_t)slot * S * state_dim(c.state_layout), c.state_layout, s, st);
-        bad = agent_finite(st) ? 0u : 1u;
-    }
-    // statistics: one warp reduction, then at most three global atomics per warp (not per agent)
-    const unsigned w_rows = __reduce_add_sync(kFull32, lead ? rows : 0u);
-    const unsigned w_gnd = __reduce_add_sync(kFull32, gnd);
-    const unsigned w_bad = __reduce_add_sync(kFull32, bad);
-    if ((threadIdx.x & 31) == 0) {
-        if (w_bad && b.status) atomicOr(b.status, MRS_STATUS_NONFINITE);
-        if (b.stats) {
-            if (w_rows) atomicAdd(b.stats + MRS_STAT_AGENT_CONTACTS, (unsigned long long)w_rows);
-            if (w_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)w_gnd);
-            if (w_bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)w_bad);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------ launch
 template <int MODE, int GT, int WPB, bool BAKED, bool MANY>
 static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
@@ -1003,12 +1124,11 @@ static int launch_group(const MrsConfig& c, const Derived& d, const MrsBuffers& 
     return launch_group_variant<MODE, GT, 4>(c, d, b, a, blocks, pdl, baked, st);
 }
 
-template <int MODE, int LPA, int LPB>
+template <int MODE, int LPA>
 static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     const size_t S = (size_t)c.E * c.N;
     constexpr int A = ModeTraits<MODE>::A;
     const unsigned blocks = (unsigned)((S * LPA + kBlock - 1) / kBlock);
-    const unsigned blocks_post = (unsigned)((S * LPB + kBlock - 1) / kBlock);
     SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
     int jw = 0, nsplit = 0;
     if (LPA > 32) pair_split(c.E, c.N, &jw, &nsplit);
@@ -1021,8 +1141,9 @@ static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffer
         } else {
             step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
         }
+        if (int rc = launch_contact_env(c, d, b, st)) return rc;
         if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
-        step_post_kernel<LPB><<<blocks_post, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
+        if (int rc = launch_step_post(c, d, b, a.slot_x - t, st)) return rc;
         if (b.A_tape) {
             cudaStream_t as = st;
             if (L) {
@@ -1050,8 +1171,9 @@ static int launch_mid(const MrsConfig& c, const Derived& d, const MrsBuffers& b,
     for (int t = 0; t < a.T; ++t) {
         const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
         step_mid_pre_kernel<MODE><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
+        if (int rc = launch_contact_env(c, d, b, st)) return rc;
         if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
-        step_post_kernel<1><<<blocks, kBlock, 0, st>>>(c, d, b, a.slot_x - t);
+        if (int rc = launch_step_post(c, d, b, a.slot_x - t, st)) return rc;
         if (b.A_tape) {
             cudaStream_t as = st;
             if (L) {
@@ -1077,8 +1199,8 @@ static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& 
     // the work once there are enough of them
     static const long long mid_min = env_int("MRS_B200_MID_MIN_AGENTS", 32768);
     if (c.N <= 128 && (long long)c.E * c.N >= mid_min) return launch_mid<MODE>(c, d, b, a, st);
-    if (c.N <= 128) return launch_wide_lpa<MODE, 8, 8>(c, d, b, a, st);
-    return launch_wide_lpa<MODE, 128, 32>(c, d, b, a, st);     // n-body tiles (pair_tile_kernel) + agent_pre_kernel
+    if (c.N <= 128) return launch_wide_lpa<MODE, 8>(c, d, b, a, st);
+    return launch_wide_lpa<MODE, 128>(c, d, b, a, st);     // n-body tiles (pair_tile_kernel) + agent_pre_kernel
 }
 
 static int pow2ceil(int n) {

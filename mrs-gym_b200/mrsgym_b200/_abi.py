@@ -11,12 +11,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MRS_B200_LIB') or os.path.join(_HERE, 'libmrs_b200.so')   # override: A/B builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 STATE_PLANES = 13
 CTRL_PLANES = 18
 STATS_SLOTS = 8
 SCRATCH_PLANES = 7
-SYNC_WORDS = 2056
+SYNC_WORDS = 8208
 
 # MrsActionType: the reference's ACTION_TYPE strings are Quadcopter method names
 # (/root/reference/mrsgym/Environment.py:92)
@@ -32,9 +32,10 @@ STATUS_NAN_ACTION = 1
 STATUS_NONFINITE = 2
 STATUS_COMM_TIMEOUT = 4
 STATUS_SYNC_TIMEOUT = 8
+STATUS_CONTACT_OVERFLOW = 16
 COMM_MAX_WORLD = 16
 COMM_HANDLE_BYTES = 64
-STAT_NAMES = ('agent_contact_rows', 'ground_contacts', 'nonfinite', 'nan_actions')
+STAT_NAMES = ('agent_contact_rows', 'ground_contacts', 'nonfinite', 'nan_actions', 'contact_chunks', 'solver_sweeps')
 
 f = C.c_float
 
@@ -62,7 +63,8 @@ class MrsPhysicsParams(C.Structure):
                 ('mu_ground', f), ('ground_z', f),
                 ('col_radius', f), ('col_halfheight', f), ('col_margin', f),
                 ('ground_contact', C.c_int), ('agent_contact', C.c_int),
-                ('agent_radius', f)]
+                ('agent_radius', f), ('contact_radius', f), ('mu_agent', f), ('solver_iters', C.c_int),
+                ('solver_tol', f)]
 
 
 class MrsConfig(C.Structure):

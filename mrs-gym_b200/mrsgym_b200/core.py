@@ -41,7 +41,7 @@ def shard_range(E_total: int, rank: int, world: int):
 
 class Swarm:
     def __init__(self, E: int, N: int, K: int = 0, action_type='set_target_vel', state_layout=_abi.X_POS_VEL,
-                 comm_range=float('inf'), dt=0.01, gravity=9.81, agent_radius=0.3, device='cuda',
+                 comm_range=float('inf'), dt=0.01, gravity=9.81, agent_radius=0.3, device='cuda', contact_radius=None,
                  tape_slots=None, want_A=True, custom_D=0, keep_rpm=False, ring=False):
         self.lib = _abi.lib()
         self.device = torch.device(device)
@@ -62,6 +62,8 @@ class Swarm:
         self.cfg.comm_range = float(comm_range)
         self.cfg.dt, self.cfg.gravity = float(dt), float(gravity)
         self.cfg.phys.agent_radius = float(agent_radius)
+        # the agent-agent contact sphere: AGENT_RADIUS unless told otherwise (0.06 = the cf2x collision cylinder)
+        self.cfg.phys.contact_radius = float(agent_radius if contact_radius is None else contact_radius)
         self.D = _abi.STATE_DIMS[state_layout] if state_layout != _abi.X_NONE else int(custom_D)
         if tape_slots:
             self.L = int(tape_slots)

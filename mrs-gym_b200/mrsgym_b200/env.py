@@ -147,6 +147,8 @@ class MRS:
         self.STATE_SIZE = 0
         self.ACTION_DIM = 0
         self.AGENT_RADIUS = 0.3
+        self.CONTACT_RADIUS = None   # agent-agent contact sphere; None = AGENT_RADIUS (0.06 = the cf2x collision hull)
+        self.SOLVER_ITERS = None     # contact solver sweeps; None = Bullet's 50
         self.COMM_RANGE = float('inf')
         self.RETURN_A = False
         self.RETURN_EVENTS = False
@@ -213,7 +215,8 @@ class MRS:
             custom_D = int(self._call_state_fn(probe).shape[-1])
         self.swarm = Swarm(self.N_ENVS, self.N_AGENTS, self.K_HOPS, self.ACTION_TYPE, layout, self.COMM_RANGE,
                            dt=self.sim.DT, gravity=self.sim.GRAVITY, agent_radius=self.AGENT_RADIUS,
-                           device=self.DEVICE, tape_slots=self.TAPE_SLOTS, want_A=True, custom_D=custom_D)
+                           device=self.DEVICE, tape_slots=self.TAPE_SLOTS, want_A=True, custom_D=custom_D,
+                           contact_radius=self.CONTACT_RADIUS)
         self.STATE_SIZE = self.swarm.D
         self.ACTION_DIM = self.swarm.action_dim
         self.env = Environment(self.swarm, squeeze=not self._batched)
@@ -234,6 +237,9 @@ class MRS:
         c = self.swarm.cfg
         c.comm_range = float(self.COMM_RANGE)
         c.phys.agent_radius = float(self.AGENT_RADIUS)
+        c.phys.contact_radius = float(self.AGENT_RADIUS if self.CONTACT_RADIUS is None else self.CONTACT_RADIUS)
+        if self.SOLVER_ITERS is not None:
+            c.phys.solver_iters = int(self.SOLVER_ITERS)
         c.dt, c.gravity = float(self.sim.DT), float(self.sim.GRAVITY)
 
     # ------------------------------------------------------------------ observation windows

@@ -20,10 +20,22 @@ algorithm from the bullet3 sources as recalled:
 
 PARITY UNPINNED for this file: the reference holds no tests / golden vectors
 and real PyBullet cannot be run here.  Every constant is a field of
-``PhysicsParams`` so a run with a real pybullet can correct it without code
-changes.  Contact is a deliberate simplification named by the north star
-(ground plane + AGENT_RADIUS sphere-sphere), specified here and mirrored
-exactly by the CUDA kernels.
+``PhysicsParams`` (loadable from the JSON that tools/pin_bullet.py writes when a real
+pybullet is importable) so a pinned run can correct it without code changes.
+
+Contact is a velocity-level sequential-impulse solver, restitution 0,
+Baumgarte push-out erp2, ``solver_iters`` Gauss-Seidel sweeps with early exit below
+``solver_tol``, mirrored row for row by the CUDA kernels:
+  * ground: the collision cylinder touches the ground box with up to four points of its lower
+    rim (Bullet keeps <= 4 manifold points); each point is a normal row applied AT the point, so a
+    tilted landing produces a righting torque; two Coulomb friction rows (world x, y) at the CoM,
+    each bounded by mu_ground * (sum of the agent's normal impulses);
+  * agent-agent: the north star's CONTACT_RADIUS sphere-sphere simplification of the hull
+    contact: central normal row + two Coulomb friction rows (mu_agent) on the CoM velocities (the
+    proxy sphere carries no rotational coupling);
+  * sweep order: all ground rows (point 0..3 normal, then friction x, y), then the pair rows in
+    round-robin-tournament order (round r pairs i with (2r - i) mod (M-1); rows of one round touch
+    disjoint bodies, so they can be processed in parallel without changing the result).
 
 All arrays are ``[..., 3]`` / ``[..., 4]`` (quaternion order xyzw, as PyBullet)
 with arbitrary leading batch dims; agent-agent contact couples the second to
@@ -110,9 +122,23 @@ class PhysicsParams:
     contact_margin: float = 0.02     # contact breaking threshold: speculative contacts
     mu_ground: float = 0.75          # plane 1.5 (plane.urdf:4-6) x link default 0.5
     ground_z: float = 0.5            # plane.urdf:21-26 box 30x30x1 centred at z=0
+    mu_agent: float = 0.25           # quad-quad: link default 0.5 x 0.5
     ground_contact: bool = True
     agent_contact: bool = True
-    agent_radius: float = 0.3        # MRS.AGENT_RADIUS (/root/reference/mrsgym/MRS.py:28)
+    agent_radius: float = 0.3        # MRS.AGENT_RADIUS (/root/reference/mrsgym/MRS.py:28): spawn separation
+    contact_radius: float = 0.3      # radius of the agent-agent contact sphere (north star: = AGENT_RADIUS;
+                                     # 0.06 gives the size of the reference's cf2x collision cylinder)
+    solver_iters: int = 50           # Bullet numSolverIterations
+    solver_tol: float = 1e-6         # early exit: largest change of a row's contact-point velocity in a sweep [m/s]
+
+    @classmethod
+    def from_json(cls, path):
+        """PhysicsParams from the JSON tools/pin_bullet.py writes (unknown keys are ignored)."""
+        import json
+        d = json.load(open(path))
+        d = d.get('PhysicsParams', d)
+        known = {f.name for f in dataclasses.fields(cls)}
+        return cls(**{k: v for k, v in d.items() if k in known})
 
     def inertia_diag(self) -> np.ndarray:
         hx = self.col_radius + self.inertia_margins * self.col_margin
@@ -186,53 +212,146 @@ def unconstrained_velocities(quat, vel, angvel, force_w, torque_w, P: PhysicsPar
     return v1, w1
 
 
-def _contact_rhs(dist, vn, P: PhysicsParams, dt: float):
-    """Target normal-velocity change of one contact row, after
-    btMultiBodyConstraintSolver::setupMultiBodyContactConstraint (restitution 0):
-    penetration = dist + slop; open gap -> may close it within the step,
-    penetrating -> Baumgarte push-out erp2*depth/dt.  Lower impulse limit 0."""
+def _contact_bias(dist, P: PhysicsParams, dt: float):
+    """Velocity bound b of a normal row (vn >= b after the solve), after
+    btMultiBodyConstraintSolver::setupMultiBodyContactConstraint with restitution 0:
+    penetration = dist + slop; an open gap may close within the step (b = -pen/dt < 0), a
+    penetrating one is pushed out Baumgarte style (b = -pen*erp2/dt > 0)."""
     pen = dist + P.slop
-    rhs = np.where(pen > 0.0, -vn - pen / dt, -vn - pen * P.erp2 / dt)
-    return np.maximum(rhs, 0.0)
+    return np.where(pen > 0.0, -pen / dt, -pen * P.erp2 / dt)
 
 
-def agent_contact_dv(pos, v1, P: PhysicsParams, dt: float):
-    """AGENT_RADIUS sphere-sphere contact (north star simplification of the quad-quad
-    hull contact).  One Jacobi pass over all pairs from the unconstrained velocities:
-    frictionless central impulse, equal masses => each body takes half of the row."""
+# lower-rim contact points of the collision cylinder in the body frame (unit radius / half height)
+RIM = np.array([[1.0, 0.0], [0.0, 1.0], [-1.0, 0.0], [0.0, -1.0]])
+
+
+def plane_space(n):
+    """btPlaneSpace1: two unit tangents p, q of the unit normal n ([..., 3])."""
+    nx, ny, nz = n[..., 0], n[..., 1], n[..., 2]
+    big = np.abs(nz) > 0.7071067811865475
+    with np.errstate(invalid='ignore', divide='ignore'):
+        a1 = ny * ny + nz * nz
+        k1 = 1.0 / np.sqrt(a1)
+        p1 = np.stack([np.zeros_like(nx), -nz * k1, ny * k1], axis=-1)
+        q1 = np.stack([a1 * k1, -nx * p1[..., 2], nx * p1[..., 1]], axis=-1)
+        a2 = nx * nx + ny * ny
+        k2 = 1.0 / np.sqrt(a2)
+        p2 = np.stack([-ny * k2, nx * k2, np.zeros_like(nx)], axis=-1)
+        q2 = np.stack([-nz * p2[..., 1], nz * p2[..., 0], a2 * k2], axis=-1)
+    return np.where(big[..., None], p1, p2), np.where(big[..., None], q1, q2)
+
+
+def tournament_partner(N):
+    """Round-robin tournament (circle method) over M = N rounded up to even: partner[r, i] for rounds
+    r = 0 .. M-2; i == partner means i sits out (odd N).  Every unordered pair meets exactly once."""
+    M = N + (N & 1)
+    if M < 2:
+        return np.zeros((0, N), dtype=np.int64)
+    part = np.empty((M - 1, M), dtype=np.int64)
+    for r in range(M - 1):
+        for i in range(M - 1):
+            j = (2 * r - i) % (M - 1)
+            part[r, i] = (M - 1) if j == i else j
+        part[r, M - 1] = r
+    part = part[:, :N].copy()
+    idx = np.arange(N)[None, :]
+    part = np.where(part >= N, idx, part)             # the dummy of an odd N: sit out
+    return part
+
+
+def solve_contacts(pos, quat, v1, w1, P: PhysicsParams, dt: float):
+    """Sequential-impulse contact solve on the unconstrained velocities (see the module
+    docstring for the row set and the sweep order).  Returns (v, w) world frame."""
+    lead = pos.shape[:-2]
     N = pos.shape[-2]
-    dp = pos[..., :, None, :] - pos[..., None, :, :]            # p_i - p_j
-    d = np.sqrt(np.sum(dp * dp, axis=-1))
-    dist = d - 2.0 * P.agent_radius
-    with np.errstate(invalid='ignore', divide='ignore'):
-        n = dp / d[..., None]
-    dv = v1[..., :, None, :] - v1[..., None, :, :]
-    vn = np.sum(dv * n, axis=-1)
-    active = (dist < P.contact_margin) & (d > 0.0) & ~np.eye(N, dtype=bool)
-    rhs = np.where(active, _contact_rhs(dist, np.where(active, vn, 0.0), P, dt), 0.0)
-    n = np.where(active[..., None], n, 0.0)
-    return 0.5 * np.sum(rhs[..., None] * n, axis=-2)
-
-
-def ground_contact(pos, quat, v, P: PhysicsParams, dt: float):
-    """Ground plane z = ground_z against the quad's collision cylinder (support extent
-    along world z, + one collision margin); impulse acts at the CoM (no torque);
-    isotropic Coulomb friction mu_ground on the tangential velocity."""
-    R22 = quat_to_mat(quat)[..., 2, 2]
-    ext = (P.col_radius * np.sqrt(np.maximum(1.0 - R22 * R22, 0.0))
-           + P.col_halfheight * np.abs(R22) + P.col_margin)
-    dist = pos[..., 2] - ext - P.ground_z
-    active = dist < P.contact_margin
-    vn = v[..., 2]
-    jn = np.where(active, _contact_rhs(dist, vn, P, dt), 0.0)    # per unit mass
-    vt = v[..., :2]
-    vt_n = np.sqrt(np.sum(vt * vt, axis=-1))
-    with np.errstate(invalid='ignore', divide='ignore'):
-        scale = np.where(vt_n > 0.0, np.minimum(vt_n, P.mu_ground * jn) / vt_n, 0.0)
-    out = v.copy()
-    out[..., 2] = vn + jn
-    out[..., :2] = vt - vt * scale[..., None]
-    return out
+    pos = pos.reshape(-1, N, 3)
+    quat = quat.reshape(-1, N, 4)
+    v = np.array(v1, np.float64).reshape(-1, N, 3)
+    w = np.array(w1, np.float64).reshape(-1, N, 3)
+    E = pos.shape[0]
+    im = 1.0 / P.mass
+    invI = 1.0 / P.inertia_diag()
+    R = quat_to_mat(quat)
+    wb = matTvec(R, w)                                     # body-frame angular velocity during the solve
+    # ---- ground rows: four lower-rim points (the face that looks down)
+    g_act = np.zeros((E, N, 4), dtype=bool)
+    if P.ground_contact:
+        sgn = np.where(R[..., 2, 2] >= 0.0, 1.0, -1.0)
+        c = np.empty((E, N, 4, 3))                         # body-frame contact points
+        c[..., 0] = P.col_radius * RIM[:, 0]
+        c[..., 1] = P.col_radius * RIM[:, 1]
+        c[..., 2] = (-P.col_halfheight * sgn)[..., None]
+        nb = R[..., 2, :]                                  # world z in the body frame (row 2 of R)
+        zoff = np.einsum('enk,enpk->enp', nb, c)           # height of the point above the CoM
+        dist = pos[..., 2, None] + zoff - P.col_margin - P.ground_z
+        g_act = dist < P.contact_margin
+        g_bias = _contact_bias(dist, P, dt)
+        g_a = np.cross(c, nb[..., None, :])                # (c x n)_body
+        g_K = im + np.sum(g_a * g_a * invI, axis=-1)
+        g_lam = np.zeros((E, N, 4))
+        f_lam = np.zeros((E, N, 2))
+    # ---- pair rows
+    part = tournament_partner(N) if (P.agent_contact and N > 1) else np.zeros((0, N), dtype=np.int64)
+    rounds = []
+    for r in range(part.shape[0]):
+        pr = part[r]
+        lo = np.nonzero(pr > np.arange(N))[0]              # the lower index of each pair of the round
+        hi = pr[lo]
+        d = pos[:, lo] - pos[:, hi]
+        dd = np.sqrt(np.sum(d * d, axis=-1))
+        act = (dd - 2.0 * P.contact_radius < P.contact_margin) & (dd > 0.0)
+        if not act.any():
+            continue
+        with np.errstate(invalid='ignore', divide='ignore'):
+            n = np.where(act[..., None], d / dd[..., None], np.array([0.0, 0.0, 1.0]))
+        t1, t2 = plane_space(n)
+        rounds.append(dict(lo=lo, hi=hi, act=act, n=n, t1=t1, t2=t2,
+                           bias=_contact_bias(dd - 2.0 * P.contact_radius, P, dt),
+                           lam=np.zeros(act.shape), lt1=np.zeros(act.shape), lt2=np.zeros(act.shape)))
+    if not (g_act.any() or rounds):
+        return np.array(v1, np.float64).reshape(lead + (N, 3)), np.array(w1, np.float64).reshape(lead + (N, 3))
+    alive = np.ones(E, dtype=bool)                         # envs that have not converged yet
+    for it in range(int(P.solver_iters)):
+        worst = np.zeros(E)
+        am = alive[:, None]
+        if P.ground_contact:
+            for p in range(4):
+                a = g_a[..., p, :]
+                vn = v[..., 2] + np.sum(a * wb, axis=-1)
+                lam_new = np.maximum(g_lam[..., p] + (g_bias[..., p] - vn) / g_K[..., p], 0.0)
+                dl = np.where(g_act[..., p] & am, lam_new - g_lam[..., p], 0.0)
+                g_lam[..., p] += dl
+                v[..., 2] += dl * im
+                wb += (a * invI) * dl[..., None]
+                worst = np.maximum(worst, np.max(np.abs(dl) * g_K[..., p], axis=-1))
+            lim = P.mu_ground * np.sum(g_lam, axis=-1)
+            for k in range(2):
+                lam_new = np.clip(f_lam[..., k] - v[..., k] / im, -lim, lim)
+                dl = np.where(am, lam_new - f_lam[..., k], 0.0)
+                f_lam[..., k] += dl
+                v[..., k] += dl * im
+                worst = np.maximum(worst, np.max(np.abs(dl) * im, axis=-1))
+        for rd in rounds:
+            lo, hi, act = rd['lo'], rd['hi'], rd['act'] & am
+            for key, lkey in (('n', 'lam'), ('t1', 'lt1'), ('t2', 'lt2')):
+                u = rd[key]
+                vr = np.sum(u * (v[:, lo] - v[:, hi]), axis=-1)
+                if key == 'n':
+                    lam_new = np.maximum(rd['lam'] + (rd['bias'] - vr) / (2.0 * im), 0.0)
+                else:
+                    lim = P.mu_agent * rd['lam']
+                    lam_new = np.clip(rd[lkey] - vr / (2.0 * im), -lim, lim)
+                dl = np.where(act, lam_new - rd[lkey], 0.0)
+                rd[lkey] = rd[lkey] + dl
+                v[:, lo] += u * (dl * im)[..., None]
+                v[:, hi] -= u * (dl * im)[..., None]
+                if dl.shape[1]:
+                    worst = np.maximum(worst, np.max(np.abs(dl) * 2.0 * im, axis=-1))
+        alive = alive & ~(worst < P.solver_tol)
+        if not alive.any():
+            break
+    w = matvec(R, wb)
+    return v.reshape(lead + (N, 3)), w.reshape(lead + (N, 3))
 
 
 def integrate_positions(pos, quat, v, w, P: PhysicsParams, dt: float):
@@ -257,9 +376,7 @@ def bullet_step(pos, quat, vel, angvel, force_w, torque_w, P: PhysicsParams,
     """One ``stepSimulation`` (numSubSteps=0).  Inputs float64, world frame; force/torque
     are the summed external wrench about the CoM.  Returns (pos, quat, vel, angvel)."""
     v1, w1 = unconstrained_velocities(quat, vel, angvel, force_w, torque_w, P, dt, gravity)
-    if P.agent_contact and pos.shape[-2] > 1:
-        v1 = v1 + agent_contact_dv(pos, v1, P, dt)
-    if P.ground_contact:
-        v1 = ground_contact(pos, quat, v1, P, dt)
+    if P.ground_contact or P.agent_contact:
+        v1, w1 = solve_contacts(pos, quat, v1, w1, P, dt)
     pos1, q1 = integrate_positions(pos, quat, v1, w1, P, dt)
     return pos1, q1, v1, w1

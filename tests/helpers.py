@@ -76,6 +76,7 @@ def read_state(swarm):
 def make_spec(E, N, mode, K, comm_range, st, agent_radius=0.3, dt=0.01, **phys):
     from oracle import spec
     from oracle import bullet_model as bm
+    phys.setdefault('contact_radius', agent_radius)
     P = bm.PhysicsParams(agent_radius=agent_radius, **phys)
     env = spec.SpecEnv(E, N, mode, K=K, comm_range=comm_range, dt=dt, phys=P)
     env.set_state(pos=st['pos'].astype(np.float64), quat=st['quat'].astype(np.float64),
