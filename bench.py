@@ -122,6 +122,54 @@ def cpu_port_throughput(wname, procs, E_per_proc, T, seed=4321, warmup=1):
     return total / max(walls), max(walls), time.perf_counter() - t0
 
 
+def _verbatim_worker(args):
+    """One process = one reference MRS env (the reference holds one global PyBullet client), stepped verbatim."""
+    wname, T, seed = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from oracle import ref_runner
+    w = WORKLOADS[wname]
+    mrsgym, fake = ref_runner.load_reference()
+    N = min(w['N'], 32)
+    rng = np.random.default_rng(seed)
+    env = ref_runner.make_env(mrsgym, fake, N, w['mode'] if w['mode'] != 'set_force' else 'set_target_accel', K=w['K'],
+                              comm_range=w['R'])
+    adim = 4 if w['mode'] in ('set_speeds', 'set_control') else 3
+    if w['mode'] == 'set_speeds':
+        acts = (HOVER * (1 + 0.05 * rng.standard_normal((T + 1, N, adim)))).astype(np.float32)
+    elif w['mode'] == 'set_control':
+        acts = np.concatenate([9.81 + rng.uniform(-1, 1, (T + 1, N, 1)), rng.uniform(-1, 1, (T + 1, N, 3))], -1).astype(np.float32)
+    else:
+        acts = rng.normal(0, 0.3, (T + 1, N, adim)).astype(np.float32)
+    env.step(torch.tensor(acts[0]))
+    t0 = time.perf_counter()
+    for t in range(T):
+        env.step(torch.tensor(acts[1 + t]))
+    return time.perf_counter() - t0, N
+
+
+def cpu_verbatim_throughput(wname, procs, T=10):
+    """The reference's own Python, imported where it lies and run verbatim on the oracle's fake pybullet backend
+    (BASELINE.md 4.2): one env per process.  None when no reference tree is present (the GPU box has none)."""
+    try:
+        from oracle import ref_runner
+        if ref_runner.reference_root() is None:
+            return None
+        ctx = mp.get_context('spawn')
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_verbatim_worker, [(wname, T, 99 + i) for i in range(procs)])
+        wall = max(r[0] for r in res)
+        N = res[0][1]
+        return {'value': procs * N * T / wall, 'unit': 'agent-steps/s', 'cores': procs,
+                'kind': 'reference python + restated Bullet (oracle/fake_pybullet; PyBullet itself is not installable)',
+                'sample': '%d processes x 1 env x %d agents x %d steps, the reference imported from %s'
+                          % (procs, N, T, ref_runner.reference_root())}
+    except Exception as exc:                    # the verbatim leg is a courtesy: never take the bench line down
+        return {'unavailable': '%s: %s' % (type(exc).__name__, exc)}
+
+
 def cpu_sample_sizes(wname):
     w = WORKLOADS[wname]
     if w['N'] >= 1024:
@@ -247,14 +295,16 @@ def run_gpu(args):
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- headline: device-resident inputs, graph replays
+    # ---- headline: device-resident inputs, graph replays.
+    # Every timed region is a defined stretch of ONE rollout: the bench's start state is uploaded again, the warm-up
+    # steps follow, then the timed steps.  The synthetic C5 swarm -- open-loop rotor speeds with 5 % noise -- tumbles
+    # into itself after ~60 steps and lies on the ground after ~200 (SURVEY.md 8d workload), so "the step" would
+    # otherwise depend on how much ran before it; with the driver's protocol the region is steps 21-40, free flight.
+    # The contact-dominated regime of the same swarm is reported separately (`contact_regime`).
+    if not os.environ.get('BENCH_NO_REUPLOAD'):
+        H.upload_state(sw, st)
     for _ in range(max(1, -(-warmup // T))):
         roll.replay()
-    # Every timed region starts from the bench's start state (uploaded again after the warm-up): the synthetic C5
-    # swarm -- open-loop rotor speeds with 5 % noise -- tumbles into itself within ~70 steps and is on the ground
-    # after ~200 (SURVEY.md 8d workload), so "the step" would otherwise depend on how many warm-up steps came
-    # first.  The contact-dominated regime of the same swarm is reported separately (`contact_regime`).
-    H.upload_state(sw, st)
     sw.stats.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(physical_gpu_index(local))
@@ -453,6 +503,9 @@ def run_gpu(args):
         out['cpu_baseline'] = {'value': v, 'unit': 'agent-steps/s', 'cores': procs, 'kind': 'port',
                                'sample': '%d processes x %d envs x %d agents x %d steps of the same workload '
                                          '(oracle/spec.py, numpy float64); %.1f s' % (procs, Ep, w['N'], Tc, total)}
+        verb = cpu_verbatim_throughput(args.workload, procs)
+        if verb is not None:
+            out['cpu_baseline_verbatim'] = verb
     emit(out)
 
 

@@ -10,7 +10,9 @@
  *     allocates or frees device memory), all work is ordered on the passed CUDA stream
  *     (a cudaStream_t passed as void*), no hidden synchronisation (except mrs_step_host);
  *   - int return: 0 = OK, <0 = MrsError (mrs_strerror); no C++ exceptions cross the ABI;
- *   - thread-safe for distinct buffer sets; one host thread per GPU.
+ *   - thread-safe for distinct buffer sets; one host thread per GPU: the calls that use the library's internal
+ *     side streams (mrs_step_many / mrs_rollout with N > 32, mrs_rollout_host) share one set of streams and events
+ *     per device and must not run concurrently on one device.
  *   - there is NO CPU fallback: without a CUDA device every compute call returns
  *     MRS_ERR_CUDA.
  *
@@ -247,11 +249,12 @@ int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* act
  * radius xy_radius, re-drawn until all agents of an env are >= 2*AGENT_RADIUS apart (at most
  * max_rounds rounds; envs that did not converge are counted in *failed_envs, device u32, may be
  * NULL); yaw ~ U[yaw_lo, yaw_hi], roll = pitch = 0; velocities zero.  Counter-based RNG: the result
- * depends on (seed, env index) only.  N <= 32.
+ * depends on (seed, env_offset + env index) only -- env_offset is the global index of this shard's first env, so
+ * the ranks of a sharded job draw different environments from one seed.  N <= 32.
  * Replaces MRS.generate_start_pos / generate_start_ori / default_spawn_dist + the set_state of
  * MRS.reset (MRS.py:69-78,127-161,174-184) without the host round trip. */
 int mrs_spawn(const MrsConfig* cfg, const MrsBuffers* bufs, const unsigned char* env_mask,
-              unsigned long long seed, float z_lo, float z_hi, float xy_radius, float xy_sigma, float yaw_lo,
+              unsigned long long seed, unsigned long long env_offset, float z_lo, float z_hi, float xy_radius, float xy_sigma, float yaw_lo,
               float yaw_hi, int max_rounds, unsigned int* failed_envs, void* stream);
 
 /* Analytic sensors on the primitives of the 'simple' world (ground box top at ground_z, agents as

@@ -29,6 +29,7 @@ struct StepArgs {
     int G;                 // group width (power of two >= N), group path only
     int role;              // range hand-over between chained single-step launches: 0 none, 1 head, 2 link (mrs_step.cuh)
     int seq;               // position of the launch in its chain (0 = head)
+    int slow_slots;        // entries of a CTA's parked-chunk list (filled in by launch_group_wpb)
     int chunk_lo, nchunks; // this launch walks the warp-sized work items [chunk_lo, nchunks), group path only
 };
 

@@ -4,6 +4,8 @@
 //
 // Reference behaviour: /root/reference/mrsgym/MRS.py:240-277 and callees (see mrs_device.cuh);
 // Bullet step restated in oracle/bullet_model.py.  No CPU fallback exists in this library.
+#include <mutex>
+
 #include "mrs_common.cuh"
 
 namespace mrs {
@@ -166,6 +168,7 @@ set_state_kernel(float* __restrict__ st, size_t S, int N, const float* __restric
 // is reproducible from (seed, env) alone and independent of the launch shape.
 struct SpawnArgs {
     unsigned long long seed;
+    unsigned long long env_offset;      // global index of this shard's first env
     float z_lo, z_hi, xy_radius, xy_sigma;
     float yaw_lo, yaw_hi;
     int max_rounds;
@@ -195,7 +198,8 @@ spawn_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const Spaw
     int round = 0;
     for (; round < sp.max_rounds; ++round) {
         if (redraw && valid) {
-            const unsigned long long key = splitmix64(sp.seed ^ splitmix64(((unsigned long long)e << 20) ^ ((unsigned long long)lane << 12) ^ (unsigned long long)round));
+            const unsigned long long ge = sp.env_offset + (unsigned long long)e;      // global env index: shards draw different envs
+            const unsigned long long key = splitmix64(sp.seed ^ splitmix64((ge << 20) ^ ((unsigned long long)lane << 12) ^ (unsigned long long)round));
             const float u1 = u01(key), u2 = u01(splitmix64(key)), u3 = u01(splitmix64(key ^ 0x5851F42D4C957F2Dull));
             const float r = sp.xy_sigma * sqrtf(-2.f * logf(u1));          // Box-Muller
             float sn, cs;
@@ -219,7 +223,7 @@ spawn_kernel(const __grid_constant__ MrsConfig c, const MrsBuffers b, const Spaw
     const unsigned s = (unsigned)e * (unsigned)N + (unsigned)lane;
     float* st = b.state;
     st[0 * (size_t)S + s] = x; st[1 * (size_t)S + s] = y; st[2 * (size_t)S + s] = z;
-    const unsigned long long ky = splitmix64(sp.seed ^ splitmix64(0xA5A5A5A5ull ^ ((unsigned long long)e << 20) ^ ((unsigned long long)lane << 12)));
+    const unsigned long long ky = splitmix64(sp.seed ^ splitmix64(0xA5A5A5A5ull ^ ((sp.env_offset + (unsigned long long)e) << 20) ^ ((unsigned long long)lane << 12)));
     const float yaw = sp.yaw_lo + (sp.yaw_hi - sp.yaw_lo) * u01(ky);
     float sy, cy;
     sincosf(0.5f * yaw, &sy, &cy);
@@ -567,16 +571,28 @@ int launch_adjacency(const float* pos, size_t cs, size_t as, float* A, int E, in
 // Side stream of the wide path: the adjacency kernel of step t (a pure streaming store that only
 // reads the new positions) runs next to the compute-bound pair kernel of step t+1; it has to be done
 // before post(t+1) overwrites the positions.  Fork / join through events, so it is capturable.
+// One lane per device, created once under a lock.  The lane's events are re-recorded by every call that uses it,
+// so the calls that do (mrs_step_many / mrs_rollout with N > 32, mrs_rollout_host) must not run concurrently on one
+// device from several host threads or caller streams (header: one host thread per GPU).
 static SideLane g_side[64];
+static std::mutex g_lane_mutex;
 SideLane* side_lane() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_lane_mutex);
     SideLane& L = g_side[dev];
     if (!L.ok) {
-        if (cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&L.posted, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&L.adj_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        L.ok = true;
+        SideLane fresh;
+        if (cudaStreamCreateWithFlags(&fresh.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&fresh.posted, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&fresh.adj_done, cudaEventDisableTiming) != cudaSuccess) {
+            if (fresh.posted) cudaEventDestroy(fresh.posted);
+            cudaStreamDestroy(fresh.s);
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        fresh.ok = true;
+        L = fresh;
     }
     return &L;
 }
@@ -611,6 +627,7 @@ static int step_impl(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
     a.G = 0;
     a.role = role;
     a.seq = seq;
+    a.slow_slots = 0;
     a.chunk_lo = 0;
     a.nchunks = 0;
     a.X0 = a.A0 = nullptr;
@@ -910,16 +927,29 @@ CopyLanes g_lanes[64];
 CopyLanes* copy_lanes() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_lane_mutex);
     CopyLanes& L = g_lanes[dev];
     if (!L.ok) {
-        if (cudaStreamCreateWithFlags(&L.h2d, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaStreamCreateWithFlags(&L.d2h, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        for (int i = 0; i < 2; ++i) {
-            if (cudaEventCreateWithFlags(&L.up[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-            if (cudaEventCreateWithFlags(&L.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        CopyLanes fresh;
+        bool good = cudaStreamCreateWithFlags(&fresh.h2d, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaStreamCreateWithFlags(&fresh.d2h, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && good; ++i)
+            good = cudaEventCreateWithFlags(&fresh.up[i], cudaEventDisableTiming) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&fresh.done[i], cudaEventDisableTiming) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&fresh.tail, cudaEventDisableTiming) == cudaSuccess;
+        if (!good) {                      // release whatever was created: the next call starts from scratch
+            if (fresh.h2d) cudaStreamDestroy(fresh.h2d);
+            if (fresh.d2h) cudaStreamDestroy(fresh.d2h);
+            for (int i = 0; i < 2; ++i) {
+                if (fresh.up[i]) cudaEventDestroy(fresh.up[i]);
+                if (fresh.done[i]) cudaEventDestroy(fresh.done[i]);
+            }
+            if (fresh.tail) cudaEventDestroy(fresh.tail);
+            (void)cudaGetLastError();
+            return nullptr;
         }
-        if (cudaEventCreateWithFlags(&L.tail, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        L.ok = true;
+        fresh.ok = true;
+        L = fresh;
     }
     return &L;
 }
@@ -974,7 +1004,7 @@ int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
 
 
 int mrs_spawn(const MrsConfig* cfg, const MrsBuffers* bufs, const unsigned char* env_mask, unsigned long long seed,
-              float z_lo, float z_hi, float xy_radius, float xy_sigma, float yaw_lo, float yaw_hi, int max_rounds,
+              unsigned long long env_offset, float z_lo, float z_hi, float xy_radius, float xy_sigma, float yaw_lo, float yaw_hi, int max_rounds,
               unsigned int* failed_envs, void* stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
@@ -982,7 +1012,7 @@ int mrs_spawn(const MrsConfig* cfg, const MrsBuffers* bufs, const unsigned char*
     if (cfg->N > 32) return MRS_ERR_UNSUPPORTED;
     if (!(z_hi >= z_lo) || !(xy_radius > 0.f) || !(xy_sigma > 0.f) || max_rounds <= 0) return MRS_ERR_ARG;
     SpawnArgs sp;
-    sp.seed = seed; sp.z_lo = z_lo; sp.z_hi = z_hi; sp.xy_radius = xy_radius; sp.xy_sigma = xy_sigma;
+    sp.seed = seed; sp.env_offset = env_offset; sp.z_lo = z_lo; sp.z_hi = z_hi; sp.xy_radius = xy_radius; sp.xy_sigma = xy_sigma;
     sp.yaw_lo = yaw_lo; sp.yaw_hi = yaw_hi; sp.max_rounds = max_rounds;
     spawn_kernel<<<(unsigned)((cfg->E + 3) / 4), 128, 0, (cudaStream_t)stream>>>(*cfg, *bufs, sp, env_mask, failed_envs);
     return last_error();

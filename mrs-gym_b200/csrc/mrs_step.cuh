@@ -57,18 +57,19 @@ __device__ __forceinline__ const float* plane_ptr(const float* p0, unsigned S, i
 // ------------------------------------------------------------------------------ contact path of the group kernels
 // One step of one warp-chunk, global memory to global memory, WITH the contact solver
 // (bullet_model.solve_contacts): the group kernels call it for a chunk in which some agent is near the ground or
-// near another agent, and carry no contact code themselves.  It is expanded at ONE place, the top of the chunk loop,
-// where nothing but the loop bookkeeping is live, and reads the kernel parameters (constant bank): the fast path pays
-// no registers for a path free flight never takes.  (A real call was tried: the ABI's caller-saved spills went to
-// local memory across the whole kernel and the chained launches started to miss their hand-over entries.)
+// near another agent, and carry no contact code themselves.  A real function, called from ONE place after the hot
+// chunk loop (the parked-chunk pass): inlined anywhere in the kernel -- even after the loop -- its mere presence
+// changed the register allocation and instruction scheduling of the hot loop (+1.3 us per C5 step, measured with
+// the path compiled in but never taken), and inside the loop its loop-invariant set-up was hoisted to the top of the
+// kernel (~290 instructions and a stack frame per warp).
 // Same arithmetic as the fast path for everything but the contact rows; plain (unrolled-free) loops.
 // In-warp solve: every lane owns one agent, its ground rows and -- per tournament round -- the pair rows with its
 // round partner; the partner's velocity travels by shuffle, both lanes of a pair evaluate the same rows from their
 // own side and get equal and opposite changes.
 template <int MODE>
-static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr, const Derived* dptr, const MrsBuffers* bptr,
-                                                       const StepArgs* aptr, int G, int chunk, int t0, int T, float4* wpos,
-                                                       unsigned* sh_events) {
+static __device__ __noinline__ void chunk_step_contact(const MrsConfig* cptr, const Derived* dptr, const MrsBuffers* bptr,
+                                                       const StepArgs* aptr, int G, int chunk, int t0, int T, unsigned lane_mask,
+                                                       float4* wpos, unsigned* sh_events) {
     const MrsConfig& c = *cptr;
     const Derived& d = *dptr;
     const MrsBuffers& b = *bptr;
@@ -79,6 +80,7 @@ static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr,
     const unsigned S = (unsigned)E * (unsigned)N;
     const int e = chunk * gpw + (lane / G);
     const bool valid = (e < E) && (ai < N);
+    const bool mine = valid && ((lane_mask >> lane) & 1u);     // lanes whose env this call handles (it stores nothing else)
     const unsigned s = valid ? (unsigned)e * (unsigned)N + (unsigned)ai : 0u;
     const MrsPhysicsParams& ph = c.phys;
     const ContactParams cp = make_contact_params(ph, d);
@@ -93,15 +95,22 @@ static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr,
 #pragma unroll
         for (int i = 0; i < 3; ++i) k.io[i] = k.ip[i] = k.iv[i] = k.lve[i] = k.dve[i] = k.ltv[i] = 0.f;
     }
-    if (lane == 0) atomicAdd(&sh_events[5], (unsigned)(T - t0));
+    if (lane == 0) atomicAdd(&sh_events[5], (unsigned)(T - t0));       // warp-chunk steps on the contact path
   for (int t = t0; t < T; ++t) {
     unsigned status = 0, n_agent_rows = 0, n_ground = 0, n_sweeps = 0;
     float act[4] = {0.f, 0.f, 0.f, 0.f};
     if (valid && kA > 0 && load_action<MODE>(a.actions, (size_t)t * S + s, act)) status |= MRS_STATUS_NAN_ACTION;
     float R[9], rpm[4];
     quat_to_mat(st, R);
-    action_to_rpm<MODE>(c, c.quad, d, st, R, act, k, rpm);
-    if (b.rpm && MODE != MRS_NO_ACTION && valid) {
+    // NaN action (the reference raises before stepping, MRS.py:247-248; device-resident actions cannot): the agent
+    // gets no rotor forces in this step, like MRS.step(None) (MRS.py:243,252), its PID state stays as it is
+    const bool nan_act = status != 0u;
+    if (nan_act) {
+        rpm[0] = rpm[1] = rpm[2] = rpm[3] = 0.f;
+    } else {
+        action_to_rpm<MODE>(c, c.quad, d, st, R, act, k, rpm);
+    }
+    if (b.rpm && MODE != MRS_NO_ACTION && mine) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) b.rpm[(size_t)i * S + s] = rpm[i];
     }
@@ -121,6 +130,7 @@ static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr,
             near = near || (dxy2 + rz * rz < cp.lim2);
         }
     }
+    if (nan_act) dw = 0.f;
     apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
     // ---- contact solve
     const bool gcand = cp.ground_contact && valid && st.pz < cp.gnd_skip_z;
@@ -185,13 +195,13 @@ static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr,
     integrate(c, d, st);
     if (!agent_finite(st)) status |= MRS_STATUS_NONFINITE;
     // ---- observation + state
-    if (a.X0 && valid) write_X(a.X0 - (long long)t * a.xstride, c.state_layout, s, st);
+    if (a.X0 && mine) write_X(a.X0 - (long long)t * a.xstride, c.state_layout, s, st);
     if (a.A0) {
         float* Arow = a.A0 - (long long)t * a.astride + (size_t)s * N;
         __syncwarp();
         wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
         __syncwarp();
-        if (valid) {
+        if (mine) {
             for (int j = 0; j < N; ++j) {
                 const float4 pj = wpos[gb + j];
                 const float hit = d.comm_inf ? 1.f : adjacency_pair(st.px, st.py, st.pz, pj.x, pj.y, pj.z, d.s_max);
@@ -200,7 +210,7 @@ static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr,
         }
         __syncwarp();
     }
-    if (!valid) { status = 0; n_agent_rows = 0; n_ground = 0; n_sweeps = 0; }
+    if (!mine) { status = 0; n_agent_rows = 0; n_ground = 0; n_sweeps = 0; }
     {
         const unsigned any_status = __reduce_or_sync(kFull32, status);
         const unsigned sum_rows = __reduce_add_sync(kFull32, n_agent_rows);
@@ -216,7 +226,7 @@ static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr,
         }
     }
   }
-    if (valid) {
+    if (mine) {
         store_agent(b.state, S, s, st);
         store_ctrl<MODE>(b.ctrl, S, s, k);
     }
@@ -224,7 +234,11 @@ static __device__ __forceinline__ void chunk_step_contact(const MrsConfig* cptr,
 
 // dynamic shared memory of one warp of the group kernel: pair tile (+ prefetch stage for full chunks)
 template <int MODE, int GT> __host__ __device__ constexpr int group_warp_smem_bytes() {
+#ifdef MRS_EXP_OLDSMEM
+    return 1024 + ((MRS_PREFETCH && GT != 0) ? mode_stage_floats<MODE>() * 4 : 0);
+#else
     return 512 + ((MRS_PREFETCH && GT != 0) ? mode_stage_floats<MODE>() * 4 : 0);
+#endif
 }
 
 //
@@ -257,8 +271,13 @@ static_assert(kSyncQueue + kSyncQueues * kSyncQueueLen <= MRS_SYNC_WORDS, "sync 
 
 template <int MODE, int GT, int WPB, bool BAKED, bool MANY>
 __global__ void __launch_bounds__(WPB * 32, WPB == 4 ? ModeTraits<MODE>::minb : (4 * ModeTraits<MODE>::minb) / WPB)
+#ifdef MRS_EXP_NOGC
+step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant__ Derived d_in, const MrsBuffers b,
+                  const StepArgs a) {
+#else
 step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant__ Derived d_in,
                   const __grid_constant__ MrsBuffers b, const __grid_constant__ StepArgs a) {
+#endif
     MrsConfig c_bk;
     Derived d_bk;
     if constexpr (BAKED) baked_fill(c_bk, d_bk, c_in, d_in);
@@ -270,13 +289,17 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     // shared memory, one contiguous region per warp so that every address is one per-warp base plus an
     // immediate: [32 positions] (the pair tile, 512 B) [prefetch stage]
     constexpr int kWarpBytes = group_warp_smem_bytes<MODE, GT>();
-    __shared__ int sh_counter, sh_hi, sh_range;
+    __shared__ int sh_counter, sh_hi, sh_range, sh_lo;
     __shared__ unsigned sh_epoch;
     __shared__ unsigned sh_events[7];       // CTA-level status word + the six statistics counters
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + wib * kWarpBytes;
     float4* wpos = reinterpret_cast<float4*>(wbase);
+#ifdef MRS_EXP_OLDSMEM
+    float* stage = reinterpret_cast<float*>(wbase + 1024);
+#else
     float* stage = reinterpret_cast<float*>(wbase + 512);
+#endif
     const int G = GT ? GT : a.G;
     const int N = GT ? GT : c.N;
     const int E = c.E;
@@ -308,7 +331,11 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             // last entry exists).  Then at most the queues of positions t-2 .. t+1 are live.
             const unsigned long long* q = b.sync + kSyncQueue + ((a.seq - 1) & (kSyncQueues - 1)) * kSyncQueueLen + blockIdx.x;
             const unsigned long long* q3 = b.sync + kSyncQueue + ((a.seq - 3) & (kSyncQueues - 1)) * kSyncQueueLen + (gridDim.x - 1);
+#ifdef MRS_EXP_NOBOUND
+            const bool bound = false;
+#else
             const bool bound = a.seq >= 3;
+#endif
             unsigned long long e = ld_acquire_gpu_u64(q), e3 = bound ? ld_acquire_gpu_u64(q3) : 0ull, t0 = 0;
             unsigned epoch = (unsigned)ld_acquire_gpu_u64(b.sync);
             auto pending = [&]() {
@@ -351,9 +378,14 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     if (threadIdx.x == 0) {
         const int nwork = a.nchunks - a.chunk_lo;
         const int r = sh_range;
-        sh_counter = a.chunk_lo + (int)(((long long)r * nwork) / gridDim.x);
+        sh_counter = sh_lo = a.chunk_lo + (int)(((long long)r * nwork) / gridDim.x);
         sh_hi = a.chunk_lo + (int)(((long long)(r + 1) * nwork) / gridDim.x);
     }
+    // chunks parked for the contact path: first step they need it and the warp that parked them (all ones = not
+    // parked), one slot per chunk of this CTA (SM-filling shape: index = chunk - first chunk of the CTA's range;
+    // small shape: warp * rounds + round).  A warp processes what it parked itself: no CTA barrier in between.
+    unsigned* parked = reinterpret_cast<unsigned*>(smem_raw + WPB * kWarpBytes);      // step | parking warp << 16
+    for (int i = threadIdx.x; i < a.slow_slots; i += WPB * 32) parked[i] = 0xffffffffu;
     __syncthreads();
     // one elected lane draws a chunk index (-1 when the share is used up); the others get it by shuffle later.
     // elect.sync keeps ptxas from wrapping the single-lane atomic in its warp-aggregation sequence (vote, popc,
@@ -437,21 +469,12 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
         if (chunk_next >= a.nchunks) chunk_next = -1;
     }
     if (kStage && chunk >= 0) prefetch(chunk);
-    // A chunk that needs the contact path is parked here and processed by the out-of-line call at the top of the
-    // next iteration, where nothing but the loop bookkeeping is live (a call in the middle of the step would make
-    // the register allocator keep the step's working set in memory on the fast path too).
-    int slow_chunk = -1, slow_t = 0;
-    while (chunk >= 0 || slow_chunk >= 0) {
-#ifndef MRS_EXP_NOCALL
-        if (slow_chunk >= 0) {
-            __syncwarp();
-            chunk_step_contact<MODE>(&c_in, &d_in, &b, &a, GT ? GT : a.G, slow_chunk, slow_t, T, wpos, sh_events);
-            slow_chunk = -1;
-            continue;
-        }
-#else
-        if (slow_chunk >= 0) { slow_chunk = -1; continue; }
-#endif
+    // A chunk that needs the contact path is PARKED (its slot in `parked` gets the step) and processed after this
+    // loop: the hot loop keeps its shape -- one vote, and a branch around the stores -- whatever the contact path
+    // costs (inside the loop it cost ~90 extra instructions per chunk: its loop-invariant set-up was hoisted here).
+    const int rounds_static = kLocal ? 0 : (a.nchunks - a.chunk_lo + wtotal - 1) / wtotal;
+    int round_i = 0, my_parked = 0;
+    while (chunk >= 0) {
         const int ticket = (kLocal && chunk_next >= 0) ? draw() : -1;   // the chunk after next; warp-uniform condition
         // kFull: the chunk is 32 consecutive valid slots; else lanes >= N of a group (and envs >= E) idle
         const int e = chunk * gpw + (lane / G);
@@ -529,14 +552,13 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
 #else
             {
 #endif
-            // ---- contact (rare): a warp with an agent near the ground or near another agent hands the whole chunk
-            // to the contact path (chunk_step_contact), which redoes this step from the state in global memory with
-            // the sequential-impulse solver; the fast path below carries no contact code at all.  Ground proximity
-            // is known at once, agent proximity after pair pass 1.
-            bool touch = __any_sync(kFull32, valid && ph.ground_contact && st.pz < d.gnd_skip_z);
+            // ---- pair pass 1: downwash + contact proximity on the pre-step positions.  Multi-step launches run it
+            // BEFORE the controller (the contact hand-off below must see the PID state of the step's start: it lives
+            // in registers only); single-step launches after it, where its shared-memory latency hides behind the
+            // controller arithmetic (the contact path re-reads the untouched PID planes from global memory).
             float dw = 0.f;
             bool near = false;
-            if (!touch) {
+            auto pair_pass1 = [&]() {
             // ---- pair pass 1: downwash + contact proximity on the pre-step positions
             __syncwarp();
             wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
@@ -553,6 +575,9 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                     float dmin = 3.0e38f;
 #pragma unroll
                     for (int k = 1; k <= GT / 2; ++k) {
+#ifdef MRS_EXP_P1FENCE
+                        asm volatile("" ::: "memory");      // keep the rounds' shared-memory loads apart
+#endif
                         const float4 pj = wpos[gb + ((ai + k) & (GT - 1))];
                         const float rx = pj.x - st.px, ry = pj.y - st.py, rz = pj.z - st.pz;
                         const float dxy2 = rx * rx + ry * ry;
@@ -585,22 +610,39 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
                     }
                 }
             }
-            touch = __any_sync(kFull32, valid && pair_contact && near);
-            }
-            if (touch) {
+            };
+            // ---- contact (rare): a warp with an agent near the ground or near another agent -- or with a NaN action,
+            // which makes that agent step without rotor forces -- hands the whole chunk to the contact path
+            // (chunk_step_contact) at the top of the next iteration: the step is redone there from the state in
+            // global memory with the sequential-impulse solver.  The fast path carries no contact code.
+            auto hand_off = [&]() -> bool {
+#ifdef MRS_EXP_NODETECT
+                return false;
+#endif
+                if (!__any_sync(kFull32, valid && ((ph.ground_contact && st.pz < d.gnd_skip_z) || (pair_contact && near) ||
+                                                   status != 0u)))
+                    return false;
                 if (MANY && valid) {         // the registers hold the newest state: make it visible to the contact path
                     store_agent(b.state, S, s, st);
                     store_ctrl<MODE>(b.ctrl, S, s, k);
                 }
-                slow_chunk = chunk;          // steps t .. T-1 of this chunk run at the top of the next iteration
-                slow_t = t;
-                state_stored = true;
-                break;
+                if (lane == 0) parked[kLocal ? chunk - sh_lo : wib * rounds_static + round_i] = (unsigned)t | ((unsigned)wib << 16);
+                ++my_parked;
+                state_stored = true;         // steps t .. T-1 of this chunk belong to the contact path
+                return true;
+            };
+            if constexpr (MANY) {
+                pair_pass1();
+                if (hand_off()) break;
             }
             float R[9];
             quat_to_mat(st, R);
             action_to_rpm<MODE>(c, c_in.quad, d, st, R, act, k, rpm);
-            if (b.rpm && MODE != MRS_NO_ACTION && valid) {       // optional Quadcopter.speeds mirror
+            if constexpr (!MANY) {
+                pair_pass1();
+                (void)hand_off();            // single step: no break -- the stores below are skipped (state_stored)
+            }
+            if (b.rpm && MODE != MRS_NO_ACTION && valid && !state_stored) {       // optional Quadcopter.speeds mirror
 #pragma unroll
                 for (int i = 0; i < 4; ++i) *plane_ptr(b.rpm + s, S, i) = rpm[i];
             }
@@ -612,6 +654,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             // ---- observation: newest X slice and newest A slice into their tape slots
             // (X rows staged through shared memory and written as whole 16-byte pieces were measured: neutral
             // at C5, 18.4 vs 18.1 us -- unlike the A rows below, the float2 stores are not the limiter)
+            if (!state_stored) {
             if (a.X0 && valid) write_X(Xs, c.state_layout, s, st);
             if (a.A0) {
                 float* Arow = As + (size_t)s * N;
@@ -700,7 +743,8 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
             // happen once per CTA at the end.  (A swarm resting on the ground reports a ground contact per
             // agent per step: with one global atomic per warp-chunk that was 10 k same-address L2 atomics
             // per launch at C5 and cost ~15 % of the step.)
-            if (!valid) { status = 0; n_agent_rows = 0; n_ground = 0; }
+            }
+            if (!valid || state_stored) { status = 0; n_agent_rows = 0; n_ground = 0; }
             if (__reduce_or_sync(kFull32, status | n_agent_rows | n_ground)) {      // rare in free flight
                 const unsigned any_status = __reduce_or_sync(kFull32, status);
                 const unsigned sum_rows = __reduce_add_sync(kFull32, n_agent_rows);
@@ -728,12 +772,26 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
         stamp();
 #endif
         chunk = chunk_next;
+        ++round_i;
         if (kLocal) {
             chunk_next = (chunk >= 0) ? claim(__shfl_sync(kFull32, ticket, 0)) : -1;
         } else {
             chunk_next = (chunk >= 0 && chunk + wtotal < a.nchunks) ? chunk + wtotal : -1;
         }
     }
+#ifndef MRS_EXP_NOCALL
+    // ---- the chunks this warp parked: contact path
+    if (my_parked) {
+        __syncwarp();
+        const int i_end = kLocal ? sh_hi - sh_lo : (wib + 1) * rounds_static;
+        for (int i = kLocal ? 0 : wib * rounds_static; i < i_end; ++i) {
+            const unsigned e = parked[i];
+            if (e == 0xffffffffu || (int)(e >> 16) != wib) continue;
+            const int pc = kLocal ? sh_lo + i : a.chunk_lo + gw + (i - wib * rounds_static) * wtotal;
+            chunk_step_contact<MODE>(&c_in, &d_in, &b, &a, GT ? GT : a.G, pc, (int)(e & 0xffffu), T, kFull32, wpos, sh_events);
+        }
+    }
+#endif
     __syncthreads();
     if (threadIdx.x == 0) {
         if (sh_events[0] && b.status) atomicOr(b.status, sh_events[0]);
@@ -789,7 +847,12 @@ __device__ __forceinline__ void agent_pre(const MrsConfig& c, const Derived& d, 
     if (load_action<MODE>(actions, s, act)) status |= MRS_STATUS_NAN_ACTION;
     float R[9], rpm[4];
     quat_to_mat(st, R);
-    action_to_rpm<MODE>(c, c.quad, d, st, R, act, k, rpm);
+    if (status) {            // NaN action: no rotor forces in this step, PID state untouched (see chunk_step_contact)
+        rpm[0] = rpm[1] = rpm[2] = rpm[3] = 0.f;
+        dw = 0.f;
+    } else {
+        action_to_rpm<MODE>(c, c.quad, d, st, R, act, k, rpm);
+    }
     apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
     float* sc = b.scratch;
     sc[0 * (size_t)S + s] = st.vx; sc[1 * (size_t)S + s] = st.vy; sc[2 * (size_t)S + s] = st.vz;
@@ -1043,18 +1106,23 @@ agent_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ De
 
 // ------------------------------------------------------------------------------ launch
 template <int MODE, int GT, int WPB, bool BAKED, bool MANY>
-static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, long long blocks,
+static int launch_group_wpb(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a_in, long long blocks,
                             bool pdl, cudaStream_t st) {
-    constexpr size_t smem = (size_t)WPB * group_warp_smem_bytes<MODE, GT>();
-    static bool configured[64] = {};          // per device: the attribute belongs to the function ON a device
+    StepArgs a = a_in;
+    // the parked-chunk list of a CTA (contact path): 4 bytes per chunk the CTA can own
+    const long long nwork = a.nchunks - a.chunk_lo;
+    a.slow_slots = (WPB > 4) ? (int)((nwork + blocks - 1) / blocks) + 1
+                             : WPB * (int)((nwork + blocks * WPB - 1) / (blocks * WPB));
+    const size_t smem = (size_t)WPB * group_warp_smem_bytes<MODE, GT>() + (((size_t)a.slow_slots * 4 + 15) & ~(size_t)15);
+    if (smem > 200 * 1024) return MRS_ERR_UNSUPPORTED;
+    static size_t configured[64] = {};        // per device: the attribute belongs to the function ON a device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MRS_ERR_CUDA;
-    if (!configured[dev]) {
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB, BAKED, MANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-                cudaSuccess)
+    if (smem > 48 * 1024 && smem > configured[dev]) {
+        if (cudaFuncSetAttribute(step_group_kernel<MODE, GT, WPB, BAKED, MANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
             return MRS_ERR_CUDA;
-        configured[dev] = true;
+        configured[dev] = smem;
     }
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)blocks);

@@ -222,6 +222,11 @@ class Swarm:
                 raise ValueError('host actions must live in pinned host memory')
         elif actions.device != self.device:
             raise ValueError('actions live on %s, the swarm on %s' % (actions.device, self.device))
+        if (adim == 4 or self.N in (8, 16, 32)) and actions.data_ptr() % 16:
+            # these shapes read actions with 16-byte cp.async / float4 loads: a misaligned pointer would be a sticky
+            # CUDA fault instead of a Python exception (3-component actions of other swarm sizes are read per float)
+            raise ValueError('actions must start on a 16-byte boundary (got a view at offset %d of its storage); '
+                             'pass actions.clone()' % actions.storage_offset())
 
     def _step_launches(self, n=1, fused=False):
         """Kernels the library launches for n steps (bench: gpu_launches).  N <= 32: one fused kernel per step
@@ -374,14 +379,16 @@ class Swarm:
         self.launches += 1
 
     def spawn(self, seed, env_mask=None, z=(1.0, 3.0), xy_radius=1.0, xy_sigma=1.0, yaw=(-math.pi / 2, math.pi / 2),
-              max_rounds=256):
-        """On-device reset with the reference's default start distribution (mrs_spawn).  Returns the
-        device counter of envs whose rejection sampling did not converge (read it lazily)."""
+              max_rounds=256, env_offset=0):
+        """On-device reset with the reference's default start distribution (mrs_spawn).  env_offset: global index
+        of this shard's first env (the draws are keyed by seed and GLOBAL env index, so the ranks of a sharded job
+        sample different environments).  Returns the device counter of envs whose rejection sampling did not
+        converge (read it lazily)."""
         if env_mask is not None:
             env_mask = torch.as_tensor(env_mask).to(self.device).to(torch.uint8).reshape(self.E).contiguous()
         failed = torch.zeros(1, device=self.device, dtype=torch.int32)
         _abi.check(self.lib.mrs_spawn(C.byref(self.cfg), C.byref(self.bufs), _ptr(env_mask), C.c_ulonglong(int(seed)),
-                                      float(z[0]), float(z[1]), float(xy_radius), float(xy_sigma), float(yaw[0]),
+                                      C.c_ulonglong(int(env_offset)), float(z[0]), float(z[1]), float(xy_radius), float(xy_sigma), float(yaw[0]),
                                       float(yaw[1]), int(max_rounds), _ptr(failed), self._stream()), 'mrs_spawn')
         self.launches += 1
         return failed
@@ -413,6 +420,52 @@ class Swarm:
         pitch = torch.asin(torch.clamp(2 * (w * y - z * x), -1.0, 1.0))
         yaw = torch.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
         return torch.stack([roll, pitch, yaw], dim=-1).reshape(self.E, self.N, 3)
+
+    def get_rotmat(self):
+        """body->world rotation matrices [E, N, 3, 3] (Object.get_ori(mat=True), Object.py:90-95)."""
+        x, y, z, w = (self.state[i] for i in range(3, 7))
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                         2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                         2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=-1)
+        return R.reshape(self.E, self.N, 3, 3)
+
+    def contact_points(self, body=False, threshold=None):
+        """Contact candidates of every agent on the contact geometry of the step (see Environment.get_contact_points):
+        slot 0 the nearest other agent (contact spheres), slots 1-4 the lower-rim points of the collision cylinder
+        against the ground.  Derived from the device state with torch ops (a diagnostic, not on the step path)."""
+        ph = self.cfg.phys
+        thr = float(ph.contact_margin if threshold is None else threshold)
+        pr = self.proximity(thr)
+        pos, R = self.get_pos(), self.get_rotmat()
+        E, N, dev = self.E, self.N, self.device
+        j = pr['nearest'].long().clamp(min=0)
+        pj = torch.gather(pos, 1, j.unsqueeze(-1).expand(E, N, 3))
+        d = pos - pj
+        dist = d.norm(dim=-1, keepdim=True).clamp(min=1e-12)
+        n_a = d / dist                                                    # on the agent: away from the partner
+        rc = float(ph.contact_radius)
+        p_a = pos - n_a * rc
+        has_a = (pr['nearest'] >= 0) & (pr['gap_agent'] < thr)
+        # rim points: c = (+-r, 0, cz), (0, +-r, cz), cz = -h sign(R22)
+        r_, h_ = float(ph.col_radius), float(ph.col_halfheight)
+        sgn = torch.where(R[..., 2, 2] >= 0, 1.0, -1.0)
+        c = torch.zeros(E, N, 4, 3, device=dev)
+        c[..., 0, 0], c[..., 1, 1], c[..., 2, 0], c[..., 3, 1] = r_, r_, -r_, -r_
+        c[..., 2] = (-h_ * sgn).unsqueeze(-1)
+        pw = pos.unsqueeze(2) + torch.einsum('enij,enpj->enpi', R, c)
+        gdist = pw[..., 2] - float(ph.col_margin) - float(ph.ground_z)
+        obj = torch.full((E, N, 5), -1, dtype=torch.int64, device=dev)
+        obj[..., 0] = torch.where(has_a, pr['nearest'].long(), torch.full_like(j, -1))
+        obj[..., 1:] = torch.where(gdist < thr, torch.full_like(gdist, float(N)).long(), torch.full_like(gdist, -1.0).long())
+        P = torch.cat([p_a.unsqueeze(2), pw], dim=2)
+        nrm = torch.zeros(E, N, 5, 3, device=dev)
+        nrm[..., 0, :] = n_a
+        nrm[..., 1:, 2] = 1.0
+        D = torch.cat([pr['gap_agent'].unsqueeze(-1), gdist], dim=-1)
+        if body:
+            P = torch.einsum('enji,enpj->enpi', R, P - pos.unsqueeze(2))
+            nrm = torch.einsum('enji,enpj->enpi', R, nrm)
+        return {'object': obj, 'pos': P, 'normal': nrm, 'distance': D, 'mask': obj >= 0}
 
     def adjacency(self, pos):
         """MRS.calc_A on arbitrary float32 positions [E,N,3] -> [E,N,N] (bit-exact with torch CPU)."""

@@ -23,6 +23,7 @@ import torch
 from . import _abi
 from .core import Swarm
 from . import spawn as _spawn
+from .spaces import Box
 
 _LAYOUTS = {'pos_vel': _abi.X_POS_VEL, 'full': _abi.X_FULL}
 
@@ -49,8 +50,10 @@ class AgentBatch:
         return self._s.state[3:7]
 
     def get_ori(self, mat=False):
+        """euler 'xyz' [3, E*N], or with mat=True the body->world rotation matrices [3, 3, E*N]
+        (Object.get_ori, Object.py:90-97: R.from_quat(q).as_matrix())."""
         if mat:
-            raise NotImplementedError('get_ori(mat=True) is not provided for batched state_fn; use get_quat()')
+            return self._s.get_rotmat().reshape(self._s.S, 3, 3).permute(1, 2, 0)
         return self._s.get_ori().reshape(self._s.S, 3).t()
 
 
@@ -80,8 +83,8 @@ class Environment:
     def get_angvel(self):
         return self._out(self.swarm.get_angvel())
 
-    def get_ori(self):
-        return self._out(self.swarm.get_ori())
+    def get_ori(self, mat=False):
+        return self._out(self.swarm.get_rotmat() if mat else self.swarm.get_ori())
 
     def get_quat(self):
         return self._out(self.swarm.get_quat())
@@ -108,6 +111,27 @@ class Environment:
     def raycast(self, directions, offset=(0.0, 0.0, 0.0), body=True, RANGE=100.0):
         r = self.swarm.raycast(directions, offset, body, RANGE)
         return {k: self._out(v) for k, v in r.items()}
+
+    def get_contact_points(self, body=False, threshold=None):
+        """Object.get_contact_points (Object.py:100-116) on the contact geometry of the step, all agents at once.
+        Per agent up to 1 + 4 candidate contacts are reported as padded arrays with a mask: the nearest other agent
+        (contact spheres of CONTACT_RADIUS) and the four lower-rim points of the collision cylinder against the
+        ground.  Keys: 'object' int [..., 5] (agent index, N_AGENTS = ground, -1 = no contact), 'pos' [..., 5, 3]
+        (world, or body frame with body=True), 'normal' [..., 5, 3] unit normal on the agent, 'distance' [..., 5],
+        'mask' bool [..., 5].  A contact exists where the gap is below `threshold` (default: the solver's contact
+        margin, like Bullet's manifold).  'normal force' magnitudes are not kept by the step; the solver's
+        impulses are internal."""
+        return {k: self._out(v) for k, v in self.swarm.contact_points(body=body, threshold=threshold).items()}
+
+    def get_closest_objects(self, radius):
+        """Object.get_closest_objects (Object.py:139-141): for every agent the other agents whose contact
+        spheres come within `radius` of its own, as a bool mask [..., N, N] plus the gaps [..., N, N]."""
+        sw = self.swarm
+        p = sw.get_pos()
+        gap = torch.cdist(p, p) - 2.0 * float(sw.cfg.phys.contact_radius)
+        eye = torch.eye(sw.N, dtype=torch.bool, device=p.device)
+        mask = (gap < float(radius)) & ~eye
+        return {'mask': self._out(mask), 'gap': self._out(gap)}
 
     # GUI / debug helpers of the reference (Environment.py:127-306) are no-ops headless
     def draw_links(self, A):
@@ -162,13 +186,17 @@ class MRS:
         self.COPY_OBS = None
         self.BATCHED = None          # None: batched shapes iff N_ENVS > 1
         self.SEED = 0                # seed of the on-device start-state sampler
+        self.ENV_OFFSET = None       # global index of this process's first env; None: shard_range(rank) under torchrun
         self.set_constants(kwargs)
         if env != 'simple':
             raise NotImplementedError("only the 'simple' world (N x cf2x + ground plane, EnvCreator.py:7-13) is in scope")
         self.state_fn = state_fn
         self.reward_fn = reward_fn if (reward_fn is not None) else (lambda **kwargs: 0.0)
+        # default done: steps since the last reset >= MAX_TIMESTEPS (MRS.py:39); batched: per env ([E] bool tensor,
+        # a masked reset restarts the count of the selected envs only)
         self.done_fn = done_fn if (done_fn is not None) else (
-            lambda **kwargs: kwargs['steps_since_reset'] >= self.MAX_TIMESTEPS)
+            lambda **kwargs: (self.env_steps >= self.MAX_TIMESTEPS) if self._batched
+            else kwargs['steps_since_reset'] >= self.MAX_TIMESTEPS)
         self.info_fn = info_fn if (info_fn is not None) else (lambda **kwargs: {})
         self.update_fn = update_fn
         self.start_fn = start_fn
@@ -194,6 +222,13 @@ class MRS:
         self._spawn_count = 0
         self.spawn_failed = None
         self._build(layout, custom_D)
+        # Gym spaces, literally as the reference builds them (MRS.py:51-52): a flat observation box whose length is
+        # the reference's own expression K_HOPS + 1 * N_AGENTS * STATE_SIZE (operator precedence included) and the
+        # set_control-style action box [9.81 -+ 1, -+1, -+1, -+1] tiled over the agents
+        n_obs = self.K_HOPS + 1 * self.N_AGENTS * self.STATE_SIZE
+        self.observation_space = Box(np.full((n_obs,), -np.inf, dtype=np.float32), np.full((n_obs,), np.inf, dtype=np.float32))
+        self.action_space = Box(np.tile(np.array([9.81 - 1, -1., -1., -1.], dtype=np.float32), self.N_AGENTS),
+                                np.tile(np.array([9.81 + 1, 1., 1., 1.], dtype=np.float32), self.N_AGENTS))
         self.env_steps = torch.zeros(self.N_ENVS, dtype=torch.int64, device=self.swarm.device)
         self.steps_since_reset = 0
         self.last_action = None
@@ -343,6 +378,14 @@ class MRS:
         self.last_obs = Xk
         return Xk
 
+    def _env_offset(self):
+        """Global index of this process's first env: ENV_OFFSET, else RANK * N_ENVS under torchrun (every rank of
+        the documented one-process-per-GPU layout owns an equal shard), else 0."""
+        if self.ENV_OFFSET is not None:
+            return int(self.ENV_OFFSET)
+        import os
+        return int(os.environ.get('RANK', '0')) * self.N_ENVS if int(os.environ.get('WORLD_SIZE', '1')) > 1 else 0
+
     def _device_spawn_ok(self):
         """The default START_POS / START_ORI (MRS.py:53-54) can be sampled on the device."""
         if not isinstance(self.START_POS, _spawn.DefaultSpawn) or self.N_AGENTS > 32:
@@ -389,7 +432,7 @@ class MRS:
             self._spawn_count += 1
             self.spawn_failed = self.swarm.spawn(self.SEED * 1000003 + self._spawn_count, env_mask=env_mask,
                                                  z=(sp.z_low, sp.z_high), xy_radius=sp.xy_radius, xy_sigma=sp.xy_radius,
-                                                 yaw=(float(ori6[2]), float(ori6[5])))
+                                                 yaw=(float(ori6[2]), float(ori6[5])), env_offset=self._env_offset())
             if vel is not None or angvel is not None:
                 self.swarm.set_state(vel=vel, angvel=angvel, env_mask=env_mask)
         else:
@@ -420,7 +463,7 @@ class MRS:
         # fast path of a training loop: a float32 device tensor of the right size needs no conversion at all
         if (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.float32
                 and actions.is_contiguous() and actions.numel() == sw.S * adim and actions.device == sw.device
-                and not actions.requires_grad and self.CHECK_NAN is not True):
+                and not actions.requires_grad and self.CHECK_NAN is not True and actions.data_ptr() % 16 == 0):
             return actions.view(self.N_ENVS, self.N_AGENTS, adim)
         host = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
         actions = torch.as_tensor(actions).detach()
@@ -431,6 +474,8 @@ class MRS:
             if bool(torch.isnan(actions).any()):
                 raise Exception('The given action contains NaN:\n %s' % str(actions))      # MRS.py:247-248
         actions = actions.to(self.swarm.device).reshape(self.N_ENVS, self.N_AGENTS, adim).contiguous()
+        if actions.data_ptr() % 16:          # a view into the middle of a buffer: the kernels need 16-byte alignment
+            actions = actions.clone()
         return actions
 
     def step(self, actions, ACTION_TYPE=None):

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from .env import MRS
+from .spaces import Box
 
 
 class MRS_RLlib(MRS):
@@ -45,6 +46,12 @@ class MRS_RLlib_MultiAgent(MRS):
         params.update(config or {})
         self.action_fn = params.pop('action_fn', lambda action: action)
         super().__init__(**params)
+        # per-agent spaces (MRSWrapper.py:37-38 indexes the flat boxes of MRS as if they were 3-D and would raise;
+        # the evident intent -- one agent's observation and action box -- is what is built here)
+        self.observation_space = Box(np.full((self.STATE_SIZE,), -np.inf, dtype=np.float32),
+                                     np.full((self.STATE_SIZE,), np.inf, dtype=np.float32))
+        self.action_space = Box(self.action_space.low[:4][:max(self.swarm.action_dim, 1)],
+                                self.action_space.high[:4][:max(self.swarm.action_dim, 1)])
         names = ['agent%d' % (i + 1) for i in range(self.N_AGENTS)]
         self.names_dict = {n: i for i, n in enumerate(names)}
         self.env.names_dict = self.names_dict

@@ -212,3 +212,24 @@ def stepSimulation(physicsClientId=0):
         w.pos[i], w.quat[i], w.vel[i], w.angvel[i] = p1[r], q1[r], v1[r], w1[r]
         w.force[i] = np.zeros(3)
         w.torque[i] = np.zeros(3)
+
+
+# ----------------------------------------------------------------------------- introspection (tools/pin_bullet.py)
+def getDynamicsInfo(bodyUniqueId, linkIndex, physicsClientId=0):
+    """(mass, lateral friction, local inertia diagonal, inertial pos, inertial orn, restitution, rolling friction,
+    spinning friction, contact damping, contact stiffness, body type, collision margin) as pybullet returns it."""
+    w = _w(physicsClientId)
+    P = w.params
+    if w.kind[bodyUniqueId] == 'static':
+        return (0.0, 1.5, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0), 0.0, 0.0, 0.0, -1.0, -1.0, 1, 0.001)
+    return (P.mass, 0.5, tuple(P.inertia_diag()), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0), 0.0, 0.0, 0.0, -1.0, -1.0, 1,
+            P.col_margin)
+
+
+def getPhysicsEngineParameters(physicsClientId=0):
+    w = _w(physicsClientId)
+    P = w.params
+    return dict(fixedTimeStep=w.dt, numSubSteps=0, numSolverIterations=int(P.solver_iters), useRealTimeSimulation=0,
+                gravityAccelerationX=0.0, gravityAccelerationY=0.0, gravityAccelerationZ=-w.gravity,
+                erp=0.2, contactERP=P.erp2, frictionERP=0.2, contactSlop=P.slop,
+                solverResidualThreshold=1e-7, numNonContactInnerIterations=1)

@@ -227,3 +227,40 @@ def test_plain_c_caller_links_and_runs(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert 'baked 1' in r.stdout and 'action dim 4' in r.stdout
+
+
+def test_box_shim():
+    from mrsgym_b200.spaces import Box
+    b = Box(np.array([0.0, -1.0], dtype=np.float32), np.array([1.0, 1.0], dtype=np.float32))
+    assert b.shape == (2,)
+    x = b.sample()
+    assert x.shape == (2,) and b.contains(x) and not b.contains(np.array([2.0, 0.0], dtype=np.float32))
+    u = Box(np.full((3,), -np.inf, dtype=np.float32), np.full((3,), np.inf, dtype=np.float32))
+    assert u.sample().shape == (3,)
+
+
+def test_pin_bullet_runs_on_the_fake_backend():
+    """tools/pin_bullet.py (SURVEY.md 8a-P 'pin these first') is exercised on oracle/fake_pybullet so that it is known
+    to run the day a real pybullet wheel is importable; on the fake backend it reads the oracle's constants back."""
+    sys.path.insert(0, os.path.join(_REPO, 'tools'))
+    import importlib
+    pin = importlib.import_module('pin_bullet')
+    from oracle import bullet_model as bm
+    doc = pin.main(['--backend', 'fake', '--models', '/nonexistent/models'])
+    assert doc['backend'] == 'fake'
+    pp, pr = doc['PhysicsParams'], doc['probes']
+    P = bm.PhysicsParams()
+    assert abs(pr['gravity'] - 9.81) < 1e-9
+    assert abs(pp['lin_damping'] - P.lin_damping) < 1e-6 and abs(pp['ang_damping'] - P.ang_damping) < 1e-6
+    assert abs(pr['link0_arm_x'] - 0.028) < 1e-9 and abs(pr['link0_arm_y'] - 0.028) < 1e-9
+    assert pp['max_coord_vel'] == P.max_coord_vel and pp['gyro'] is True
+    np.testing.assert_allclose(pp['measured_inertia_diag'], P.inertia_diag(), rtol=1e-12)
+    assert abs(pr['rest']['height'] - (P.ground_z + P.col_halfheight + P.col_margin - P.slop)) < 1e-6
+    assert pr['tilted_landing']['body_z_dot_world_z'] > 0.999999
+    assert len(pr['one_step_goldens']) == 8
+    # the JSON loads back into the oracle's parameter set
+    import json, tempfile
+    with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
+        json.dump(doc, f)
+    P2 = bm.PhysicsParams.from_json(f.name)
+    assert P2.solver_iters == 50 and abs(P2.mu_ground - 0.75) < 1e-12

@@ -286,3 +286,137 @@ def test_analytic_sensors_vs_oracle():
     c = env.env.collision()
     assert tuple(c.shape) == (3, 4) and bool(c[:, 0].all())
     assert bool(c[:, 2].all()) and bool(c[:, 3].all()) and not bool(c[:, 1].any())
+
+
+def test_gym_spaces_like_the_reference():
+    """observation_space / action_space as MRS.py:51-52 builds them (flat boxes, the reference's own length
+    expression K_HOPS + 1 * N_AGENTS * STATE_SIZE), per-agent boxes on the multi-agent wrapper."""
+    import mrsgym_b200 as mrsgym
+    from mrsgym_b200.wrappers import MRS_RLlib, MRS_RLlib_MultiAgent
+    env = mrsgym.MRS(N_AGENTS=3, K_HOPS=2, START_POS=torch.tensor(H.grid_positions(1, 3)[0]), START_ORI=torch.zeros(3, 3))
+    assert env.observation_space.shape == (2 + 1 * 3 * 6,)
+    assert env.action_space.shape == (12,)
+    np.testing.assert_allclose(env.action_space.low[:4], [8.81, -1, -1, -1], rtol=1e-6)
+    np.testing.assert_allclose(env.action_space.high[4:8], [10.81, 1, 1, 1], rtol=1e-6)
+    a = env.action_space.sample()
+    assert a.shape == (12,) and env.action_space.contains(a)
+    cfg = dict(N_AGENTS=3, START_POS=torch.tensor(H.grid_positions(1, 3)[0]), START_ORI=torch.zeros(3, 3))
+    flat = MRS_RLlib(dict(cfg))
+    assert flat.observation_space.shape == (0 + 18,) and flat.action_space.shape == (12,)
+    multi = MRS_RLlib_MultiAgent(dict(cfg, ACTION_TYPE='set_control'))
+    assert multi.observation_space.shape == (6,) and multi.action_space.shape == (4,)
+
+
+def test_get_ori_mat_for_state_fn():
+    """Object.get_ori(mat=True) (Object.py:90-95) in a reference-style state_fn: [3, 3, E*N] body->world matrices."""
+    import mrsgym_b200 as mrsgym
+    from scipy.spatial.transform import Rotation as R
+    rpy = torch.tensor([[0.1, -0.2, 0.3], [0.0, 0.4, -1.0], [-0.3, 0.1, 2.0]])
+
+    def state_fn(quad):
+        m = quad.get_ori(mat=True)                       # [3, 3, S]
+        return torch.cat([quad.get_pos(), m[:, 2, :]])   # position + body z axis in world coordinates
+
+    env = mrsgym.MRS(state_fn=state_fn, N_AGENTS=3, START_POS=torch.tensor(H.grid_positions(1, 3)[0]), START_ORI=rpy)
+    X = env.reset()
+    assert tuple(X.shape) == (1, 3, 6)
+    want = R.from_euler('xyz', rpy.numpy()).as_matrix()[:, :, 2]
+    np.testing.assert_allclose(X[0, :, 3:].cpu().numpy(), want, atol=1e-6)
+    np.testing.assert_allclose(env.env.get_ori(mat=True).cpu().numpy(), R.from_euler('xyz', rpy.numpy()).as_matrix(), atol=1e-6)
+
+
+def test_contact_points_and_closest_objects():
+    """Object.get_contact_points / get_closest_objects (Object.py:100-141) on the contact geometry of the step"""
+    import mrsgym_b200 as mrsgym
+    pos = torch.tensor([[0.0, 0.0, 0.5135], [0.55, 0.0, 0.5135], [3.0, 0.0, 2.0]])      # two resting and touching, one aloft
+    env = mrsgym.MRS(N_AGENTS=3, START_POS=pos, START_ORI=torch.zeros(3, 3))
+    env.reset()
+    c = env.env.get_contact_points()
+    assert tuple(c['object'].shape) == (3, 5) and tuple(c['pos'].shape) == (3, 5, 3)
+    obj = c['object'].cpu().numpy()
+    assert obj[0, 0] == 1 and obj[1, 0] == 0 and obj[2, 0] == -1          # sphere contact 0 <-> 1
+    assert (obj[0, 1:] == 3).all() and (obj[1, 1:] == 3).all() and (obj[2, 1:] == -1).all()   # 3 = N_AGENTS = the ground
+    np.testing.assert_allclose(c['distance'][0, 0].item(), 0.55 - 0.6, atol=1e-6)
+    np.testing.assert_allclose(c['distance'][0, 1:].cpu().numpy(), 0.5135 - 0.0125 - 0.001 - 0.5, atol=1e-6)
+    np.testing.assert_allclose(c['pos'][0, 1].cpu().numpy(), [0.06, 0.0, 0.501], atol=1e-6)
+    np.testing.assert_allclose(c['normal'][0, 0].cpu().numpy(), [-1.0, 0.0, 0.0], atol=1e-6)
+    cb = env.env.get_contact_points(body=True)
+    np.testing.assert_allclose(cb['pos'][1, 3].cpu().numpy(), [-0.06, 0.0, -0.0125], atol=1e-6)
+    near = env.env.get_closest_objects(0.1)
+    assert near['mask'].cpu().numpy().tolist() == [[False, True, False], [True, False, False], [False, False, False]]
+
+
+def test_rpm_mirror_matches_the_reference_anchors():
+    """Swarm(keep_rpm=True): the rotor speeds the GPU controller commands against the reference's own numbers for the
+    seven anchor cases of SURVEY.md 8(c) (tests/golden/ref_anchor_*.npz, generated from /root/reference)."""
+    import glob
+    import mrsgym_b200 as M
+    files = sorted(glob.glob(os.path.join(GOLDEN, 'ref_anchor_*.npz')))
+    assert len(files) >= 7
+    for f in files:
+        g = np.load(f)
+        N, mode = int(g['N']), str(g['mode'])
+        sw = M.Swarm(1, N, 0, mode, M._abi.X_POS_VEL, float(g['comm_range']), keep_rpm=True)
+        st = {k: g['start_' + k][None].astype(np.float32) for k in ('pos', 'quat', 'vel', 'angvel')}
+        H.upload_state(sw, st)
+        sw.step(torch.from_numpy(g['actions'][0][None]).cuda())
+        rpm = sw.rpm.cpu().numpy().T.reshape(N, 4)
+        np.testing.assert_allclose(rpm, g['rpm'][0], rtol=2e-5, err_msg=os.path.basename(f))
+
+
+def test_shards_spawn_different_environments():
+    """mrs_spawn keys its draws by seed and GLOBAL env index: two shards of a job (ENV_OFFSET = the shard's first
+    env) sample different start states, and a shard equals the matching slice of the unsharded batch."""
+    import mrsgym_b200 as mrsgym
+    whole = mrsgym.MRS(N_AGENTS=4, N_ENVS=64, SEED=7)
+    lo = mrsgym.MRS(N_AGENTS=4, N_ENVS=32, SEED=7, ENV_OFFSET=0)
+    hi = mrsgym.MRS(N_AGENTS=4, N_ENVS=32, SEED=7, ENV_OFFSET=32)
+    pw, pl, ph = whole.env.get_pos(), lo.env.get_pos(), hi.env.get_pos()
+    assert torch.equal(pw[:32], pl) and torch.equal(pw[32:], ph)
+    assert not torch.equal(pl, ph)
+
+
+def test_batched_default_done_is_per_env():
+    import mrsgym_b200 as mrsgym
+    env = mrsgym.MRS(N_AGENTS=2, N_ENVS=3, MAX_TIMESTEPS=2)
+    a = torch.zeros(3, 2, 3, device='cuda')
+    for _ in range(2):
+        X, r, done, info = env.step(a)
+    assert done.tolist() == [False, False, False]         # evaluated before the counter is incremented (MRS.py:272-274)
+    env.reset(env_mask=torch.tensor([False, True, False]))
+    X, r, done, info = env.step(a)
+    assert done.tolist() == [True, False, True]
+
+
+def test_device_nan_action_does_not_poison_the_state():
+    """A NaN in a device-resident action cannot raise before the step (MRS.py:247-248 does for host actions): that
+    agent steps without rotor forces, keeps its PID state, the status bit is raised -- everything stays finite."""
+    import mrsgym_b200 as M
+    for N in (8, 40):
+        sw = M.Swarm(4, N, 0, 'set_target_vel', M._abi.X_POS_VEL, 2.0)
+        rng = np.random.default_rng(3)
+        st = H.random_state(rng, 4, N)
+        H.upload_state(sw, st)
+        act = torch.zeros(4, N, 3, device='cuda')
+        act[1, 2, 0] = float('nan')
+        ctrl0 = sw.ctrl.clone()
+        sw.step(act)
+        assert bool(torch.isfinite(sw.state).all())
+        s = 1 * N + 2
+        assert torch.equal(sw.ctrl[:, s].nan_to_num(nan=-7.0), ctrl0[:, s].nan_to_num(nan=-7.0))     # PID state untouched
+        assert sw.read_status() & M._abi.STATUS_NAN_ACTION
+        # the agent fell freely: no thrust
+        assert float(sw.state[9, s]) < float(st['vel'][1, 2, 2]) - 0.09
+
+
+def test_misaligned_action_views_are_handled():
+    import mrsgym_b200 as mrsgym
+    import mrsgym_b200 as M
+    env = mrsgym.MRS(N_AGENTS=2, N_ENVS=2, ACTION_TYPE='set_speeds', START_POS=torch.tensor(H.grid_positions(1, 2)[0]),
+                     START_ORI=torch.zeros(2, 3))
+    buf = torch.full((1 + 16,), 14475.8, device='cuda')
+    view = buf[1:].view(2, 2, 4)                      # 4 bytes into its storage: the kernels read float4 actions
+    assert view.data_ptr() % 16 != 0
+    env.step(view)                                    # MRS.step re-aligns
+    with pytest.raises(ValueError, match='16-byte'):
+        env.swarm.step(view)                          # the raw Swarm refuses instead of faulting
