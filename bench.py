@@ -70,6 +70,18 @@ def workload_config(w, E, world):
             'parallelism': 'env-shard x%d' % world}
 
 
+def kernel_sources_hash():
+    """sha256 over the CUDA sources of the library (csrc/*.cu, *.cuh, include/mrs_b200.h)."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(_REPO, 'mrs-gym_b200', 'csrc')
+    files = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith(('.cu', '.cuh'))]
+    files.append(os.path.join(_REPO, 'include', 'mrs_b200.h'))
+    for f in files:
+        h.update(open(f, 'rb').read())
+    return h.hexdigest()
+
+
 # ------------------------------------------------------------------------------ synthetic inputs
 def make_inputs(w, E, T, seed):
     import numpy as np
@@ -408,7 +420,7 @@ def run_gpu(args):
     n_e = min(steps, args.e2e_steps)
     h2d = E * N * adim * 4
     d2h = E * N * (6 + (N if sw.A_tape is not None else 0)) * 4
-    e2e_value = e2e_pipe_value = None
+    e2e_value = e2e_pipe_value = e2e_compact = pcie_gbs = None
     if n_e > 0:
         host_act = [torch.from_numpy(act_np[i % T]).pin_memory() for i in range(min(n_e, T))]
         dev_act = torch.empty(E, N, max(adim, 1), device=dev)
@@ -440,6 +452,27 @@ def run_gpu(args):
         barrier()
         pipe_ms = D.max_over_ranks(p0.elapsed_time(p1), dev)
         e2e_pipe_value = float(E) * N * n_p * world / (pipe_ms * 1e-3)
+        # opt-in compact adjacency on the wire: one bit per entry instead of one float32 (mrs_pack_adjacency)
+        e2e_compact = None
+        if sw.A_tape is not None:
+            Wd = (N + 31) // 32
+            Bhh = torch.empty(n_p, E, N, Wd, dtype=torch.int32).pin_memory()
+            devB = torch.empty(2, E, N, Wd, dtype=torch.int32, device=dev)
+            sw.rollout_host(ah, dev2, Xhh, None, Bhh, devB)
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            sw.rollout_host(ah, dev2, Xhh, None, Bhh, devB)
+            q1.record()
+            barrier()
+            cms = D.max_over_ranks(q0.elapsed_time(q1), dev)
+            d2h_c = E * N * (6 + Wd) * 4
+            e2e_compact = {'value': float(E) * N * n_p * world / (cms * 1e-3), 'unit': 'agent-steps/s',
+                           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_c,
+                           'pcie_gbs_per_rank': (h2d + d2h_c) * n_p / (cms * 1e-3) / 1e9,
+                           'api': 'mrs_rollout_host with Abits_host: newest X slice + the adjacency bit-packed (u32 per row)'}
+            del Bhh, devB
+        pcie_gbs = (h2d + d2h) * n_p / (pipe_ms * 1e-3) / 1e9
         del ah, Xhh, Ahh
 
     if world > 1:
@@ -455,10 +488,15 @@ def run_gpu(args):
     ms_per_step = ms / steps
     bytes_per_launch = float(E) * N * w['B']
     achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+    # DRAM bytes per launch of the dominant kernel come from an ncu --set full capture (profiles/traffic.json, written
+    # by tools/evidence_collect.py together with the hash of the kernel sources it was taken with): reported only
+    # when that hash matches the sources of the library that just ran, null otherwise -- never a stale number
     traffic = None
     tp = os.path.join(_REPO, 'profiles', 'traffic.json')
     if os.path.isfile(tp):
-        traffic = json.load(open(tp)).get(args.workload)
+        tj = json.load(open(tp))
+        if tj.get('kernel_sources_sha256') == kernel_sources_hash():
+            traffic = tj.get(args.workload)
     kernel = 'step_group_kernel<%s>' % w['mode'] if N <= 32 else 'step_pre/step_post/adjacency_tiled'
     out = {
         'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': steps,
@@ -491,7 +529,8 @@ def run_gpu(args):
                 'steps': n_e, 'api': 'mrs_rollout_host (C ABI, pinned host buffers; every step: H2D actions, kernel, D2H '
                                      'newest X and A; copies of neighbouring steps overlap the kernels)',
                 'sync_per_step': {'value': e2e_value, 'api': 'mrs_step_host (same copies, stream sync after every step)'},
-                'numa_bound': numa_bound},
+                'numa_bound': numa_bound, 'pcie_gbs_per_rank': pcie_gbs},
+        'e2e_compactA': e2e_compact,
         'gpu_launches': gpu_launches,
         'clocks': sampler.summary(),
         'status_word': sw_status,
@@ -558,7 +597,7 @@ def emit(obj):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c5', choices=sorted(WORKLOADS))

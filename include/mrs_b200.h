@@ -238,11 +238,20 @@ int mrs_tape_fill(const MrsConfig* cfg, const MrsBuffers* bufs, int which, int s
                   int count, void* stream);
 
 /* End-to-end step over HOST buffers (pinned recommended): H2D actions, mrs_step, D2H of the
- * newest X slice ([E][N][D]) and A slice ([E][N][N]); X_host / A_host may be NULL.
+ * newest X slice ([E][N][D]) and A slice ([E][N][N], and / or its bit-packed form, see mrs_pack_adjacency); X_host /
+ * A_host / Abits_host may be NULL.
  * dev_actions: caller-owned device staging float[E][N][ACTION_DIM].  Synchronises the
  * stream before returning (the reference's step is synchronous). */
 int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host,
-                  float* dev_actions, float* X_host, float* A_host, int slot_x, int slot_a, void* stream);
+                  float* dev_actions, float* X_host, float* A_host, unsigned int* Abits_host,
+                  unsigned int* dev_Abits, int slot_x, int slot_a, void* stream);
+
+/* Compact adjacency for the wire (opt-in; the float32 {0,1} matrix of MRS.calc_A stays the default): A float[E][N][N]
+ * -> bits u32[E][N][ceil(N/32)], bit j of word w of row i = A[i][32 w + j] != 0.  At C5 the newest A slice shrinks from
+ * 16.8 MB to 2.1 MB; the host paths are PCIe-bound, so this is what the caller with a bandwidth problem asks for:
+ * mrs_step_host / mrs_rollout_host take Abits_host (pinned host u32, [T] x that shape) + dev_Abits (caller-owned
+ * device staging: one such array for mrs_step_host, TWO for mrs_rollout_host) next to or instead of A_host. */
+int mrs_pack_adjacency(const MrsConfig* cfg, const float* A, unsigned int* bits, void* stream);
 
 /* On-device reset with the reference's DEFAULT start distribution for the envs selected by
  * env_mask (NULL = all): positions z ~ U[z_lo, z_hi], xy ~ N(0, xy_sigma) pulled onto the disc of
@@ -281,8 +290,8 @@ int mrs_raycast(const MrsConfig* cfg, const MrsBuffers* bufs, const float* direc
  * returning.  The open-loop rollout of examples/simulating_data/helper/DataGenerator.py:8-48 for a
  * caller whose actions and trajectory buffers live in host memory. */
 int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host,
-                     float* dev_actions, float* X_host, float* A_host, int T, int slot_x_first,
-                     int slot_a_first, void* stream);
+                     float* dev_actions, float* X_host, float* A_host, unsigned int* Abits_host,
+                     unsigned int* dev_Abits, int T, int slot_x_first, int slot_a_first, void* stream);
 
 /* ---- the one exchange step of the path: per-rollout statistics reduction across env shards (SURVEY.md §8b/§8e;
  * the reference runs one environment per process and has no counterpart, examples/simulating_data/helper/

@@ -118,6 +118,35 @@ adjacency_tiled_kernel(const float* __restrict__ pos, size_t cs, size_t as, floa
     }
 }
 
+// Compact adjacency for the wire: one bit per entry, ceil(N / 32) words per row (bit j of word w = A[i][32 w + j]).
+// One thread per row; a row of N <= 32 floats is read with 128-bit loads when N % 4 == 0.
+__global__ void __launch_bounds__(256)
+pack_adjacency_kernel(const float* __restrict__ A, unsigned* __restrict__ bits, size_t rows, int N, int W) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* row = A + r * (size_t)N;
+    for (int w = 0; w < W; ++w) {
+        unsigned m = 0u;
+        const int j1 = min(32, N - 32 * w);
+        if ((N & 3) == 0) {
+            for (int j = 0; j < j1; j += 4) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(row + 32 * w + j));
+                m |= (v.x != 0.f ? 1u : 0u) << j | (v.y != 0.f ? 2u : 0u) << j | (v.z != 0.f ? 4u : 0u) << j | (v.w != 0.f ? 8u : 0u) << j;
+            }
+        } else {
+            for (int j = 0; j < j1; ++j) m |= (row[32 * w + j] != 0.f ? 1u : 0u) << j;
+        }
+        bits[r * (size_t)W + w] = m;
+    }
+}
+
+static int launch_pack_adjacency(const float* A, unsigned* bits, int E, int N, cudaStream_t st) {
+    const size_t rows = (size_t)E * N;
+    const int W = (N + 31) / 32;
+    pack_adjacency_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(A, bits, rows, N, W);
+    return last_error();
+}
+
 // X of the current state (MRS.calc_Xk outside step)
 __global__ void __launch_bounds__(256)
 observe_x_kernel(const MrsBuffers b, unsigned S, int layout, int slot) {
@@ -884,8 +913,16 @@ int mrs_tape_fill(const MrsConfig* cfg, const MrsBuffers* bufs, int which, int s
     return last_error();
 }
 
+int mrs_pack_adjacency(const MrsConfig* cfg, const float* A, unsigned int* bits, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!A || !bits) return MRS_ERR_ARG;
+    return launch_pack_adjacency(A, bits, cfg->E, cfg->N, (cudaStream_t)stream);
+}
+
 int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host, float* dev_actions,
-                  float* X_host, float* A_host, int slot_x, int slot_a, void* stream) {
+                  float* X_host, float* A_host, unsigned int* Abits_host, unsigned int* dev_Abits, int slot_x, int slot_a,
+                  void* stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (!bufs) return MRS_ERR_ARG;
@@ -910,6 +947,14 @@ int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* act
                             cudaMemcpyDeviceToHost, st) != cudaSuccess)
             return MRS_ERR_CUDA;
     }
+    if (Abits_host && bufs->A_tape) {
+        if (!dev_Abits) return MRS_ERR_ARG;
+        rc = launch_pack_adjacency(bufs->A_tape + (size_t)slot_a * S * cfg->N, dev_Abits, cfg->E, cfg->N, st);
+        if (rc) return rc;
+        if (cudaMemcpyAsync(Abits_host, dev_Abits, S * ((cfg->N + 31) / 32) * sizeof(unsigned), cudaMemcpyDeviceToHost, st) !=
+            cudaSuccess)
+            return MRS_ERR_CUDA;
+    }
     return cudaStreamSynchronize(st) == cudaSuccess ? MRS_OK : MRS_ERR_CUDA;
 }
 
@@ -920,7 +965,7 @@ int mrs_step_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* act
 namespace {
 struct CopyLanes {
     cudaStream_t h2d = nullptr, d2h = nullptr;
-    cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, tail = nullptr;
+    cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr}, tail = nullptr;
     bool ok = false;
 };
 CopyLanes g_lanes[64];
@@ -935,7 +980,8 @@ CopyLanes* copy_lanes() {
                     cudaStreamCreateWithFlags(&fresh.d2h, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 2 && good; ++i)
             good = cudaEventCreateWithFlags(&fresh.up[i], cudaEventDisableTiming) == cudaSuccess &&
-                   cudaEventCreateWithFlags(&fresh.done[i], cudaEventDisableTiming) == cudaSuccess;
+                   cudaEventCreateWithFlags(&fresh.done[i], cudaEventDisableTiming) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&fresh.packed[i], cudaEventDisableTiming) == cudaSuccess;
         good = good && cudaEventCreateWithFlags(&fresh.tail, cudaEventDisableTiming) == cudaSuccess;
         if (!good) {                      // release whatever was created: the next call starts from scratch
             if (fresh.h2d) cudaStreamDestroy(fresh.h2d);
@@ -943,6 +989,7 @@ CopyLanes* copy_lanes() {
             for (int i = 0; i < 2; ++i) {
                 if (fresh.up[i]) cudaEventDestroy(fresh.up[i]);
                 if (fresh.done[i]) cudaEventDestroy(fresh.done[i]);
+                if (fresh.packed[i]) cudaEventDestroy(fresh.packed[i]);
             }
             if (fresh.tail) cudaEventDestroy(fresh.tail);
             (void)cudaGetLastError();
@@ -956,7 +1003,8 @@ CopyLanes* copy_lanes() {
 }  // namespace
 
 int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* actions_host, float* dev_actions,
-                     float* X_host, float* A_host, int T, int slot_x_first, int slot_a_first, void* stream) {
+                     float* X_host, float* A_host, unsigned int* Abits_host, unsigned int* dev_Abits, int T,
+                     int slot_x_first, int slot_a_first, void* stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (!bufs || T <= 0) return MRS_ERR_ARG;
@@ -968,7 +1016,8 @@ int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
     const size_t S = (size_t)cfg->E * cfg->N;
     const size_t abytes = S * adim * sizeof(float);
     const int D = mrs_state_dim(cfg->state_layout);
-    const size_t xelems = S * (size_t)D, aelems = S * (size_t)cfg->N;
+    const size_t xelems = S * (size_t)D, aelems = S * (size_t)cfg->N, belems = S * (size_t)((cfg->N + 31) / 32);
+    if (Abits_host && !dev_Abits) return MRS_ERR_ARG;
     // the copy lanes start after whatever the caller already queued on the compute stream
     if (cudaEventRecord(L->tail, st) != cudaSuccess) return MRS_ERR_CUDA;
     if (cudaStreamWaitEvent(L->h2d, L->tail, 0) != cudaSuccess) return MRS_ERR_CUDA;
@@ -984,7 +1033,16 @@ int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
         rc = step_impl(cfg, bufs, da, 1, slot_x_first - t, slot_a_first - t, stream);
         if (rc) return rc;
         if (cudaEventRecord(L->done[bsel], st) != cudaSuccess) return MRS_ERR_CUDA;
-        if ((X_host && bufs->X_tape && D > 0) || (A_host && bufs->A_tape)) {
+        if (Abits_host && bufs->A_tape) {
+            // pack the newest A slice on the compute stream into staging half `bsel`, once the D2H copy of step
+            // t - 2 out of that half is through (packed[bsel]); done[bsel] is recorded again behind the pack kernel
+            if (t >= 2 && cudaStreamWaitEvent(st, L->packed[bsel], 0) != cudaSuccess) return MRS_ERR_CUDA;
+            rc = launch_pack_adjacency(bufs->A_tape + (size_t)(slot_a_first - t) * aelems, dev_Abits + (size_t)bsel * belems, cfg->E,
+                                       cfg->N, st);
+            if (rc) return rc;
+            if (cudaEventRecord(L->done[bsel], st) != cudaSuccess) return MRS_ERR_CUDA;
+        }
+        if ((X_host && bufs->X_tape && D > 0) || (A_host && bufs->A_tape) || (Abits_host && bufs->A_tape)) {
             if (cudaStreamWaitEvent(L->d2h, L->done[bsel], 0) != cudaSuccess) return MRS_ERR_CUDA;
             if (X_host && bufs->X_tape && D > 0 &&
                 cudaMemcpyAsync(X_host + (size_t)t * xelems, bufs->X_tape + (size_t)(slot_x_first - t) * xelems,
@@ -994,6 +1052,12 @@ int mrs_rollout_host(const MrsConfig* cfg, const MrsBuffers* bufs, const float* 
                 cudaMemcpyAsync(A_host + (size_t)t * aelems, bufs->A_tape + (size_t)(slot_a_first - t) * aelems,
                                 aelems * sizeof(float), cudaMemcpyDeviceToHost, L->d2h) != cudaSuccess)
                 return MRS_ERR_CUDA;
+            if (Abits_host && bufs->A_tape) {
+                if (cudaMemcpyAsync(Abits_host + (size_t)t * belems, dev_Abits + (size_t)bsel * belems, belems * sizeof(unsigned),
+                                    cudaMemcpyDeviceToHost, L->d2h) != cudaSuccess)
+                    return MRS_ERR_CUDA;
+                if (cudaEventRecord(L->packed[bsel], L->d2h) != cudaSuccess) return MRS_ERR_CUDA;
+            }
         }
     }
     // join: the caller's stream continues only after the last copies

@@ -107,9 +107,10 @@ _SIGNATURES = {
     'mrs_tape_fill': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p]),
     'mrs_step_host': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_void_p, C.c_void_p,
-                                C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'mrs_pack_adjacency': (C.c_int, [C.POINTER(MrsConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
     'mrs_rollout_host': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'mrs_spawn': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_float, C.c_float,
                             C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     'mrs_proximity': (C.c_int, [C.POINTER(MrsConfig), C.POINTER(MrsBuffers), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -32,6 +32,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def unpack_adjacency(bits, N: int):
+    """Inverse of mrs_pack_adjacency: int32 [..., N, ceil(N/32)] -> float32 {0,1} [..., N, N]."""
+    b = bits.to(torch.int64) & 0xffffffff
+    j = torch.arange(N, device=bits.device)
+    return ((b[..., j // 32] >> (j % 32)) & 1).to(torch.float32)
+
+
 def shard_range(E_total: int, rank: int, world: int):
     """Contiguous env block owned by `rank`: [lo, hi)."""
     base, rem = divmod(E_total, world)
@@ -322,13 +329,15 @@ class Swarm:
         self.hx = hx
         return hx
 
-    def step_host(self, actions_host, dev_actions, X_host, A_host):
-        """mrs_step_host: pinned host actions in, newest X/A slice out, synchronous."""
+    def step_host(self, actions_host, dev_actions, X_host, A_host, Abits_host=None, dev_Abits=None):
+        """mrs_step_host: pinned host actions in, newest X/A slice out, synchronous.  Abits_host (pinned int32
+        [E,N,ceil(N/32)]) + dev_Abits (device staging of the same shape): the adjacency bit-packed for the wire."""
         self._check_actions(actions_host, host=True)
         hx = self._make_room(1) - 1 if self.X_tape is not None else 0
         ha = self._make_room(2) - 1 if self.A_tape is not None else 0
         _abi.check(self.lib.mrs_step_host(C.byref(self.cfg), C.byref(self.bufs), _ptr(actions_host), _ptr(dev_actions),
-                                          _ptr(X_host), _ptr(A_host), hx, ha, self._stream()), 'mrs_step_host')
+                                          _ptr(X_host), _ptr(A_host), _ptr(Abits_host), _ptr(dev_Abits), hx, ha, self._stream()),
+                   'mrs_step_host')
         self.launches += self._step_launches()
         if self.X_tape is not None:
             self.hx = hx
@@ -336,9 +345,10 @@ class Swarm:
             self.ha = ha
             self.a_empty = False
 
-    def rollout_host(self, actions_host, dev_actions2, X_host=None, A_host=None):
+    def rollout_host(self, actions_host, dev_actions2, X_host=None, A_host=None, Abits_host=None, dev_Abits2=None):
         """mrs_rollout_host: T steps from pinned host actions [T,E,N,A] with the newest X / A slice of
-        every step copied to pinned host arrays [T,E,N,D] / [T,E,N,N]; copies overlap the kernels.
+        every step copied to pinned host arrays [T,E,N,D] / [T,E,N,N] (and / or the adjacency bit-packed:
+        Abits_host int32 [T,E,N,ceil(N/32)] with dev_Abits2 [2,E,N,ceil(N/32)] device staging); copies overlap the kernels.
         Chunks at tape wrap-arounds."""
         T = int(actions_host.shape[0])
         self._check_actions(actions_host, T, host=True)
@@ -351,6 +361,7 @@ class Swarm:
                 C.byref(self.cfg), C.byref(self.bufs), _ptr(actions_host[done:done + n]), _ptr(dev_actions2),
                 _ptr(X_host[done:done + n]) if X_host is not None else C.c_void_p(0),
                 _ptr(A_host[done:done + n]) if A_host is not None else C.c_void_p(0),
+                _ptr(Abits_host[done:done + n]) if Abits_host is not None else C.c_void_p(0), _ptr(dev_Abits2),
                 n, hx - 1, ha - 1, self._stream()), 'mrs_rollout_host')
             self.launches += self._step_launches(n)
             if self.X_tape is not None:
@@ -474,6 +485,14 @@ class Swarm:
         _abi.check(self.lib.mrs_adjacency(C.byref(self.cfg), _ptr(pos), _ptr(A), self._stream()), 'mrs_adjacency')
         self.launches += 1
         return A
+
+    def pack_adjacency(self, A):
+        """mrs_pack_adjacency: float32 A [E,N,N] on the device -> int32 [E,N,ceil(N/32)] (bit j of word w = A[..., 32w+j])."""
+        A = A.contiguous()
+        out = torch.empty(self.E, self.N, (self.N + 31) // 32, dtype=torch.int32, device=self.device)
+        _abi.check(self.lib.mrs_pack_adjacency(self._cfg_ref, _ptr(A), _ptr(out), self._stream()), 'mrs_pack_adjacency')
+        self.launches += 1
+        return out
 
     def proximity(self, threshold=0.04):
         """mrs_proximity: dict of [E,N] tensors -- 'gap_agent' (to the nearest other agent), 'nearest'

@@ -229,7 +229,10 @@ class MRS:
         self.observation_space = Box(np.full((n_obs,), -np.inf, dtype=np.float32), np.full((n_obs,), np.inf, dtype=np.float32))
         self.action_space = Box(np.tile(np.array([9.81 - 1, -1., -1., -1.], dtype=np.float32), self.N_AGENTS),
                                 np.tile(np.array([9.81 + 1, 1., 1., 1.], dtype=np.float32), self.N_AGENTS))
-        self.env_steps = torch.zeros(self.N_ENVS, dtype=torch.int64, device=self.swarm.device)
+        # per-env steps since that env's last reset = _steps_total - _steps_at_reset[e]: stepping costs a Python
+        # increment, not a device launch; the tensor is materialised when somebody reads env_steps
+        self._steps_total = 0
+        self._steps_at_reset = torch.zeros(self.N_ENVS, dtype=torch.int64, device=self.swarm.device)
         self.steps_since_reset = 0
         self.last_action = None
         self.last_obs = None
@@ -256,6 +259,8 @@ class MRS:
         self.ACTION_DIM = self.swarm.action_dim
         self.env = Environment(self.swarm, squeeze=not self._batched)
         self._built_K = self.K_HOPS
+        self._cfg_key = None
+        self._last_mode = None
 
     def _call_state_fn(self, swarm):
         """User state_fn on the whole batch -> [E, N, D] float32."""
@@ -266,9 +271,14 @@ class MRS:
         return out.reshape(swarm.E, swarm.N, -1)
 
     def _sync_cfg(self):
-        """Attributes are mutable after construction in the reference (e.g. analytics.py:40)."""
+        """Attributes are mutable after construction in the reference (e.g. analytics.py:40).  The C struct is
+        rewritten only when one of them changed (a tuple compare per step instead of six ctypes stores)."""
         if self.K_HOPS != self._built_K:
             raise RuntimeError('K_HOPS cannot change after construction (tape geometry); build a new MRS')
+        key = (self.COMM_RANGE, self.AGENT_RADIUS, self.CONTACT_RADIUS, self.sim.DT, self.sim.GRAVITY, self.SOLVER_ITERS)
+        if key == self._cfg_key:
+            return
+        self._cfg_key = key
         c = self.swarm.cfg
         c.comm_range = float(self.COMM_RANGE)
         c.phys.agent_radius = float(self.AGENT_RADIUS)
@@ -276,6 +286,11 @@ class MRS:
         if self.SOLVER_ITERS is not None:
             c.phys.solver_iters = int(self.SOLVER_ITERS)
         c.dt, c.gravity = float(self.sim.DT), float(self.sim.GRAVITY)
+
+    @property
+    def env_steps(self):
+        """[E] int64: steps since each env's last (masked) reset."""
+        return self._steps_total - self._steps_at_reset
 
     # ------------------------------------------------------------------ observation windows
     def _shape(self, w):
@@ -367,7 +382,8 @@ class MRS:
     def _after_state_change(self):
         """Tail of MRS.reset / MRS.set (MRS.py:185-192): clear rings, steps := 0, start_fn, X0."""
         self.steps_since_reset = 0
-        self.env_steps.zero_()
+        self._steps_total = 0
+        self._steps_at_reset.zero_()
         if self.start_fn is not None:
             self.start_fn(self)
         self.swarm.reset_windows()
@@ -402,7 +418,7 @@ class MRS:
         per process, so this is the batched reading of MRS.reset's tail (MRS.py:185-192)."""
         sw = self.swarm
         m = torch.as_tensor(env_mask).to(sw.device).bool().reshape(sw.E)
-        self.env_steps[m] = 0
+        self._steps_at_reset[m] = self._steps_total
         if self.start_fn is not None:
             self.start_fn(self)
         if sw.X_tape is not None:
@@ -484,11 +500,14 @@ class MRS:
         if actions is not None:
             if ACTION_TYPE is None:
                 ACTION_TYPE = self.ACTION_TYPE
-            self.ACTION_DIM = self.swarm.set_action_type(ACTION_TYPE)
+            if ACTION_TYPE != self._last_mode:
+                self.ACTION_DIM = self.swarm.set_action_type(ACTION_TYPE)
+                self._last_mode = ACTION_TYPE
             actions = self._prep_actions(actions)
             self.last_action = actions if self._batched else actions[0]
         else:
             self.swarm.set_action_type(None)
+            self._last_mode = None
         self.swarm.step(actions)
         if self._layout == _abi.X_NONE:
             self.swarm.X_tape[self.swarm.hx] = self._call_state_fn(self.swarm)
@@ -507,7 +526,7 @@ class MRS:
         done = self.done_fn(X=Xk, Xlast=self.last_obs, **kw)
         self.last_loop_time = time.monotonic()
         self.steps_since_reset += 1
-        self.env_steps += 1
+        self._steps_total += 1
         return Xk, reward, done, info
 
     def step_many(self, actions, ACTION_TYPE=None):
@@ -520,12 +539,13 @@ class MRS:
         if ACTION_TYPE is None:
             ACTION_TYPE = self.ACTION_TYPE
         adim = self.swarm.set_action_type(ACTION_TYPE)
+        self._last_mode = ACTION_TYPE
         actions = torch.as_tensor(actions, dtype=torch.float32).to(self.swarm.device)
         T = actions.shape[0]
         actions = actions.reshape(T, self.N_ENVS, self.N_AGENTS, adim).contiguous()
         self.swarm.step_many(actions, T)
         self.steps_since_reset += T
-        self.env_steps += T
+        self._steps_total += T
         Xk = self.get_Xk()
         self.last_obs = Xk
         return Xk, self.get_Ak()

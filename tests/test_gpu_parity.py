@@ -747,3 +747,29 @@ def test_chained_rollout_equals_plain_steps(N, mode, E):
     assert torch.equal(a.X_tape, b.X_tape) and torch.equal(a.A_tape, b.A_tape)
     assert a.read_status() == 0 and b.read_status() == 0
     assert a.read_stats() == b.read_stats()
+
+
+@pytest.mark.parametrize('E,N', [(256, 8), (33, 16), (7, 32), (5, 40), (3, 100)])
+def test_packed_adjacency_on_the_wire_equals_float_adjacency(E, N):
+    """Opt-in compact adjacency of the host paths (mrs_pack_adjacency): unpacked bits == the float32 A the step wrote,
+    bit for bit, through mrs_step_host and the pipelined mrs_rollout_host (which may deliver both forms at once)."""
+    from mrsgym_b200.core import unpack_adjacency
+    K, T = 1, 7
+    rng = np.random.default_rng(5 + N)
+    st = H.random_state(rng, E, N)
+    act = H.random_actions(rng, 'set_speeds', T, E, N)
+    sw = _swarm(E, N, 'set_speeds', K, 1.3, tape_slots=16)
+    H.upload_state(sw, st)
+    W = (N + 31) // 32
+    ah = torch.from_numpy(act).pin_memory()
+    Xh = torch.empty(T, E, N, 6).pin_memory()
+    Ah = torch.empty(T, E, N, N).pin_memory()
+    Bh = torch.empty(T, E, N, W, dtype=torch.int32).pin_memory()
+    sw.rollout_host(ah, torch.empty(2, E, N, 4, device='cuda'), Xh, Ah, Bh, torch.empty(2, E, N, W, dtype=torch.int32, device='cuda'))
+    assert torch.equal(unpack_adjacency(Bh, N), Ah)
+    assert float(Ah.sum()) > 0 and float((1 - Ah).sum()) > 0            # the case has both zeros and ones
+    # compact form only, one synchronous step
+    B1 = torch.empty(E, N, W, dtype=torch.int32).pin_memory()
+    sw.step_host(ah[0], torch.empty(E, N, 4, device='cuda'), Xh[0], None, B1, torch.empty(E, N, W, dtype=torch.int32, device='cuda'))
+    assert torch.equal(unpack_adjacency(B1, N).cuda(), sw.A_window()[0])
+    assert torch.equal(unpack_adjacency(sw.pack_adjacency(sw.A_window()[0]), N), sw.A_window()[0])

@@ -10,14 +10,15 @@ import sys
 
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 O, P = os.path.join(R, 'gpurun_out'), os.path.join(R, 'profiles')
-TAG = sys.argv[1] if len(sys.argv) > 1 else 'r1'
+TAG = sys.argv[1] if len(sys.argv) > 1 else 'r2'
+sys.path.insert(0, R)
 
 
 def sh(cmd):
     return subprocess.run(cmd, shell=True, capture_output=True, text=True).stdout
 
 
-for w in ('c5', 'c2', 'c3', 'c4', 'c5v', 'c5p', 'reference_arm'):
+for w in ('c5', 'c5_200', 'c2', 'c3', 'c4', 'c5v', 'c5p', 'm64', 'reference_arm'):
     src = os.path.join(O, 'ev_bench_%s.json' % w)
     if os.path.isfile(src) and os.path.getsize(src) > 0:
         json.load(open(src))
@@ -68,7 +69,9 @@ if cold:
     traffic['c5'] = cold
 if warm:
     traffic['c5_warm'] = warm
-traffic['note'] = ('dram__bytes_read.sum + dram__bytes_write.sum per single-step launch of step_group_kernel<6,8,28,1>. c5: ncu --set '
+import bench
+traffic['kernel_sources_sha256'] = bench.kernel_sources_hash()
+traffic['note'] = ('dram__bytes_read.sum + dram__bytes_write.sum per single-step launch of step_group_kernel<6,8,7,1,0>. c5: ncu --set '
                    'full with cold L2 (profiles/%s_ncu_full_step_group_c5.csv; reads = state + actions = the algorithmic reads; '
                    'stores still resident in the 126 MB L2 at kernel end are not counted). c5_warm: --cache-control none '
                    '(profiles/%s_ncu_warm_cache_c5.csv): what a rollout step moves through DRAM (actions in, write-back out; the '
@@ -81,4 +84,8 @@ open(os.path.join(P, '%s_ncu_source_hotlines_c5.txt' % TAG), 'w').write(
     sh('python %s/tools/ncu_source_hotlines.py %s 30' % (R, src)))
 if os.path.isfile(os.path.join(O, 'ev_latency.txt')):
     shutil.copy(os.path.join(O, 'ev_latency.txt'), os.path.join(P, '%s_latency_small_batches.txt' % TAG))
+for name in ('ev_soak.txt', 'ev_gputest.log'):
+    if os.path.isfile(os.path.join(O, name)):
+        tail = open(os.path.join(O, name)).read().strip().splitlines()[-3:]
+        open(os.path.join(P, '%s_%s' % (TAG, name[3:])), 'w').write('\n'.join(tail) + '\n')
 print(json.dumps(traffic, indent=1))
