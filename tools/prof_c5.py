@@ -14,7 +14,7 @@ w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else 'c5']
 E, N, K = w['E'], w['N'], w['K']
 T = 24
 st, act = bench.make_inputs(w, E, T, 1)
-sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T + 2 * K + 2)
+sw = M.Swarm(E, N, K, w['mode'], M._abi.X_POS_VEL, w['R'], tape_slots=T + 2 * K + 2, want_A=w.get('A', True))
 H.upload_state(sw, st)
 actions = torch.from_numpy(act).cuda()
 for t in range(6):
