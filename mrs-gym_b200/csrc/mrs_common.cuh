@@ -225,6 +225,34 @@ inline int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// Programmatic dependent launch for the multi-kernel paths (N > 32: pre / contact / post): a kernel lets its
+// successor start launching at once and waits for its predecessor's completion + flush before it touches memory, so
+// launch latency and the prologue overlap the predecessor's tail.  Every kernel launched through launch_pdl calls
+// pdl_enter() first; without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+    static const int use_pdl = env_int("MRS_B200_PDL", 1);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid;
+    lc.blockDim = dim3(block);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = use_pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&lc, kernel, KArgs(args)...) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return MRS_ERR_CUDA;
+    }
+    return MRS_OK;
+}
+
 // largest float s with sqrt_rn(s) <= r  (see adjacency_pair)
 inline float adjacency_threshold(float r) {
     if (!(r >= 0.f)) return -1.f;          // negative or NaN range: nothing is adjacent

@@ -391,6 +391,7 @@ contact_env_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int n_flag, n_pair;
     __shared__ unsigned worst_bits;
+    pdl_enter();
     const int cap = blockDim.x, pcap = 4 * blockDim.x;
     int* fl_idx = reinterpret_cast<int*>(smem_raw);
     float* sp = reinterpret_cast<float*>(fl_idx + cap);            // [cap][3] pre-step positions
@@ -512,6 +513,7 @@ contact_env_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ 
 // contact were solved by contact_env_kernel), position / attitude integration, state store, newest X slice
 __global__ void __launch_bounds__(kBlock)
 step_post_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int slot) {
+    pdl_enter();
     const unsigned S = (unsigned)c.E * (unsigned)c.N;
     const unsigned gid = blockIdx.x * kBlock + threadIdx.x;
     const bool valid = gid < S;
@@ -565,14 +567,12 @@ int launch_contact_env(const MrsConfig& c, const Derived& d, const MrsBuffers& b
             return MRS_ERR_CUDA;
         configured[dev] = true;
     }
-    contact_env_kernel<<<(unsigned)c.E, threads, smem, st>>>(c, d, b);
-    return last_error();
+    return launch_pdl(contact_env_kernel, dim3((unsigned)c.E), (unsigned)threads, smem, st, c, d, b);
 }
 
 int launch_step_post(const MrsConfig& c, const Derived& d, const MrsBuffers& b, int slot, cudaStream_t st) {
     const size_t S = (size_t)c.E * c.N;
-    step_post_kernel<<<(unsigned)((S + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, d, b, slot);
-    return last_error();
+    return launch_pdl(step_post_kernel, dim3((unsigned)((S + kBlock - 1) / kBlock)), kBlock, 0, st, c, d, b, slot);
 }
 
 // ------------------------------------------------------------------------------ host side

@@ -874,6 +874,7 @@ template <int MODE, int LPA>
 __global__ void __launch_bounds__(kBlock)
 step_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
                 const float* __restrict__ actions) {
+    pdl_enter();
     const int N = c.N;
     const unsigned S = (unsigned)c.E * (unsigned)N;
     const unsigned gid = (blockIdx.x * kBlock + threadIdx.x) / LPA;      // agent slot of this lane group
@@ -945,6 +946,7 @@ __global__ void __launch_bounds__(kBlock)
 step_mid_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
                     const float* __restrict__ actions) {
     __shared__ float4 tile[kMidTile];
+    pdl_enter();
     const int N = c.N;
     const unsigned S = (unsigned)c.E * (unsigned)N;
     const unsigned s0 = blockIdx.x * (unsigned)kBlock;
@@ -1008,6 +1010,7 @@ __global__ void __launch_bounds__(kBlock)
 pair_tile_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b, int jw,
                  int nsplit) {
     __shared__ float4 tile[kBlock];
+    pdl_enter();
     const int N = c.N;
     const unsigned S = (unsigned)c.E * (unsigned)N;
     const int itiles = (N + kBlock - 1) / kBlock;
@@ -1086,6 +1089,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kBlock)
 agent_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
                  const float* __restrict__ actions, int nsplit) {
+    pdl_enter();
     const unsigned S = (unsigned)c.E * (unsigned)c.N;
     const unsigned s = blockIdx.x * kBlock + threadIdx.x;
     if (s >= S) return;
@@ -1204,10 +1208,14 @@ static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffer
         const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
         if constexpr (LPA > 32) {
             const int itiles = (c.N + kBlock - 1) / kBlock;
-            pair_tile_kernel<MODE><<<(unsigned)((long long)itiles * nsplit * c.E), kBlock, 0, st>>>(c, d, b, jw, nsplit);
-            agent_pre_kernel<MODE><<<(unsigned)((S + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, d, b, act_t, nsplit);
+            if (int rc = launch_pdl(pair_tile_kernel<MODE>, dim3((unsigned)((long long)itiles * nsplit * c.E)), kBlock, 0, st, c, d,
+                                    b, jw, nsplit))
+                return rc;
+            if (int rc = launch_pdl(agent_pre_kernel<MODE>, dim3((unsigned)((S + kBlock - 1) / kBlock)), kBlock, 0, st, c, d, b,
+                                    act_t, nsplit))
+                return rc;
         } else {
-            step_pre_kernel<MODE, LPA><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
+            if (int rc = launch_pdl(step_pre_kernel<MODE, LPA>, dim3(blocks), kBlock, 0, st, c, d, b, act_t)) return rc;
         }
         if (int rc = launch_contact_env(c, d, b, st)) return rc;
         if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
@@ -1238,7 +1246,7 @@ static int launch_mid(const MrsConfig& c, const Derived& d, const MrsBuffers& b,
     SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
     for (int t = 0; t < a.T; ++t) {
         const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
-        step_mid_pre_kernel<MODE><<<blocks, kBlock, 0, st>>>(c, d, b, act_t);
+        if (int rc = launch_pdl(step_mid_pre_kernel<MODE>, dim3(blocks), kBlock, 0, st, c, d, b, act_t)) return rc;
         if (int rc = launch_contact_env(c, d, b, st)) return rc;
         if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
         if (int rc = launch_step_post(c, d, b, a.slot_x - t, st)) return rc;

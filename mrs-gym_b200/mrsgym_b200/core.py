@@ -49,7 +49,7 @@ def shard_range(E_total: int, rank: int, world: int):
 class Swarm:
     def __init__(self, E: int, N: int, K: int = 0, action_type='set_target_vel', state_layout=_abi.X_POS_VEL,
                  comm_range=float('inf'), dt=0.01, gravity=9.81, agent_radius=0.3, device='cuda', contact_radius=None,
-                 tape_slots=None, want_A=True, custom_D=0, keep_rpm=False, ring=False):
+                 tape_slots=None, want_A=True, custom_D=0, keep_rpm=False, ring=False, fresh_tapes=False):
         self.lib = _abi.lib()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -104,6 +104,13 @@ class Swarm:
         self.hx = self.L - self.K - 1
         self.ha = self.L - self.K - 1
         self.ring = bool(ring)     # True: heads wrap around the tape, nothing is ever moved (graph rollouts)
+        # fresh tapes: a tape that has been written down to slot 0 (or is re-initialised by a reset) is not reused --
+        # the next slots come from a NEW tensor, so a window view handed out earlier is never overwritten and stays
+        # valid for as long as somebody holds it (reference semantics: every step returns fresh tensors) without a
+        # copy per step.  Only for small slots: one held view keeps its whole tape generation alive.
+        slot_bytes = 4 * self.S * (max(self.D, 0) + (self.N if want_A else 0))
+        self.fresh = bool(fresh_tapes) and not self.ring and slot_bytes * self.L <= (64 << 20)
+        self.generation = 0        # bumped whenever a fresh tape replaces the current one
         self.a_empty = True        # no A slice pushed since the last full reset (MRS.py:186)
         self._stats_sum = None     # result buffer of allreduce_stats(comm)
         self.launches = 0          # kernel launches issued through the ABI (bench: gpu_launches)
@@ -151,7 +158,12 @@ class Swarm:
         if self.ring:                # ring mode (graph rollouts): wrap around, nothing is moved
             return L
         tape = self.X_tape if which == 1 else self.A_tape
-        if tape is not None and K > 0 and which == 1 and self.cfg.state_layout == _abi.X_NONE:
+        if tape is not None and self.fresh:
+            new = torch.empty_like(tape)
+            if K > 0:
+                new[L - K:L] = tape[head:head + K]
+            self._swap_tape(which, new)
+        elif tape is not None and K > 0 and which == 1 and self.cfg.state_layout == _abi.X_NONE:
             tape[L - K:L] = tape[head:head + K].clone()      # python-written X (custom state_fn)
         elif tape is not None and K > 0:
             for i in range(K - 1, -1, -1):           # move the K newest slots to the top
@@ -165,6 +177,35 @@ class Swarm:
             self.ha = head
         return head
 
+    def _swap_tape(self, which, new):
+        if which == 1:
+            self.X_tape = new
+            if self.cfg.state_layout != _abi.X_NONE:
+                self.bufs.X_tape = new.data_ptr()
+        else:
+            self.A_tape = new
+            self.bufs.A_tape = new.data_ptr()
+        self.generation += 1
+
+    def renew_tapes(self):
+        """Fresh-tape mode: continue on new tapes (the current windows move to their top), so that an in-place edit
+        of the history -- a masked reset -- does not show through windows handed out earlier."""
+        if not self.fresh:
+            return
+        for which in (1, 2):
+            tape = self.X_tape if which == 1 else self.A_tape
+            if tape is None:
+                continue
+            head = self.hx if which == 1 else self.ha
+            n = min(self.K + 1, self.L - head)
+            new = torch.empty_like(tape)
+            new[self.L - n:] = tape[head:head + n]
+            self._swap_tape(which, new)
+            if which == 1:
+                self.hx = self.L - n
+            else:
+                self.ha = self.L - n
+
     def max_chunk(self):
         """Largest T a single mrs_step_many may take with this tape size."""
         return self.L - self.K
@@ -175,6 +216,11 @@ class Swarm:
         K, L = self.K, self.L
         self.hx = self.ha = L - K - 1
         st = self._stream()
+        if self.fresh:             # the windows handed out before the reset keep their contents
+            if self.X_tape is not None:
+                self._swap_tape(1, torch.empty_like(self.X_tape))
+            if self.A_tape is not None:
+                self._swap_tape(2, torch.empty_like(self.A_tape))
         if self.X_tape is not None:
             if write_X and self.cfg.state_layout != _abi.X_NONE:
                 _abi.check(self.lib.mrs_observe(C.byref(self.cfg), C.byref(self.bufs), self.hx, 1, 0, st), 'mrs_observe')

@@ -194,9 +194,7 @@ class MRS:
         self.reward_fn = reward_fn if (reward_fn is not None) else (lambda **kwargs: 0.0)
         # default done: steps since the last reset >= MAX_TIMESTEPS (MRS.py:39); batched: per env ([E] bool tensor,
         # a masked reset restarts the count of the selected envs only)
-        self.done_fn = done_fn if (done_fn is not None) else (
-            lambda **kwargs: (self.env_steps >= self.MAX_TIMESTEPS) if self._batched
-            else kwargs['steps_since_reset'] >= self.MAX_TIMESTEPS)
+        self.done_fn = done_fn if (done_fn is not None) else self._default_done
         self.info_fn = info_fn if (info_fn is not None) else (lambda **kwargs: {})
         self.update_fn = update_fn
         self.start_fn = start_fn
@@ -209,6 +207,7 @@ class MRS:
         self._batched = (self.N_ENVS > 1) if self.BATCHED is None else bool(self.BATCHED)
         self._copy = (not self._batched) if self.COPY_OBS is None else bool(self.COPY_OBS)
         self._views = {}
+        self._bases = {}
         # state_fn: None / 'pos_vel' / 'full' -> fused in the step kernel; callable -> python
         if state_fn is None:
             state_fn = 'pos_vel'
@@ -233,6 +232,8 @@ class MRS:
         # increment, not a device launch; the tensor is materialised when somebody reads env_steps
         self._steps_total = 0
         self._steps_at_reset = torch.zeros(self.N_ENVS, dtype=torch.int64, device=self.swarm.device)
+        self._uniform_reset = True      # no masked reset since the last full one: env_steps is the same for all envs
+        self._done_const = {}
         self.steps_since_reset = 0
         self.last_action = None
         self.last_obs = None
@@ -254,7 +255,8 @@ class MRS:
         self.swarm = Swarm(self.N_ENVS, self.N_AGENTS, self.K_HOPS, self.ACTION_TYPE, layout, self.COMM_RANGE,
                            dt=self.sim.DT, gravity=self.sim.GRAVITY, agent_radius=self.AGENT_RADIUS,
                            device=self.DEVICE, tape_slots=self.TAPE_SLOTS, want_A=True, custom_D=custom_D,
-                           contact_radius=self.CONTACT_RADIUS)
+                           contact_radius=self.CONTACT_RADIUS, fresh_tapes=self._copy)
+        self._clone = self._copy and not self.swarm.fresh      # fresh tapes: views stay valid, no copy per step
         self.STATE_SIZE = self.swarm.D
         self.ACTION_DIM = self.swarm.action_dim
         self.env = Environment(self.swarm, squeeze=not self._batched)
@@ -287,6 +289,19 @@ class MRS:
             c.phys.solver_iters = int(self.SOLVER_ITERS)
         c.dt, c.gravity = float(self.sim.DT), float(self.sim.GRAVITY)
 
+    def _default_done(self, **kwargs):
+        """MRS.py:39: steps since the last reset >= MAX_TIMESTEPS; batched: [E] bool.  While every env was last reset
+        at the same step (no masked reset since) the answer is one Python compare and a cached constant tensor."""
+        if not self._batched:
+            return kwargs['steps_since_reset'] >= self.MAX_TIMESTEPS
+        if self._uniform_reset:
+            flag = kwargs['steps_since_reset'] >= self.MAX_TIMESTEPS
+            t = self._done_const.get(flag)
+            if t is None:
+                t = self._done_const[flag] = torch.full((self.N_ENVS,), flag, dtype=torch.bool, device=self.swarm.device)
+            return t
+        return self.env_steps >= self.MAX_TIMESTEPS
+
     @property
     def env_steps(self):
         """[E] int64: steps since each env's last (masked) reset."""
@@ -299,7 +314,7 @@ class MRS:
             w = w.permute(1, 0, 2, 3)
         else:
             w = w[:, 0]
-        return w.clone() if self._copy else w
+        return w.clone() if self._clone else w
 
     def _window(self, which):
         """Newest-first K+1 window of tape `which` in the reference's layout.  The window of a given head slot
@@ -308,8 +323,15 @@ class MRS:
         sw = self.swarm
         head = sw.hx if which == 1 else sw.ha
         tape = sw.X_tape if which == 1 else sw.A_tape
-        if tape is None or self._copy or (sw.ring and head + sw.K + 1 > sw.L):     # copies / wrapped windows are fresh
+        if tape is None or (sw.ring and head + sw.K + 1 > sw.L):          # wrapped windows are assembled afresh
             return self._shape(sw.X_window() if which == 1 else sw.A_window())
+        if self._copy:
+            # one slice of a per-tape base view ([E, L, N, *] or, unbatched, [L, N, *]) instead of slice + index
+            b = self._bases.get(which)
+            if b is None or b[0] is not tape:
+                b = self._bases[which] = (tape, tape.permute(1, 0, 2, 3) if self._batched else tape[:, 0])
+            w = b[1][:, head:head + sw.K + 1] if self._batched else b[1][head:head + sw.K + 1]
+            return w.clone() if self._clone else w
         key = (which, head, tape.data_ptr())
         v = self._views.get(key)
         if v is None:
@@ -384,6 +406,7 @@ class MRS:
         self.steps_since_reset = 0
         self._steps_total = 0
         self._steps_at_reset.zero_()
+        self._uniform_reset = True
         if self.start_fn is not None:
             self.start_fn(self)
         self.swarm.reset_windows()
@@ -417,8 +440,10 @@ class MRS:
         := copies of X0, A history := zeros); the other envs keep theirs.  The reference has one env
         per process, so this is the batched reading of MRS.reset's tail (MRS.py:185-192)."""
         sw = self.swarm
+        sw.renew_tapes()
         m = torch.as_tensor(env_mask).to(sw.device).bool().reshape(sw.E)
         self._steps_at_reset[m] = self._steps_total
+        self._uniform_reset = False
         if self.start_fn is not None:
             self.start_fn(self)
         if sw.X_tape is not None:
@@ -480,6 +505,9 @@ class MRS:
         if (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.float32
                 and actions.is_contiguous() and actions.numel() == sw.S * adim and actions.device == sw.device
                 and not actions.requires_grad and self.CHECK_NAN is not True and actions.data_ptr() % 16 == 0):
+            if actions.dim() == (3 if self._batched else 2):      # already in the shape the callbacks see: no view at all
+                self.last_action = actions
+                return actions
             return actions.view(self.N_ENVS, self.N_AGENTS, adim)
         host = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
         actions = torch.as_tensor(actions).detach()
@@ -503,8 +531,10 @@ class MRS:
             if ACTION_TYPE != self._last_mode:
                 self.ACTION_DIM = self.swarm.set_action_type(ACTION_TYPE)
                 self._last_mode = ACTION_TYPE
+            self.last_action = None
             actions = self._prep_actions(actions)
-            self.last_action = actions if self._batched else actions[0]
+            if self.last_action is None:
+                self.last_action = actions if self._batched else actions[0]
         else:
             self.swarm.set_action_type(None)
             self._last_mode = None

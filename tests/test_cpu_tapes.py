@@ -52,7 +52,7 @@ class FakeLib:
         return 0
 
 
-def make_swarm(K, L, ring=False):
+def make_swarm(K, L, ring=False, fresh=False):
     sw = object.__new__(Swarm)              # bypass the CUDA-only constructor: host logic only
     sw.E, sw.N, sw.K, sw.L, sw.S, sw.D = 1, 1, K, L, 1, 1
     sw.cfg = _abi.MrsConfig()
@@ -67,6 +67,8 @@ def make_swarm(K, L, ring=False):
     sw.launches = 0
     sw.hx = sw.ha = L - K - 1
     sw.ring = ring
+    sw.fresh = fresh and not ring
+    sw.generation = 0
     sw.a_empty = True
     sw.lib = FakeLib(sw)
     sw._stream = lambda: None
@@ -102,11 +104,13 @@ class RefRings:
             self.A.append(0.0)
 
 
-@pytest.mark.parametrize('ring', [False, True])
+@pytest.mark.parametrize('ring', [False, True, 'fresh'])
 @pytest.mark.parametrize('K,L', [(0, 2), (0, 5), (1, 4), (2, 6), (3, 8), (3, 16), (5, 12)])
 def test_tape_windows_follow_the_reference_deques(K, L, ring):
     rnd = random.Random(K * 100 + L)
-    sw = make_swarm(K, L, ring)
+    fresh = ring == 'fresh'           # fresh tapes: windows handed out earlier are never overwritten
+    sw = make_swarm(K, L, ring is True, fresh)
+    held = []
     ref = RefRings(K)
     sw.reset_windows()
     ref.reset(float(sw.lib.serial))
@@ -130,12 +134,21 @@ def test_tape_windows_follow_the_reference_deques(K, L, ring):
             sw.reset_windows()
             ref.reset(float(sw.lib.serial))
         assert sw.X_window().flatten().tolist() == list(ref.X), (it, 'X')
+        if fresh:
+            if op > 0.97:
+                sw.renew_tapes()
+                assert sw.X_window().flatten().tolist() == list(ref.X)
+            held.append((sw.X_window(), list(ref.X), sw.A_window(), None if sw.a_empty else list(ref.A)))
         got_A = sw.A_window().flatten().tolist()
         if len(ref.A) == 0:
             assert sw.a_empty                            # empty deque: no window yet (reference would raise)
         else:
             assert not sw.a_empty and got_A == list(ref.A), (it, 'A')
         assert 0 <= sw.hx < L and 0 <= sw.ha <= L
+    for Xw, Xl, Aw, Al in held:
+        assert Xw.flatten().tolist() == Xl
+        assert Al is None or Aw.flatten().tolist() == Al
+    assert not fresh or sw.generation > 300 // L
 
 
 def test_capture_needs_room_and_action_checks():

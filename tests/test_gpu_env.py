@@ -420,3 +420,29 @@ def test_misaligned_action_views_are_handled():
     env.step(view)                                    # MRS.step re-aligns
     with pytest.raises(ValueError, match='16-byte'):
         env.swarm.step(view)                          # the raw Swarm refuses instead of faulting
+
+
+def test_single_env_windows_stay_valid_without_a_copy_per_step():
+    """N_ENVS = 1 hands out fresh tensors like the reference (MRS.py:87-110 builds X and A anew every step): a held
+    observation never changes afterwards, across tape renewals and resets, and equals what a copying env returns."""
+    import mrsgym_b200 as mrsgym
+    start = torch.tensor([[0., 0, 2], [1, 0, 2], [0, 1, 2.5], [1, 1, 3]])
+    kw = dict(N_AGENTS=4, K_HOPS=2, COMM_RANGE=1.2, ACTION_TYPE='set_target_vel', START_POS=start, START_ORI=torch.zeros(4, 3),
+              TAPE_SLOTS=8)
+    env = mrsgym.make('mrs-v0', **kw)
+    ref = mrsgym.make('mrs-v0', BATCHED=False, COPY_OBS=False, **kw)
+    assert env.swarm.fresh and not env._clone and not ref.swarm.fresh
+    g = torch.Generator().manual_seed(5)
+    held, want = [], []
+    gen0 = env.swarm.generation
+    for t in range(40):
+        if t == 25:
+            held.append((env.reset(), None)); want.append((ref.reset().clone(), None))
+        a = torch.randn(4, 3, generator=g) * 0.5
+        X, _, _, info = env.step(a)
+        Xr, _, _, infor = ref.step(a)
+        held.append((X, info['A'])); want.append((Xr.clone(), infor['A'].clone()))
+    assert env.swarm.generation > gen0 + 4          # the 8-slot tapes were renewed several times
+    for (X, A), (Xr, Ar) in zip(held, want):
+        assert torch.equal(X, Xr)
+        assert A is None or torch.equal(A, Ar)
