@@ -1208,18 +1208,18 @@ static int launch_wide_lpa(const MrsConfig& c, const Derived& d, const MrsBuffer
         const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
         if constexpr (LPA > 32) {
             const int itiles = (c.N + kBlock - 1) / kBlock;
-            if (int rc = launch_pdl(pair_tile_kernel<MODE>, dim3((unsigned)((long long)itiles * nsplit * c.E)), kBlock, 0, st, c, d,
+            if (int rc = launch_pdl(true, pair_tile_kernel<MODE>, dim3((unsigned)((long long)itiles * nsplit * c.E)), kBlock, 0, st, c, d,
                                     b, jw, nsplit))
                 return rc;
-            if (int rc = launch_pdl(agent_pre_kernel<MODE>, dim3((unsigned)((S + kBlock - 1) / kBlock)), kBlock, 0, st, c, d, b,
+            if (int rc = launch_pdl(true, agent_pre_kernel<MODE>, dim3((unsigned)((S + kBlock - 1) / kBlock)), kBlock, 0, st, c, d, b,
                                     act_t, nsplit))
                 return rc;
         } else {
-            if (int rc = launch_pdl(step_pre_kernel<MODE, LPA>, dim3(blocks), kBlock, 0, st, c, d, b, act_t)) return rc;
+            if (int rc = launch_pdl(false, step_pre_kernel<MODE, LPA>, dim3(blocks), kBlock, 0, st, c, d, b, act_t)) return rc;
         }
-        if (int rc = launch_contact_env(c, d, b, st)) return rc;
+        if (int rc = launch_contact_env(c, d, b, LPA > 32, st)) return rc;
         if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
-        if (int rc = launch_step_post(c, d, b, a.slot_x - t, st)) return rc;
+        if (int rc = launch_step_post(c, d, b, a.slot_x - t, LPA > 32, st)) return rc;
         if (b.A_tape) {
             cudaStream_t as = st;
             if (L) {
@@ -1246,10 +1246,10 @@ static int launch_mid(const MrsConfig& c, const Derived& d, const MrsBuffers& b,
     SideLane* L = (b.A_tape && a.T > 1) ? side_lane() : nullptr;
     for (int t = 0; t < a.T; ++t) {
         const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
-        if (int rc = launch_pdl(step_mid_pre_kernel<MODE>, dim3(blocks), kBlock, 0, st, c, d, b, act_t)) return rc;
-        if (int rc = launch_contact_env(c, d, b, st)) return rc;
+        if (int rc = launch_pdl(false, step_mid_pre_kernel<MODE>, dim3(blocks), kBlock, 0, st, c, d, b, act_t)) return rc;
+        if (int rc = launch_contact_env(c, d, b, false, st)) return rc;
         if (L && t > 0 && cudaStreamWaitEvent(st, L->adj_done, 0) != cudaSuccess) return MRS_ERR_CUDA;
-        if (int rc = launch_step_post(c, d, b, a.slot_x - t, st)) return rc;
+        if (int rc = launch_step_post(c, d, b, a.slot_x - t, false, st)) return rc;
         if (b.A_tape) {
             cudaStream_t as = st;
             if (L) {

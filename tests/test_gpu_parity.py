@@ -662,6 +662,31 @@ def test_tiled_pair_path_ragged(E, N, mode):
     assert torch.equal(sw.state, sw2.state)
 
 
+def test_wide_contact_dense_cluster_uses_the_round_walk():
+    """N > 32 with an agent that has more than 16 pairs in range (a clump of 18 agents, all within the 0.62 m contact
+    range of each other: 17 pairs each, 153 in the env): the per-env solver's level schedule does not apply and it
+    walks the tournament rounds instead -- same rows, same order as the oracle.  The overlaps are deep (impulses of
+    tens of m/s), so the comparison is relative to the largest velocity."""
+    E, N = 3, 48
+    rng = np.random.default_rng(4848)
+    st = H.random_state(rng, E, N, spacing=1.5, z0=3.0, jitter=0.05, tilt=0.05, vel=0.2, angvel=0.2)
+    clump = np.array([[i, j, k] for i in range(3) for j in range(3) for k in range(2)], np.float32) * 0.2
+    where = rng.permutation(N)[:18]
+    st['pos'][:, where] = (clump + np.array([10., 10., 3.], np.float32))[None] + rng.uniform(-0.004, 0.004, (E, 18, 3)).astype(np.float32)
+    act = H.random_actions(rng, 'set_target_vel', 1, E, N)
+    sw = _swarm(E, N, 'set_target_vel', 0)
+    H.upload_state(sw, st)
+    sw.step(_dev(act[0]))
+    ref = H.make_spec(E, N, 'set_target_vel', 0, float('inf'), st)
+    ref.step(act[0])
+    g1, r1 = H.read_state(sw), H.spec_state(ref)
+    scale = float(np.max(np.abs(r1['vel'])))
+    assert scale > 1.0 and sw.read_stats()['agent_contact_rows'] > 20 * E
+    assert sw.read_status() == 0
+    np.testing.assert_allclose(g1['vel'], r1['vel'], rtol=0, atol=3e-4 * scale)
+    np.testing.assert_allclose(g1['pos'], r1['pos'], rtol=0, atol=3e-6 * scale)
+
+
 def test_capture_rollout_leaves_the_swarm_untouched():
     """capture_rollout warms the launch path up outside the capture; that must not advance the swarm: a captured
     twin replayed once equals T plain steps from the same start, windows included."""
