@@ -551,6 +551,11 @@ __device__ __forceinline__ int tour_partner(int r, int i, int N) {
     }
     return (j >= N) ? i : j;
 }
+__device__ __forceinline__ int tour_round_small(int i, int j, int N) {    // i < j < N <= 32: 32-bit arithmetic
+    const int M = N + (N & 1), m1 = M - 1;
+    if (j == m1) return i;
+    return ((i + j) * (M / 2)) % m1;
+}
 __device__ __forceinline__ int tour_round(int i, int j, int N) {          // i < j < N
     const int M = N + (N & 1), m1 = M - 1;
     if (j == m1) return i;

@@ -62,20 +62,22 @@ __device__ __forceinline__ const float* plane_ptr(const float* p0, unsigned S, i
 // changed the register allocation and instruction scheduling of the hot loop (+1.3 us per C5 step, measured with
 // the path compiled in but never taken), and inside the loop its loop-invariant set-up was hoisted to the top of the
 // kernel (~290 instructions and a stack frame per warp).
-// Same arithmetic as the fast path for everything but the contact rows; plain (unrolled-free) loops.
+// Same arithmetic as the fast path for everything but the contact rows.  GT = the compile-time group width of the
+// full-chunk kernels (8 / 16 / 32 = N), 0 = run-time width.
 // In-warp solve: every lane owns one agent, its ground rows and -- per tournament round -- the pair rows with its
 // round partner; the partner's velocity travels by shuffle, both lanes of a pair evaluate the same rows from their
 // own side and get equal and opposite changes.
-template <int MODE>
+template <int MODE, int GT>
 static __device__ __noinline__ void chunk_step_contact(const MrsConfig* cptr, const Derived* dptr, const MrsBuffers* bptr,
-                                                       const StepArgs* aptr, int G, int chunk, int t0, int T, unsigned lane_mask,
+                                                       const StepArgs* aptr, int G_in, int chunk, int t0, int T, unsigned lane_mask,
                                                        float4* wpos, unsigned* sh_events) {
     const MrsConfig& c = *cptr;
     const Derived& d = *dptr;
     const MrsBuffers& b = *bptr;
     const StepArgs& a = *aptr;
     const int lane = threadIdx.x & 31;
-    const int N = c.N, E = c.E;
+    const int G = GT ? GT : G_in;                       // full-chunk kernels: group width = N = GT at compile time
+    const int N = GT ? GT : c.N, E = c.E;
     const int gpw = 32 / G, ai = lane & (G - 1), gb = lane - ai;
     const unsigned S = (unsigned)E * (unsigned)N;
     const int e = chunk * gpw + (lane / G);
@@ -118,16 +120,19 @@ static __device__ __noinline__ void chunk_step_contact(const MrsConfig* cptr, co
     __syncwarp();
     wpos[lane] = make_float4(st.px, st.py, st.pz, 0.f);
     __syncwarp();
+    // ... and the rounds of the tournament in which some pair of this warp is in range (positions do not change
+    // during the solve): every lane marks the rounds of its own pairs, the warp ORs them
     float dw = 0.f;
-    bool near = false;
-    for (int r = 1; r < G; ++r) {
+    unsigned my_rounds = 0u;
+#pragma unroll
+    for (int r = 1; r < (GT ? GT : G); ++r) {
         const int j = ai ^ r;
         if (j < N) {
             const float4 pj = wpos[gb + j];
             const float rx = pj.x - st.px, ry = pj.y - st.py, rz = pj.z - st.pz;
             const float dxy2 = rx * rx + ry * ry;
             if (MODE != MRS_NO_ACTION) dw += downwash_pair(c.quad, d, dxy2, rz);
-            near = near || (dxy2 + rz * rz < cp.lim2);
+            if (dxy2 + rz * rz < cp.lim2) my_rounds |= 1u << tour_round_small(min(ai, j), max(ai, j), N);
         }
     }
     if (nan_act) dw = 0.f;
@@ -137,24 +142,24 @@ static __device__ __noinline__ void chunk_step_contact(const MrsConfig* cptr, co
     GroundRows g;
     g.act = 0u;
     if (gcand) ground_setup(cp, st.pz, R, g);
-    // rounds in which some pair of this warp is in range (positions do not change during the solve)
-    unsigned ract = 0u;
-    if (__any_sync(kFull32, cp.agent_contact && near && valid)) {
-        const int rounds = N + (N & 1) - 1;
-        for (int r = 0; r < rounds; ++r) {
-            const int j = valid ? tour_partner(r, ai, N) : ai;
-            const float4 pj = wpos[gb + j];
-            const float dx = st.px - pj.x, dy = st.py - pj.y, dz = st.pz - pj.z;
-            const bool in = (j != ai) && (dx * dx + dy * dy + dz * dz < cp.lim2);
-            if (__any_sync(kFull32, in)) ract |= 1u << r;
-        }
-    }
+    const unsigned ract = __reduce_or_sync(kFull32, (cp.agent_contact && valid) ? my_rounds : 0u);
     if (__any_sync(kFull32, g.act != 0u) || ract) {
         float lam_g[4] = {0.f, 0.f, 0.f, 0.f}, fl[2] = {0.f, 0.f};
-        float lam_p[3 * 31];
-        for (unsigned m = ract; m; m &= m - 1u) {
-            const int r = __ffs(m) - 1;
-            lam_p[3 * r] = lam_p[3 * r + 1] = lam_p[3 * r + 2] = 0.f;
+        // pair impulses, three per round.  N = 8: seven rounds, walked by an unrolled loop so that the impulses stay in
+        // registers and the partner of a round is a compile-time function of the lane; wider groups index the
+        // array by the round (local memory) and walk only the occupied rounds
+        constexpr bool kStaticRounds = false;   // measured at N = 8: the unrolled walk makes the sweep loop 1170 instructions
+                                                // (instruction-fetch stalls), 165 vs 150 us per step on the collapsed C5 swarm
+        constexpr int kRoundsMax = GT ? GT - 1 : 31;
+        float lam_p[3 * kRoundsMax];
+        if constexpr (kStaticRounds) {
+#pragma unroll
+            for (int i = 0; i < 3 * kRoundsMax; ++i) lam_p[i] = 0.f;
+        } else {
+            for (unsigned m = ract; m; m &= m - 1u) {
+                const int r = __ffs(m) - 1;
+                lam_p[3 * r] = lam_p[3 * r + 1] = lam_p[3 * r + 2] = 0.f;
+            }
         }
         float v[3] = {st.vx, st.vy, st.vz};
         float wb[3] = {R[0] * st.wx + R[3] * st.wy + R[6] * st.wz, R[1] * st.wx + R[4] * st.wy + R[7] * st.wz,
@@ -162,21 +167,31 @@ static __device__ __noinline__ void chunk_step_contact(const MrsConfig* cptr, co
         // An env stops sweeping when ITS rows have converged (like the oracle), whatever the other envs of the warp
         // do: its result does not depend on which envs it shares a warp with (shard invariance).
         bool alive = valid;
+        float worst;
+        auto do_round = [&](int r, float* lam3) {
+            const int j = valid ? tour_partner(r, ai, N) : ai;
+            const float vj[3] = {__shfl_sync(kFull32, v[0], gb + j), __shfl_sync(kFull32, v[1], gb + j),
+                                 __shfl_sync(kFull32, v[2], gb + j)};
+            if (alive && j != ai) {
+                const float4 pj = wpos[gb + j];
+                float dv[3];
+                bool on;
+                const float wr = pair_rows(cp, st.px - pj.x, st.py - pj.y, st.pz - pj.z, v, vj, lam3, dv, on);
+                v[0] += dv[0]; v[1] += dv[1]; v[2] += dv[2];
+                worst = fmaxf(worst, wr);
+            }
+        };
         for (int it = 0; it < cp.solver_iters; ++it) {
-            float worst = 0.f;
+            worst = 0.f;
             if (alive && g.act) worst = ground_sweep(cp, g, lam_g, fl, v, wb);
-            for (unsigned m = ract; m; m &= m - 1u) {
-                const int r = __ffs(m) - 1;
-                const int j = valid ? tour_partner(r, ai, N) : ai;
-                const float vj[3] = {__shfl_sync(kFull32, v[0], gb + j), __shfl_sync(kFull32, v[1], gb + j),
-                                     __shfl_sync(kFull32, v[2], gb + j)};
-                if (alive && j != ai) {
-                    const float4 pj = wpos[gb + j];
-                    float dv[3];
-                    bool on;
-                    const float wr = pair_rows(cp, st.px - pj.x, st.py - pj.y, st.pz - pj.z, v, vj, lam_p + 3 * r, dv, on);
-                    v[0] += dv[0]; v[1] += dv[1]; v[2] += dv[2];
-                    worst = fmaxf(worst, wr);
+            if constexpr (kStaticRounds) {
+#pragma unroll
+                for (int r = 0; r < kRoundsMax; ++r)
+                    if ((ract >> r) & 1u) do_round(r, lam_p + 3 * r);
+            } else {
+                for (unsigned m = ract; m; m &= m - 1u) {
+                    const int r = __ffs(m) - 1;
+                    do_round(r, lam_p + 3 * r);
                 }
             }
             if (alive) ++n_sweeps;
@@ -189,8 +204,14 @@ static __device__ __noinline__ void chunk_step_contact(const MrsConfig* cptr, co
         st.wy = R[3] * wb[0] + R[4] * wb[1] + R[5] * wb[2];
         st.wz = R[6] * wb[0] + R[7] * wb[1] + R[8] * wb[2];
         if ((lam_g[0] + lam_g[1]) + (lam_g[2] + lam_g[3]) > 0.f) ++n_ground;
-        for (unsigned m = ract; m; m &= m - 1u)
-            if (lam_p[3 * (__ffs(m) - 1)] > 0.f) ++n_agent_rows;
+        if constexpr (kStaticRounds) {
+#pragma unroll
+            for (int r = 0; r < kRoundsMax; ++r)
+                if (((ract >> r) & 1u) && lam_p[3 * r] > 0.f) ++n_agent_rows;
+        } else {
+            for (unsigned m = ract; m; m &= m - 1u)
+                if (lam_p[3 * (__ffs(m) - 1)] > 0.f) ++n_agent_rows;
+        }
     }
     integrate(c, d, st);
     if (!agent_finite(st)) status |= MRS_STATUS_NONFINITE;
@@ -289,7 +310,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     // shared memory, one contiguous region per warp so that every address is one per-warp base plus an
     // immediate: [32 positions] (the pair tile, 512 B) [prefetch stage]
     constexpr int kWarpBytes = group_warp_smem_bytes<MODE, GT>();
-    __shared__ int sh_counter, sh_hi, sh_range, sh_lo;
+    __shared__ int sh_counter, sh_hi, sh_range, sh_lo, sh_pull;
     __shared__ unsigned sh_epoch;
     __shared__ unsigned sh_events[7];       // CTA-level status word + the six statistics counters
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -320,6 +341,7 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
     const int T = MANY ? a.T : 1;
     const int gw = blockIdx.x * WPB + wib;
     if (threadIdx.x < 7) sh_events[threadIdx.x] = 0u;
+    if (threadIdx.x == 7) sh_pull = 0;
     const int role = kHand ? a.role : 0;
     if (role == 2) {
         asm volatile("griddepcontrol.launch_dependents;");
@@ -780,15 +802,21 @@ step_group_kernel(const __grid_constant__ MrsConfig c_in, const __grid_constant_
         }
     }
 #ifndef MRS_EXP_NOCALL
-    // ---- the chunks this warp parked: contact path
-    if (my_parked) {
-        __syncwarp();
-        const int i_end = kLocal ? sh_hi - sh_lo : (wib + 1) * rounds_static;
-        for (int i = kLocal ? 0 : wib * rounds_static; i < i_end; ++i) {
+    // ---- the parked chunks: contact path.  Shared out over the CTA's warps through a counter (a chunk's solve takes
+    // anything from one sweep to solver_iters, so the warp that parked a chunk is not the one that has to redo it);
+    // in free flight this is one CTA-wide vote.
+    if (__syncthreads_or(my_parked)) {
+        const int n_slots = kLocal ? sh_hi - sh_lo : WPB * rounds_static;
+        for (;;) {
+            int i = 0;
+            if (lane == 0) i = atomicAdd(&sh_pull, 1);
+            i = __shfl_sync(kFull32, i, 0);
+            if (i >= n_slots) break;
             const unsigned e = parked[i];
-            if (e == 0xffffffffu || (int)(e >> 16) != wib) continue;
-            const int pc = kLocal ? sh_lo + i : a.chunk_lo + gw + (i - wib * rounds_static) * wtotal;
-            chunk_step_contact<MODE>(&c_in, &d_in, &b, &a, GT ? GT : a.G, pc, (int)(e & 0xffffu), T, kFull32, wpos, sh_events);
+            if (e == 0xffffffffu) continue;
+            const int w = (int)(e >> 16);
+            const int pc = kLocal ? sh_lo + i : a.chunk_lo + blockIdx.x * WPB + w + (i - w * rounds_static) * wtotal;
+            chunk_step_contact<MODE, GT>(&c_in, &d_in, &b, &a, GT ? GT : a.G, pc, (int)(e & 0xffffu), T, kFull32, wpos, sh_events);
         }
     }
 #endif
