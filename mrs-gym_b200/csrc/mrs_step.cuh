@@ -21,6 +21,7 @@
 // Bullet step restated in oracle/bullet_model.py.  No CPU fallback exists in this library.
 #pragma once
 #include "mrs_common.cuh"
+#include "mrs_contact_env.cuh"
 
 namespace mrs {
 
@@ -1022,6 +1023,158 @@ step_mid_pre_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__
     if (valid) agent_pre<MODE>(c, d, b, actions, S, s, dw, near && pair_contact);
 }
 
+// ------------------------------------------------------------------------------ 32 < N <= 128, many envs: the whole step in one launch
+// One CTA per env, one thread per agent (blockDim = N rounded up to a warp).  The same arithmetic as the three-kernel
+// path above (pair loop of step_mid_pre_kernel, agent_pre, contact_env_body, step_post_kernel, adjacency rows), in the
+// same order (results equal to the bit for all modes but set_control, whose mixer ptxas contracts differently in
+// the two kernels: float32 rounding there) -- but the unconstrained velocities stay in registers, the
+// scratch planes are touched only by an env that has a pair in contact range (CTA-wide vote), and the env's slice of
+// A is written by the CTA that has just moved its agents (row-contiguous 16-byte stores) instead of a fourth kernel
+// on a side stream.  At 1024 envs x 64 agents: one launch per step instead of four.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, 4)
+step_env_kernel(const __grid_constant__ MrsConfig c, const __grid_constant__ Derived d, const MrsBuffers b,
+                const float* __restrict__ actions, int slot_x, float* __restrict__ A_slice) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float4 tile[kBlock];
+    pdl_enter();
+    const int N = c.N, tid = threadIdx.x;
+    const unsigned S = (unsigned)c.E * (unsigned)N;
+    const unsigned env0 = blockIdx.x * (unsigned)N;
+    const bool valid = tid < N;
+    const unsigned s = env0 + (unsigned)(valid ? tid : N - 1);
+    const MrsPhysicsParams& ph = c.phys;
+    Agent st;
+    Ctrl k;
+    load_agent(b.state, S, s, st);
+    load_ctrl<MODE>(b.ctrl, S, s, k);
+    tile[tid] = make_float4(st.px, st.py, st.pz, 0.f);
+    __syncthreads();
+    // ---- pair pass (step_mid_pre_kernel's loop)
+    const float4 me = tile[valid ? tid : N - 1];
+    const bool pair_contact = ph.agent_contact && N > 1;
+    const unsigned lim_m1 = __float_as_uint(d.lim2) - 1u;
+    float dw = 0.f;
+    bool near = false;
+    for (int j0 = 0; j0 < N; j0 += 4) {
+        float dxy2[4], rz[4];
+        bool live[4], any_live = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = min(j0 + u, N - 1);
+            const bool in = j0 + u < N;
+            const float4 pj = tile[j];
+            const float rx = pj.x - me.x, ry = pj.y - me.y;
+            rz[u] = pj.z - me.z;
+            dxy2[u] = rx * rx + ry * ry;
+            const float d2 = dxy2[u] + rz[u] * rz[u];
+            near = near || (in && __float_as_uint(d2) - 1u < lim_m1);
+            const float beta = c.quad.dw2 * rz[u] + c.quad.dw3;
+            live[u] = MODE != MRS_NO_ACTION && in && rz[u] > 0.f && dxy2[u] < 100.f && !(dxy2[u] > 208.f * beta * beta);
+            any_live = any_live || live[u];
+        }
+        if (MODE != MRS_NO_ACTION && __any_sync(kFull32, any_live)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float f = downwash_pair(c.quad, d, dxy2[u], rz[u]);
+                dw += live[u] ? f : 0.f;
+            }
+        }
+    }
+    near = near && pair_contact && valid;
+    // ---- per-agent part (agent_pre): controller -> rotor wrench + aero -> unconstrained velocities, in registers
+    const float pix = st.px, piy = st.py, piz = st.pz;
+    float act[4];
+    unsigned status = 0;
+    if (valid && load_action<MODE>(actions, s, act)) status |= MRS_STATUS_NAN_ACTION;
+    float R[9], rpm[4];
+    quat_to_mat(st, R);
+    if (status) {
+        rpm[0] = rpm[1] = rpm[2] = rpm[3] = 0.f;
+        dw = 0.f;
+    } else {
+        action_to_rpm<MODE>(c, c.quad, d, st, R, act, k, rpm);
+    }
+    apply_wrench<MODE != MRS_NO_ACTION>(c, d, st, R, rpm, dw);
+    if (valid) {
+        store_ctrl<MODE>(b.ctrl, S, s, k);
+        if (b.rpm && MODE != MRS_NO_ACTION) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b.rpm[i * (size_t)S + s] = rpm[i];
+        }
+    }
+    // ---- joint contact solve, only for an env that has a pair in range
+    if (__syncthreads_or(near)) {
+        float* sc = b.scratch;
+        if (valid) {
+            sc[0 * (size_t)S + s] = st.vx; sc[1 * (size_t)S + s] = st.vy; sc[2 * (size_t)S + s] = st.vz;
+            sc[3 * (size_t)S + s] = pix; sc[4 * (size_t)S + s] = piy; sc[5 * (size_t)S + s] = piz;
+            sc[6 * (size_t)S + s] = near ? 1.f : 0.f;
+            b.state[10 * (size_t)S + s] = st.wx; b.state[11 * (size_t)S + s] = st.wy; b.state[12 * (size_t)S + s] = st.wz;
+        }
+        __syncthreads();
+        contact_env_body(c, d, b, blockIdx.x, smem_raw);
+        __syncthreads();
+        if (near) {
+            st.vx = sc[0 * (size_t)S + s]; st.vy = sc[1 * (size_t)S + s]; st.vz = sc[2 * (size_t)S + s];
+            st.wx = b.state[10 * (size_t)S + s]; st.wy = b.state[11 * (size_t)S + s]; st.wz = b.state[12 * (size_t)S + s];
+        }
+    }
+    // ---- post (step_post_kernel): ground-only solve for agents that touch nothing else, integration, state, X
+    unsigned gnd = 0, bad = 0;
+    if (valid) {
+        if (ph.ground_contact && !near && st.pz < d.gnd_skip_z) {
+            if (ground_solve(make_contact_params(ph, d), st, R)) gnd = 1;
+        }
+        integrate(c, d, st);
+        store_agent(b.state, S, s, st);
+        if (b.X_tape && c.state_layout != MRS_X_NONE)
+            write_X(b.X_tape + (size_t)slot_x * S * state_dim(c.state_layout), c.state_layout, s, st);
+        bad = agent_finite(st) ? 0u : 1u;
+    }
+    {
+        const unsigned w_gnd = __reduce_add_sync(kFull32, gnd);
+        const unsigned w_bad = __reduce_add_sync(kFull32, bad);
+        const unsigned w_nan = __reduce_add_sync(kFull32, status ? 1u : 0u);
+        if ((tid & 31) == 0) {
+            if ((w_bad || w_nan) && b.status)
+                atomicOr(b.status, (w_bad ? MRS_STATUS_NONFINITE : 0u) | (w_nan ? MRS_STATUS_NAN_ACTION : 0u));
+            if (b.stats) {
+                if (w_gnd) atomicAdd(b.stats + MRS_STAT_GROUND_CONTACTS, (unsigned long long)w_gnd);
+                if (w_bad) atomicAdd(b.stats + MRS_STAT_NONFINITE, (unsigned long long)w_bad);
+                if (w_nan) atomicAdd(b.stats + MRS_STAT_NAN_ACTIONS, (unsigned long long)w_nan);
+            }
+        }
+    }
+    // ---- the env's slice of A from the new positions
+    if (A_slice) {
+        __syncthreads();
+        if (valid) tile[tid] = make_float4(st.px, st.py, st.pz, 0.f);
+        __syncthreads();
+        float* out = A_slice + (size_t)env0 * N;
+        if ((N & 3) == 0) {
+            const int qpr = N >> 2;                     // quads per row
+            for (int q = tid; q < N * qpr; q += blockDim.x) {
+                const int i = q / qpr, j = (q - i * qpr) * 4;
+                const float4 pi = tile[i];
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 pj = tile[j + u];
+                    v[u] = (j + u == i) ? 0.f : (d.comm_inf ? 1.f : adjacency_pair(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, d.s_max));
+                }
+                __stcs(reinterpret_cast<float4*>(out + (size_t)i * N + j), make_float4(v[0], v[1], v[2], v[3]));
+            }
+        } else {
+            for (int q = tid; q < N * N; q += blockDim.x) {
+                const int i = q / N, j = q - i * N;
+                const float4 pi = tile[i], pj = tile[j];
+                out[q] = (j == i) ? 0.f : (d.comm_inf ? 1.f : adjacency_pair(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, d.s_max));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ pair pass for N > 128
 // n-body tiling.  A CTA owns 128 agents of one env (one per thread, own position in registers) and one
 // of `nsplit` slices of the partner range; partner positions go through shared memory in tiles of 128
@@ -1295,6 +1448,23 @@ static int launch_mid(const MrsConfig& c, const Derived& d, const MrsBuffers& b,
     return last_error();
 }
 
+// 32 < N <= 128, many envs: one fused launch per step (step_env_kernel)
+template <int MODE>
+static int launch_env_fused(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
+    const size_t S = (size_t)c.E * c.N;
+    constexpr int A = ModeTraits<MODE>::A;
+    const unsigned threads = (unsigned)((c.N + 31) / 32 * 32);
+    const size_t smem = contact_env_smem((int)threads);
+    for (int t = 0; t < a.T; ++t) {
+        const float* act_t = a.actions ? a.actions + (size_t)t * S * A : nullptr;
+        float* A_slice = b.A_tape ? b.A_tape + (size_t)(a.slot_a - t) * S * c.N : nullptr;
+        if (int rc = launch_pdl(true, step_env_kernel<MODE>, dim3((unsigned)c.E), threads, smem, st, c, d, b, act_t, a.slot_x - t,
+                                A_slice))
+            return rc;
+    }
+    return last_error();
+}
+
 template <int MODE>
 static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& b, const StepArgs& a, cudaStream_t st) {
     if (!b.scratch) return MRS_ERR_ARG;
@@ -1302,7 +1472,9 @@ static int launch_tiled(const MrsConfig& c, const Derived& d, const MrsBuffers& 
     // lanes-per-agent kernels fill the GPU with few agents (latency); thread-per-agent kernels do a quarter of
     // the work once there are enough of them
     static const long long mid_min = env_int("MRS_B200_MID_MIN_AGENTS", 32768);
-    if (c.N <= 128 && (long long)c.E * c.N >= mid_min) return launch_mid<MODE>(c, d, b, a, st);
+    const int fused_mid = env_int("MRS_B200_FUSED_MID", 1);       // 0: the three-kernel path (A/B runs, parity test)
+    if (c.N <= 128 && (long long)c.E * c.N >= mid_min)
+        return fused_mid ? launch_env_fused<MODE>(c, d, b, a, st) : launch_mid<MODE>(c, d, b, a, st);
     if (c.N <= 128) return launch_wide_lpa<MODE, 8>(c, d, b, a, st);
     return launch_wide_lpa<MODE, 128>(c, d, b, a, st);     // n-body tiles (pair_tile_kernel) + agent_pre_kernel
 }

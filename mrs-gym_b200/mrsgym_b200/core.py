@@ -284,12 +284,15 @@ class Swarm:
     def _step_launches(self, n=1, fused=False):
         """Kernels the library launches for n steps (bench: gpu_launches).  N <= 32: one fused kernel per step
         (per call when `fused`: mrs_step_many), plus one for a ragged last warp-chunk when N is 8, 16 or 32 and E
-        is not a multiple of 32 / N.  N > 32: pre (+ per-agent kernel for N > 128), post, adjacency per step."""
+        is not a multiple of 32 / N.  N > 32: pre (+ per-agent kernel for N > 128), per-env contact, post, adjacency per
+        step; 32 < N <= 128 with >= 32768 agents: one fused launch per step."""
         if self.N <= 32:
             gpw = 32 // self.N if self.N in (8, 16, 32) else 0
             per = 1 + (1 if gpw and self.E % gpw and self.E >= gpw else 0)
             return per if fused else per * n
-        return n * ((3 if self.N > 128 else 2) + (1 if self.A_tape is not None else 0))
+        if self.N <= 128 and self.S >= 32768:
+            return n                     # one CTA per env: the whole step incl. the A slice in one launch (step_env_kernel)
+        return n * ((3 if self.N > 128 else 2) + (1 if self.N > 1 else 0) + (1 if self.A_tape is not None else 0))
 
     def step(self, actions):
         """One env.step for all envs.  actions: device float32 [E,N,A] contiguous, or None."""

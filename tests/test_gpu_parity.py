@@ -711,6 +711,44 @@ def test_capture_rollout_leaves_the_swarm_untouched():
     assert a.read_stats() == b.read_stats()
 
 
+@pytest.mark.parametrize('E,N,mode,spacing', [(512, 64, 'set_target_vel', 0.55), (328, 100, 'set_control', 0.8),
+                                              (1000, 33, 'set_speeds', 0.55), (256, 128, 'set_target_pos', 2.0)])
+def test_fused_env_kernel_equals_the_three_kernel_path(E, N, mode, spacing, monkeypatch):
+    """32 < N <= 128 with >= 32768 agents: step_env_kernel (one CTA per env, one launch per step) against the
+    pre / contact / post / adjacency kernels it replaces (MRS_B200_FUSED_MID=0) -- state, controller state, rpm
+    mirror, X and A windows and the statistics bit for bit over several steps (set_control: to float32 rounding), in
+    contact (0.55 m), in sparse contact (0.8 m) and in free flight (2 m), with a NaN action on the way."""
+    import mrsgym_b200 as M
+    rng = np.random.default_rng(77 + N)
+    st = H.random_state(rng, E, N, spacing=spacing, jitter=0.05, z0=0.6 if spacing < 1 else 2.0)
+    T = 4
+    act = _dev(H.random_actions(rng, mode, T, E, N, start_pos=st['pos']))
+    act[2, 3, 5, 0] = float('nan')
+    out = []
+    for fused in ('1', '0'):
+        monkeypatch.setenv('MRS_B200_FUSED_MID', fused)
+        sw = M.Swarm(E, N, 2, mode, M._abi.X_FULL, 1.5, keep_rpm=True)
+        H.upload_state(sw, st)
+        sw.reset_windows()
+        for t in range(T):
+            sw.step(act[t])
+        out.append((sw.state.clone(), sw.ctrl.clone().view(torch.int32), sw.rpm.clone(), sw.X_window().clone(),
+                    sw.A_window().clone(), sw.read_stats(), sw.read_status()))
+    a, b = out
+    if mode == 'set_control':
+        # the mixer's NNLS branch is inlined into two different kernels and contracted into FMAs differently: equal to
+        # float32 rounding, not to the bit
+        for x, y in zip(a[:4], b[:4]):
+            x, y = (t.view(torch.float32).nan_to_num(nan=-7.0) for t in (x, y))
+            assert float((x - y).abs().max()) <= 2e-6 * max(1.0, float(y.abs().max())), float((x - y).abs().max())
+        assert torch.equal(a[4], b[4])
+    else:
+        for x, y in zip(a[:5], b[:5]):
+            assert torch.equal(x, y)
+    assert a[5] == b[5] and a[6] == b[6] == M._abi.STATUS_NAN_ACTION
+    assert a[5]['nan_actions'] == 1 and (spacing > 1 or a[5]['agent_contact_rows'] > 0)
+
+
 @pytest.mark.parametrize('E,N,mode', [(512, 64, 'set_target_vel'), (400, 100, 'set_control'), (1000, 33, 'set_speeds'),
                                       (260, 128, 'set_target_pos')])
 def test_thread_per_agent_mid_path(E, N, mode):
