@@ -18,7 +18,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_group -s 4 -c 2 -f -o $O/ev_full_cold python tools/prof_c5.py > $O/ev_full_cold.log 2>&1
 timeout 600 ncu --set full --cache-control none --clock-control none --import-source on -k regex:step_group -s 3 -c 4 -f -o $O/ev_full_warm python tools/prof_c5.py > $O/ev_full_warm.log 2>&1
 timeout 300 python tools/latency_c1.py > $O/ev_latency.txt 2>&1
-timeout 600 python tools/soak.py c5 3000 > $O/ev_soak.txt 2>&1
+timeout 600 python tools/soak.py c5 2000 > $O/ev_soak.txt 2>&1
 tail -3 $O/ev.err
 tail -2 $O/ev_soak.txt
 ls -la $O/ev_* | awk '{print $5, $9}'
