@@ -42,6 +42,7 @@ for _p in (_REPO, os.path.join(_REPO, 'mrs-gym_b200'), os.path.join(_REPO, 'test
 
 HOVER = 14475.809
 
+CPU_REPS = 24        # rollouts per process of the cpu_baseline leg (see cpu_sample_sizes)
 WORKLOADS = {
     # name: E (per GPU), N, mode, K, comm_range, spacing, z0, algorithmic bytes / agent-step
     'c5': dict(E=65536, N=8, mode='set_speeds', K=3, R=2.0, spacing=1.0, z0=2.5, B=176,
@@ -108,29 +109,35 @@ def make_inputs(w, E, T, seed):
 
 # ------------------------------------------------------------------------------ CPU arm (oracle port)
 def _cpu_worker(args):
-    wname, E, T, seed, W = args
+    """`reps` rollouts of a cache-sized batch (E envs), each W untimed warm-up steps then T timed steps: the sum of the
+    timed stretches.  Every rollout starts from a fresh start state, so all of them cover the same stretch of the
+    trajectory as the GPU's timed region."""
+    wname, E, T, seed, W, reps = args
     os.environ.setdefault('OMP_NUM_THREADS', '1')
     import numpy as np
     import helpers as H
     w = WORKLOADS[wname]
-    st, act = make_inputs(w, E, T + W, seed)
-    env = H.make_spec(E, w['N'], w['mode'], w['K'], w['R'], st)
-    for t in range(W):                     # untimed warm-up steps (imports, scipy caches)
-        env.step(act[t])
-    t0 = time.perf_counter()
-    for t in range(T):
-        env.step(act[W + t])
-    return time.perf_counter() - t0
+    spent = 0.0
+    for r in range(reps):
+        st, act = make_inputs(w, E, T + W, seed + 1000 * r)
+        env = H.make_spec(E, w['N'], w['mode'], w['K'], w['R'], st)
+        for t in range(W):                     # untimed warm-up steps (imports, scipy caches)
+            env.step(act[t])
+        t0 = time.perf_counter()
+        for t in range(T):
+            env.step(act[W + t])
+        spent += time.perf_counter() - t0
+    return spent
 
 
-def cpu_port_throughput(wname, procs, E_per_proc, T, seed=4321, warmup=1):
-    """agent-steps/s of the oracle port on `procs` host processes (slowest worker's wall time)."""
+def cpu_port_throughput(wname, procs, E_per_proc, T, seed=4321, warmup=1, reps=1):
+    """agent-steps/s of the oracle port on `procs` host processes (slowest worker's timed seconds)."""
     w = WORKLOADS[wname]
     ctx = mp.get_context('spawn')
     t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        walls = pool.map(_cpu_worker, [(wname, E_per_proc, T, seed + i, max(1, warmup)) for i in range(procs)])
-    total = procs * E_per_proc * w['N'] * T
+        walls = pool.map(_cpu_worker, [(wname, E_per_proc, T, seed + i, max(1, warmup), reps) for i in range(procs)])
+    total = procs * E_per_proc * w['N'] * T * reps
     return total / max(walls), max(walls), time.perf_counter() - t0
 
 
@@ -186,7 +193,11 @@ def cpu_sample_sizes(wname):
     w = WORKLOADS[wname]
     if w['N'] >= 1024:
         return 1, 2          # one env of 4096 agents: ~N^2 pair arrays in numpy
-    return max(1, 4096 // w['N']), 800          # ~10 s of CPU work per process (oracle port: ~4.5e5 agent-steps/s/core)
+    # a cache-sized batch per process (4096 agents), 40 steps per rollout: the SAME stretch of the rollout as the
+    # GPU's timed region -- the first steps, before the synthetic swarm collapses (the oracle's sequential-impulse
+    # solver in numpy is an order of magnitude slower per step once every agent is in contact).  cpu_baseline
+    # repeats such rollouts (CPU_REPS) to reach ~10 s of CPU work per process at ~5e5 agent-steps/s/core.
+    return max(1, 4096 // w['N']), 40
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -538,10 +549,12 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu:
         procs = min(os.cpu_count() or 1, 64)
         Ep, Tc = cpu_sample_sizes(args.workload)
-        v, wall, total = cpu_port_throughput(args.workload, procs, Ep, Tc)
+        reps = 1 if w['N'] >= 1024 else (4 if w['spacing'] < 0.75 else CPU_REPS)
+        v, wall, total = cpu_port_throughput(args.workload, procs, Ep, Tc, warmup=max(args.warmup, 3), reps=reps)
         out['cpu_baseline'] = {'value': v, 'unit': 'agent-steps/s', 'cores': procs, 'kind': 'port',
-                               'sample': '%d processes x %d envs x %d agents x %d steps of the same workload '
-                                         '(oracle/spec.py, numpy float64); %.1f s' % (procs, Ep, w['N'], Tc, total)}
+                               'sample': '%d processes x %d rollouts x %d envs x %d agents x %d steps (after %d warm-up '
+                                         'steps each) of the same workload (oracle/spec.py, numpy float64); %.1f s'
+                                         % (procs, reps, Ep, w['N'], Tc, max(args.warmup, 3), total)}
         verb = cpu_verbatim_throughput(args.workload, procs)
         if verb is not None:
             out['cpu_baseline_verbatim'] = verb
