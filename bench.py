@@ -508,7 +508,14 @@ def run_gpu(args):
         tj = json.load(open(tp))
         if tj.get('kernel_sources_sha256') == kernel_sources_hash():
             traffic = tj.get(args.workload)
-    kernel = 'step_group_kernel<%s>' % w['mode'] if N <= 32 else 'step_pre/step_post/adjacency_tiled'
+    if N <= 32:
+        kernel = 'step_group_kernel<%s>' % w['mode']
+    elif N <= 128 and E * N >= 32768:
+        kernel = 'step_env_kernel<%s> (one CTA per env, the whole step)' % w['mode']
+    elif N <= 128:
+        kernel = 'step_pre_kernel + contact_env_kernel + step_post_kernel + adjacency kernel (the step = their sum)'
+    else:
+        kernel = 'pair_tile_kernel + agent_pre_kernel + contact_env_kernel + step_post_kernel + adjacency_tiled_kernel (the step = their sum)'
     out = {
         'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': steps,
         'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling,
