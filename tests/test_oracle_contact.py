@@ -101,3 +101,57 @@ def test_heap_spreads_and_rests():
     assert d.min() > 0.6 - 1e-3
     assert np.abs(pos - snap['p']).max() < 1e-3          # 120 steps after settling: within a millimetre
     assert np.abs(v).max() < 1e-4
+
+
+def _levels(pairs, rounds, n_agents):
+    """csrc/mrs_contact_env.cuh: the relaxation that turns tournament rounds into dependency levels -- per-agent pair
+    lists sorted by round, level[k] >= 1 + level[previous pair of either agent], iterated to the fixed point."""
+    inc = [[] for _ in range(n_agents)]
+    for k, (i, j) in enumerate(pairs):
+        inc[i].append(k)
+        inc[j].append(k)
+    for lst in inc:
+        lst.sort(key=lambda k: rounds[k])
+    level = [1] * len(pairs)
+    changed = True
+    while changed:
+        changed = False
+        for lst in inc:
+            run = 0
+            for k in lst:
+                lv = max(level[k], run + 1)
+                if lv > level[k]:
+                    level[k] = lv
+                    changed = True
+                run = lv
+    return level
+
+
+def test_level_schedule_of_the_per_env_solver_equals_the_round_order():
+    """The per-env contact kernel (N > 32) walks dependency levels instead of tournament rounds.  Pairs of one level
+    must touch disjoint agents, pairs that share an agent must keep their round order, and a non-commutative update
+    applied level by level must give exactly what the round-by-round walk gives."""
+    rng = np.random.default_rng(12)
+    for N, p in ((40, 0.08), (64, 0.05), (129, 0.02), (200, 0.03), (33, 0.5)):
+        pairs = [(i, j) for i in range(N) for j in range(i + 1, N) if rng.random() < p]
+        rounds = [_round_formula(i, j, N) for i, j in pairs]
+        level = _levels(pairs, rounds, N)
+        for lv in set(level):
+            touched = [a for k, pr in enumerate(pairs) if level[k] == lv for a in pr]
+            assert len(touched) == len(set(touched))                   # a level is a matching
+        for a in range(N):
+            mine = sorted((rounds[k], level[k]) for k, pr in enumerate(pairs) if a in pr)
+            assert all(x[1] < y[1] for x, y in zip(mine, mine[1:]))     # round order kept along every agent
+        assert max(level, default=0) <= max(len(set(rounds)), 1)       # never more barriers than occupied rounds
+
+        def walk(order):
+            v = np.arange(1.0, N + 1.0)
+            for k in order:
+                i, j = pairs[k]
+                d = 0.37 * (v[i] - v[j]) + 0.001 * v[i] * v[j]          # order-sensitive, like a Gauss-Seidel row
+                v[i] -= d
+                v[j] += 0.5 * d
+            return v
+        by_round = sorted(range(len(pairs)), key=lambda k: (rounds[k], k))
+        by_level = sorted(range(len(pairs)), key=lambda k: (level[k], -k))
+        assert np.array_equal(walk(by_round), walk(by_level))
