@@ -84,3 +84,35 @@ def rollout(env, policy, T, episode_length=None, record=('X', 'A', 'action', 're
             X = env.reset(env_mask=done_e)
             A = env.refresh_A(done_e)
     return data
+
+
+def to_trainer_history(data, envs=None):
+    """The batched dataset of rollout() in the layout of the reference's replay store, `Trainer.history`
+    (examples/simulating_data/helper/Trainer.py:89-108: parallel lists `X` (N, D), `A` (N, N), `expert` (N, ACTION_DIM),
+    `done`, `context`, one entry per time step, episodes back to back).  The envs of the batch are laid end to end;
+    the last recorded step of every env is marked `done` (as Trainer.save_trainer does for the last entry, :44-45), so
+    that a K-step window (`Trainer.get_state`, :112-125) never straddles two envs.  The result can be handed to
+    `Trainer.load_trainer_dict({'history': ...})` or saved with torch.save; tensors are moved to the CPU like the
+    reference's `.cpu()` calls in DataGenerator.py:41."""
+    X, A = data['X'], data['A']
+    T, E = X.shape[0], X.shape[1]
+    envs = range(E) if envs is None else envs
+    done = data['done'] if 'done' in data else torch.zeros(T, E, dtype=torch.bool)
+    act = data.get('action')
+    Xc, Ac, dc = X.cpu(), A.cpu(), done.cpu()
+    ac = act.cpu() if act is not None else None
+    hist = {'done': [], 'A': [], 'X': [], 'context': [], 'expert': []}
+    for e in envs:
+        for t in range(T):
+            hist['X'].append(Xc[t, e])
+            hist['A'].append(Ac[t, e])
+            hist['expert'].append(ac[t, e] if ac is not None else None)
+            hist['context'].append({})
+            hist['done'].append(bool(dc[t, e]) or t == T - 1)
+    return hist
+
+
+def save_dataset(data, path):
+    """torch.save of the dataset dict (device tensors are written as they are; load with map_location as needed)."""
+    with open(path, 'wb') as fp:
+        torch.save(data, fp)

@@ -264,3 +264,33 @@ def test_pin_bullet_runs_on_the_fake_backend():
         json.dump(doc, f)
     P2 = bm.PhysicsParams.from_json(f.name)
     assert P2.solver_iters == 50 and abs(P2.mu_ground - 0.75) < 1e-12
+
+
+def test_rollout_dataset_in_the_reference_trainer_layout(tmp_path):
+    """to_trainer_history: the batched dataset as Trainer.history (helper/Trainer.py:89-108) -- the valid K-step windows
+    that Trainer.update_valid_idxs (:128-138) derives from the `done` list never straddle two envs or two episodes."""
+    import mrsgym_b200 as M
+    T, E, N, D, K = 7, 3, 4, 6, 2
+    g = torch.Generator().manual_seed(3)
+    data = {'X': torch.randn(T, E, N, D, generator=g), 'A': (torch.rand(T, E, N, N, generator=g) < 0.5).float(),
+            'action': torch.randn(T, E, N, 3, generator=g), 'done': torch.zeros(T, E, dtype=torch.bool)}
+    data['done'][3, 1] = True                           # env 1 ends an episode after step 3
+    h = M.to_trainer_history(data)
+    assert len(h['X']) == len(h['A']) == len(h['expert']) == len(h['done']) == len(h['context']) == T * E
+    assert h['X'][T + 4].shape == (N, D) and torch.equal(h['X'][T + 4], data['X'][4, 1])
+    assert torch.equal(h['A'][2 * T + 6], data['A'][6, 2]) and torch.equal(h['expert'][0], data['action'][0, 0])
+    assert [i for i, d in enumerate(h['done']) if d] == [T - 1, T + 3, 2 * T - 1, 3 * T - 1]
+    # the reference's window bookkeeping, restated: an entry is a valid window end when K earlier entries of the same
+    # episode precede it
+    valid, since = [], -1
+    for idx, d in enumerate(h['done']):
+        since = -1 if d else since + 1
+        if since >= K:
+            valid.append(idx)
+    for idx in valid:
+        env = idx // T
+        assert all((idx - k) // T == env for k in range(K + 1))
+        assert not any(h['done'][idx - k] for k in range(K + 1))
+    M.save_dataset(data, str(tmp_path / 'd.pt'))
+    back = torch.load(str(tmp_path / 'd.pt'))
+    assert all(torch.equal(back[k], data[k]) for k in data)
